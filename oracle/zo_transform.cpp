@@ -1,0 +1,182 @@
+// zo_transform.cpp -- CPU oracle for Image.rotate / rotateInto / rotateBounds / warp.
+// TEST INFRASTRUCTURE ONLY (see zignal_oracle.h).  Restates image/transforms.zig:112-149
+// (rotateBounds), :163-212 (rotateInto), :385-462 (rotate0/90/180/270), :522-531 (warp),
+// image.zig:200-229 (setBorder), :322-327 (getCenter), geometry/transforms.zig:39-42, :147-150,
+// :224-231 (project) and matrix/SMatrix.zig:530-560 (the scalar gemm tail project() runs through).
+#include "zo_sample.h"
+
+namespace zo {
+
+static const float TAU_F = 6.283185307179586f;   // std.math.tau coerced to f32
+static const float PI_F = 3.141592653589793f;
+
+// Zig's float @mod lowers to: a = frem(l, r); if (l < 0) frem(a + r, r) else a  (result has r's sign).
+static inline float zig_mod_f32(float l, float r) {
+    const float a = std::fmod(l, r);
+    if (l < 0) return std::fmod(a + r, r);
+    return a;
+}
+
+// transforms.zig:114-136 / :165-187: which orthogonal fast path (if any) `angle` selects.
+static int rotate_class(float angle) {
+    const float n = zig_mod_f32(angle, TAU_F);
+    const float eps = 1e-6f;
+    if (std::fabs(n) < eps || std::fabs(n - TAU_F) < eps) return 1;
+    if (std::fabs(n - PI_F / 2.0f) < eps) return 2;
+    if (std::fabs(n - PI_F) < eps) return 3;
+    if (std::fabs(n - 3.0f * PI_F / 2.0f) < eps) return 4;
+    return 0;
+}
+
+// image.zig:200-229 setBorder(rect, zero) with rect = (l, t, r, b) clipped to the image
+template <typename PX>
+static void set_border_zero(const Img<typename PX::T>& out, uint32_t l, uint32_t t, uint32_t r, uint32_t b) {
+    const uint32_t il = std::min(l, out.cols), ir = std::min(r, out.cols), it = std::min(t, out.rows), ib = std::min(b, out.rows);
+    if (il >= ir || it >= ib) {  // no intersection -> fill
+        for (uint32_t y = 0; y < out.rows; ++y)
+            for (uint32_t x = 0; x < out.cols; ++x) out.at(y, x) = PX::zero();
+        return;
+    }
+    for (uint32_t y = 0; y < out.rows; ++y)
+        for (uint32_t x = 0; x < out.cols; ++x)
+            if (y < it || y >= ib || x < il || x >= ir) out.at(y, x) = PX::zero();
+}
+
+// transforms.zig:385-462.  kind: 1 = 0deg, 2 = 90 CCW, 3 = 180, 4 = 270 CCW.
+template <typename PX>
+static void rotate_orthogonal(const Img<typename PX::T>& self, const Img<typename PX::T>& out, int kind) {
+    const bool swap = (kind == 2 || kind == 4);
+    const uint32_t content_rows = swap ? self.cols : self.rows;
+    const uint32_t content_cols = swap ? self.rows : self.cols;
+    const uint32_t offset_r = (out.rows > content_rows ? out.rows - content_rows : 0) / 2;  // -| then /2
+    const uint32_t offset_c = (out.cols > content_cols ? out.cols - content_cols : 0) / 2;
+    for (uint32_t r = 0; r < self.rows; ++r)
+        for (uint32_t c = 0; c < self.cols; ++c) {
+            size_t new_r, new_c;
+            switch (kind) {
+                case 1: new_r = r; new_c = c; break;
+                case 2: new_r = self.cols - 1 - c; new_c = r; break;
+                case 3: new_r = self.rows - 1 - r; new_c = self.cols - 1 - c; break;
+                default: new_r = c; new_c = self.rows - 1 - r; break;
+            }
+            new_r += offset_r;
+            new_c += offset_c;
+            if (new_r < out.rows && new_c < out.cols) out.at(new_r, new_c) = self.at(r, c);
+        }
+    if (offset_r != 0 || offset_c != 0) set_border_zero<PX>(out, offset_c, offset_r, offset_c + content_cols, offset_r + content_rows);
+}
+
+// transforms.zig:163-212
+template <typename PX>
+static void rotate_into(const zo_image* src, zo_image* dst, float angle, float cos_a, float sin_a, int method, float mb,
+                        float mc, int border) {
+    using T = typename PX::T;
+    Img<T> self(src), out(dst);
+    const int cls = rotate_class(angle);
+    if (cls != 0) { rotate_orthogonal<PX>(self, out, cls); return; }
+    const float cx = (float)self.cols / 2.0f, cy = (float)self.rows / 2.0f;  // image.zig:322-327
+    const float offset_x = ((float)out.cols - (float)self.cols) / 2.0f;
+    const float offset_y = ((float)out.rows - (float)self.rows) / 2.0f;
+    const float rcx = cx + offset_x, rcy = cy + offset_y;
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (g_threads > 1)
+    for (uint32_t r = 0; r < out.rows; ++r) {
+        const float y = (float)r;
+        for (uint32_t c = 0; c < out.cols; ++c) {
+            const float x = (float)c;
+            const float dx = x - rcx;
+            const float dy = y - rcy;
+            const float rotated_dx = cos_a * dx - sin_a * dy;
+            const float rotated_dy = sin_a * dx + cos_a * dy;
+            const float src_x = rotated_dx + cx;
+            const float src_y = rotated_dy + cy;
+            T val;
+            if (!interpolate<PX>(self, src_x, src_y, method, mb, mc, border, &val)) val = PX::zero();
+            out.at(r, c) = val;
+        }
+    }
+}
+
+// geometry/transforms.zig:39-42 / :147-150: matrix.dot(src).add(bias); SMatrix.gemm scalar tail
+// (SMatrix.zig:554-560): acc = 0; acc += a_ik*b_k ...; result = 0 + 1*acc.
+static inline void project_affine(const float* m, float x, float y, float* ox, float* oy) {
+    float a0 = 0; a0 += m[0] * x; a0 += m[1] * y; a0 = 0.0f + 1.0f * a0;
+    float a1 = 0; a1 += m[2] * x; a1 += m[3] * y; a1 = 0.0f + 1.0f * a1;
+    *ox = a0 + m[4];
+    *oy = a1 + m[5];
+}
+// geometry/transforms.zig:224-231
+static inline void project_projective(const float* m, float x, float y, float* ox, float* oy) {
+    float d[3];
+    for (int i = 0; i < 3; ++i) {
+        float a = 0; a += m[3 * i + 0] * x; a += m[3 * i + 1] * y; a += m[3 * i + 2] * 1.0f;
+        d[i] = 0.0f + 1.0f * a;
+    }
+    if (d[2] != 0) {
+        const float s = 1 / d[2];
+        d[0] = d[0] * s; d[1] = d[1] * s;  // SMatrix.scale
+    }
+    *ox = d[0];
+    *oy = d[1];
+}
+
+// transforms.zig:522-531
+template <typename PX>
+static void warp(const zo_image* src, zo_image* dst, int kind, const float* m, int method, float mb, float mc) {
+    using T = typename PX::T;
+    Img<T> self(src), out(dst);
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (g_threads > 1)
+    for (uint32_t r = 0; r < out.rows; ++r)
+        for (uint32_t c = 0; c < out.cols; ++c) {
+            float sx, sy;
+            if (kind == ZO_XFORM_PROJECTIVE) project_projective(m, (float)c, (float)r, &sx, &sy);
+            else project_affine(m, (float)c, (float)r, &sx, &sy);
+            T val;
+            if (!interpolate<PX>(self, sx, sy, method, mb, mc, ZO_BORDER_MIRROR, &val)) val = PX::zero();
+            out.at(r, c) = val;
+        }
+}
+
+}  // namespace zo
+
+extern "C" {
+
+int zo_rotate_class(float angle) { return zo::rotate_class(angle); }
+
+void zo_rotate_bounds(uint32_t rows, uint32_t cols, float angle, uint32_t* out_rows, uint32_t* out_cols) {
+    const int cls = zo::rotate_class(angle);
+    if (cls == 1 || cls == 3) { *out_rows = rows; *out_cols = cols; return; }
+    if (cls == 2 || cls == 4) { *out_rows = cols; *out_cols = rows; return; }
+    const float cos_abs = std::fabs(std::cos(angle)), sin_abs = std::fabs(std::sin(angle));
+    const float w = (float)cols, h = (float)rows;
+    const float new_w = w * cos_abs + h * sin_abs;
+    const float new_h = h * cos_abs + w * sin_abs;
+    *out_cols = (uint32_t)std::ceil(new_w);
+    *out_rows = (uint32_t)std::ceil(new_h);
+}
+
+int zo_rotate_into(const zo_image* src, zo_image* dst, int pixfmt, float angle, float cos_a, float sin_a, int method,
+                   float mb, float mc, int border) {
+    using namespace zo;
+    switch (pixfmt) {
+        case ZO_PIX_U8: rotate_into<PxU8>(src, dst, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_F32: rotate_into<PxF32>(src, dst, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGB8: rotate_into<PxRgb8>(src, dst, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGBA8: rotate_into<PxRgba8>(src, dst, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGBAF32: rotate_into<PxRgbaF32>(src, dst, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+    }
+    return ZO_ERR_UNSUPPORTED;
+}
+
+int zo_warp(const zo_image* src, zo_image* dst, int pixfmt, int kind, const float* m, int method, float mb, float mc) {
+    using namespace zo;
+    switch (pixfmt) {
+        case ZO_PIX_U8: warp<PxU8>(src, dst, kind, m, method, mb, mc); return ZO_OK;
+        case ZO_PIX_F32: warp<PxF32>(src, dst, kind, m, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGB8: warp<PxRgb8>(src, dst, kind, m, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGBA8: warp<PxRgba8>(src, dst, kind, m, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGBAF32: warp<PxRgbaF32>(src, dst, kind, m, method, mb, mc); return ZO_OK;
+    }
+    return ZO_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,508 @@
+"""Known-answer tests that pin the CPU oracle to the facts the reference's own tests hold for the hot
+path.  Each test cites the reference test it ports (paths under /root/reference/src/).
+CPU only; the oracle is test infrastructure (oracle/zignal_oracle.h)."""
+import numpy as np
+import pytest
+
+import oracle_lib as zo
+
+
+# --------------------------------------------------------------------------------------- border.zig:65-139
+def test_resolve_index_basic():
+    for b in ("zero", "replicate", "mirror", "wrap"):
+        assert zo.resolve_index(5, 10, b) == 5
+        assert zo.resolve_index(0, 0, b) is None
+
+
+def test_resolve_index_zero():
+    for i in (-1, -5, 10, 15):
+        assert zo.resolve_index(i, 10, "zero") is None
+
+
+def test_resolve_index_replicate():
+    assert zo.resolve_index(-1, 10, "replicate") == 0
+    assert zo.resolve_index(-5, 10, "replicate") == 0
+    assert zo.resolve_index(10, 10, "replicate") == 9
+    assert zo.resolve_index(15, 10, "replicate") == 9
+
+
+def test_resolve_index_mirror():
+    assert zo.resolve_index(-1, 5, "mirror") == 1
+    assert zo.resolve_index(-2, 5, "mirror") == 2
+    assert zo.resolve_index(5, 5, "mirror") == 3
+    assert zo.resolve_index(6, 5, "mirror") == 2
+    assert zo.resolve_index(-1, 1, "mirror") == 0
+    assert zo.resolve_index(5, 1, "mirror") == 0
+
+
+def test_resolve_index_wrap():
+    assert zo.resolve_index(-1, 5, "wrap") == 4
+    assert zo.resolve_index(-6, 5, "wrap") == 4
+    assert zo.resolve_index(5, 5, "wrap") == 0
+    assert zo.resolve_index(6, 5, "wrap") == 1
+
+
+# --------------------------------------------------------------------------------------- meta.zig:229-249
+def test_meta_clamp_rounding():
+    L = zo.lib()
+    assert L.zo_clamp_u8_f32(-5.0) == 0
+    assert L.zo_clamp_u8_f32(300.0) == 255
+    assert L.zo_clamp_u8_f32(0.5) == 1      # half away from zero
+    assert L.zo_clamp_u8_f32(1.5) == 2
+    assert L.zo_clamp_u8_f32(2.5) == 3
+    assert L.zo_clamp_u8_f32(254.49) == 254
+    # divClampU8 (convolution.zig:18-22): symmetric rounding
+    assert L.zo_div_clamp_u8(128, 256) == 1
+    assert L.zo_div_clamp_u8(127, 256) == 0
+    assert L.zo_div_clamp_u8(-128, 256) == 0
+    assert L.zo_div_clamp_u8(255 * 256, 256) == 255
+    assert L.zo_div_clamp_u8(10 ** 9, 256) == 255
+
+
+# --------------------------------------------------------------------------------------- tests/integral.zig
+def test_integral_all_ones_scalar():  # :11-28
+    img = np.ones((21, 13), np.uint8)
+    sat = zo.integral_plane(img)
+    r, c = np.mgrid[0:21, 0:13]
+    assert np.array_equal(sat, ((r + 1) * (c + 1)).astype(np.float32))
+
+
+def test_integral_all_ones_view():  # :30-47
+    img = np.ones((21, 13), np.uint8)
+    view = img[3:10, 2:8]
+    sat = zo.integral_plane(view)
+    r, c = np.mgrid[0:7, 0:6]
+    assert np.array_equal(sat, ((r + 1) * (c + 1)).astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------- tests/filters.zig
+def test_box_blur_uniform():  # :87-103
+    img = np.full((5, 5), 128, np.uint8)
+    assert np.all(zo.box_blur(img, 1) == 128)
+
+
+def test_box_blur_radius0_views():  # :50-75, :105-126
+    base = np.arange(36, dtype=np.uint8).reshape(6, 6)
+    view = base[1:5, 1:5]
+    out = zo.box_blur(view, 0, out=np.zeros((4, 4), np.uint8))
+    assert np.array_equal(out, view)
+
+
+def test_box_blur_border_effects():  # :128-154
+    img = np.zeros((5, 5), np.uint8)
+    img[2, 2] = 255
+    out = zo.box_blur(img, 1)
+    assert out[0, 0] < out[2, 2] < 255
+    assert out[2, 2] == 28  # 255/9 = 28.33 -> 28
+
+
+def test_box_blur_border_area():  # :186-207: every border pixel of a uniform image keeps its value
+    img = np.full((12, 12), 200, np.uint8)
+    assert np.all(zo.box_blur(img, 3) == 200)
+
+
+@pytest.mark.parametrize("size", [8, 32])
+@pytest.mark.parametrize("radius", [1, 3])
+def test_box_blur_rgba_alpha_preserved(size, radius):  # :234-264
+    rng = np.random.default_rng(size * 10 + radius)
+    img = rng.integers(0, 256, (size, size, 4), dtype=np.uint8)
+    img[..., 3] = 255
+    out = zo.box_blur(img, radius)
+    assert np.all(out[..., 3] == 255)
+
+
+def test_sharpen_uniform():  # :327-343
+    img = np.full((5, 5), 100, np.uint8)
+    assert np.all(zo.sharpen(img, 1) == 100)
+
+
+def test_convolve_identity():  # :370-398, :662-699
+    rng = np.random.default_rng(1)
+    ident = np.zeros((3, 3), np.float32)
+    ident[1, 1] = 1
+    for shape in [(5, 5), (7, 9, 3), (6, 8, 4)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(zo.convolve(img, ident, "zero"), img)
+    imgf = rng.random((9, 11), dtype=np.float32)
+    assert np.array_equal(zo.convolve(imgf, ident, "mirror"), imgf)
+
+
+def test_convolve_identity_into_view_sentinels():  # :701-744
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 256, (4, 4), dtype=np.uint8)
+    big = np.full((8, 8), 0xAA, np.uint8)
+    ident = np.zeros((3, 3), np.float32)
+    ident[1, 1] = 1
+    zo.convolve(src, ident, "zero", out=big[2:6, 2:6])
+    assert np.array_equal(big[2:6, 2:6], src)
+    mask = np.ones((8, 8), bool)
+    mask[2:6, 2:6] = False
+    assert np.all(big[mask] == 0xAA)
+
+
+def test_convolve_zero_corner_white_rgb():  # :571-600
+    img = np.full((5, 5, 3), 255, np.uint8)
+    k = np.full((3, 3), 1.0 / 9.0, np.float32)
+    out = zo.convolve(img, k, "zero")
+    assert out[0, 0, 0] != 255
+    assert abs(int(out[0, 0, 0]) - 113) <= 1
+    # Q8 fixed point: round(256/9) = 28; 4 taps * 255 * 28 = 28560 -> /256 = 111.56 -> 112
+    assert out[0, 0, 0] == 112
+    assert out[2, 2, 0] == zo.lib().zo_div_clamp_u8(9 * 28 * 255, 256)
+
+
+def test_convolve_issue_255():  # :1302-1342
+    img = np.ones((10, 20), np.uint8)
+    k = np.array([[1, 1, 1], [1, 0, 1], [1, 1, 1]], np.float32)
+    out = zo.convolve(img, k, "zero", out=np.full((10, 20), 0xAA, np.uint8))
+    assert np.all(out[1:9, 0] == 5)
+    assert np.all(out[1:9, 1] == 8)
+
+
+def test_convolve_replicate_corner():  # :427-463
+    img = np.zeros((3, 3), np.uint8)
+    img[1, 1] = 255
+    k = np.array([[0.25, 0.25, 0], [0.25, 0.25, 0], [0, 0, 0]], np.float32)
+    assert zo.convolve(img, k, "replicate")[0, 0] == 0
+
+
+def test_separable_identity_view_f32():  # :602-632
+    base = (np.arange(5)[:, None] * 10 + np.arange(5)[None, :]).astype(np.float32)
+    view = base[1:4, 1:4]
+    out = zo.conv_separable(view, [1.0], [1.0], "zero", out=np.zeros((3, 3), np.float32))
+    assert np.array_equal(out, view)
+
+
+def test_separable_identity_view_u8_sentinels():  # :746-783
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (4, 4), dtype=np.uint8)
+    big = np.full((8, 8), 0x55, np.uint8)
+    zo.conv_separable(src, [1.0], [1.0], "zero", out=big[2:6, 2:6])
+    assert np.array_equal(big[2:6, 2:6], src)
+    assert np.count_nonzero(big != 0x55) <= 16
+
+
+def test_separable_impulse():  # :469-491
+    img = np.zeros((7, 7), np.float32)
+    img[3, 3] = 1
+    g = [0.25, 0.5, 0.25]
+    out = zo.conv_separable(img, g, g, "zero")
+    assert out[3, 3] < 1.0 and out[3, 2] > 0 and out[3, 3] > out[3, 2]
+    assert out[3, 3] == np.float32(0.25) and out[3, 2] == np.float32(0.125)
+
+
+def test_gaussian_sigma0_copy_and_negative():  # :1159-1180, image.zig:966-970
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (6, 7), dtype=np.uint8)
+    assert np.array_equal(zo.gaussian_blur(img, 0.0), img)
+    with pytest.raises(ValueError):
+        zo.gaussian_blur(img, -1.0)
+
+
+def test_gaussian_taps_shape():  # image.zig:973-990
+    t = zo.gaussian_taps(2.25)
+    assert t.size == 15
+    assert abs(float(t.sum()) - 1.0) < 1e-6
+    assert np.array_equal(t, t[::-1])
+    assert zo.gaussian_taps(1.0).size == 7
+    assert zo.gaussian_taps(0.5).size == 5
+
+
+def test_gaussian_ordering_property():  # :521-546
+    img = np.zeros((21, 21), np.uint8)
+    img[10, 10] = 255
+    a = zo.gaussian_blur(img, 0.5)
+    b = zo.gaussian_blur(img, 2.0)
+    assert a[10, 10] > b[10, 10]
+    assert b[10, 14] >= a[10, 14]
+
+
+def test_gaussian_rgb_red_square_stays_red():  # :785-815
+    img = np.zeros((20, 20, 3), np.uint8)
+    img[5:15, 5:15, 0] = 255
+    out = zo.gaussian_blur(img, 1.0)
+    assert out[10, 10, 0] > 200 and out[10, 10, 1] == 0 and out[10, 10, 2] == 0
+
+
+def test_uniform_channel_shortcut_equals_full_convolution():  # convolution.zig:363-429 is a pure optimisation
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (12, 17, 4), dtype=np.uint8)
+    img[..., 3] = 200  # uniform alpha -> shortcut path
+    taps = zo.gaussian_taps(1.0)
+    out = zo.conv_separable(img, taps, taps, "mirror")
+    alpha_plane = zo.conv_separable(np.ascontiguousarray(img[..., 3]), taps, taps, "mirror")
+    assert np.array_equal(out[..., 3], alpha_plane)
+
+
+# --------------------------------------------------------------------------------------- tests/interpolation.zig
+def _gradient(rows, cols):
+    r, c = np.mgrid[0:rows, 0:cols]
+    return np.minimum(255, (r + c) * 255 // (rows + cols - 2)).astype(np.uint8)
+
+
+def _checker(rows, cols):
+    r, c = np.mgrid[0:rows, 0:cols]
+    return np.where((r + c) % 2 == 0, 0, 255).astype(np.uint8)
+
+
+def test_nearest_exact_and_rounding():  # :36-70
+    img = _gradient(10, 10)
+    for p in (0, 5, 9):
+        assert zo.interpolate(img, p, p, "nearest") == img[p, p]
+    ch = _checker(10, 10)
+    assert zo.interpolate(ch, 0.4, 0.4, "nearest") == 0
+    assert zo.interpolate(ch, 0.6, 0.6, "nearest") == 0
+    assert zo.interpolate(ch, 1.5, 0.5, "nearest") == 255
+
+
+def test_bilinear_midpoints():  # :72-108
+    img = _gradient(10, 10)
+    assert zo.interpolate(img, 0, 0, "bilinear") == img[0, 0]
+    assert zo.interpolate(img, 5, 5, "bilinear") == img[5, 5]
+    p = np.tile(np.array([0, 100, 200], np.uint8), (3, 1))
+    assert zo.interpolate(p, 0.5, 0, "bilinear") == 50
+    assert zo.interpolate(p, 0.5, 0.5, "bilinear") == 50
+
+
+@pytest.mark.parametrize("method,pts,tol", [("bicubic", (2, 5), 0), ("catmull_rom", (2, 5), 0),
+                                            ("lanczos", (3, 5), 1), ("mitchell", (2, 5), 1)])
+def test_kernel_exact_pixels(method, pts, tol):  # :110-162
+    img = _gradient(10, 10)
+    for p in pts:
+        v = zo.interpolate(img, p, p, method)
+        assert abs(int(v) - int(img[p, p])) <= tol
+
+
+def test_rgb_interpolation():  # :234-268
+    r, c = np.mgrid[0:4, 0:4]
+    img = np.stack([r * 85, c * 85, np.full_like(r, 128)], axis=-1).astype(np.uint8)
+    assert np.array_equal(zo.interpolate(img, 1.6, 1.4, "nearest"), img[1, 2])
+    v = zo.interpolate(img, 0.5, 0.5, "bilinear")
+    assert tuple(v) == (43, 43, 128)
+    assert zo.interpolate(img, 1.5, 1.5, "mitchell") is not None
+
+
+def test_float_bilinear():  # :333-353
+    r, c = np.mgrid[0:4, 0:4]
+    img = (r * 0.25 + c * 0.25).astype(np.float32)
+    assert abs(float(zo.interpolate(img, 1.5, 1.5, "bilinear")) - 0.75) < 1e-3
+    assert zo.interpolate(img, 1.5, 1.5, "bicubic") is not None
+
+
+def test_resize_bilinear_range():  # :270-305
+    img = np.array([[0, 80, 160, 240]] * 4, np.uint8)
+    out = zo.resize(img, (8, 8), "bilinear")
+    assert out.max() <= 240
+
+
+def test_catmull_rom_within_range():  # :307-331
+    r, c = np.mgrid[0:5, 0:5]
+    img = (50 + (r + c) * 20).astype(np.uint8)
+    rr = np.float32(1.5)
+    while rr < 3.5:
+        cc = np.float32(1.5)
+        while cc < 3.5:
+            v = zo.interpolate(img, float(cc), float(rr), "catmull_rom")
+            assert v is not None and 50 <= v <= 200
+            cc = np.float32(cc + np.float32(0.1))
+        rr = np.float32(rr + np.float32(0.1))
+
+
+def test_single_pixel_image():  # :587-601
+    img = np.array([[77]], np.uint8)
+    for m in zo.INTERP:
+        assert zo.interpolate(img, 0.0, 0.0, m) == 77
+
+
+def test_interpolate_rejects_non_finite():  # interpolation.zig:73-75
+    img = _gradient(4, 4)
+    assert zo.interpolate(img, float("nan"), 0.0, "bilinear") is None
+    assert zo.interpolate(img, float("inf"), 0.0, "nearest") is None
+
+
+# --------------------------------------------------------------------------------------- tests/resize.zig:258-298 (shapes are host logic; see test_host_api)
+def test_resize_same_shape_is_copy():
+    img = _gradient(6, 7)
+    assert np.array_equal(zo.resize(img, (6, 7), "lanczos"), img)
+
+
+def test_resize_4to1_bicubic_constant_weights():  # at 4:1, fx = fy = 128 -> [-32,160,160,-32]
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (16, 16, 3), dtype=np.uint8)
+    out = zo.resize(img, (4, 4), "bicubic")
+    w1 = np.array([-32, 160, 160, -32], np.int64)
+    w = (np.outer(w1, w1) / 256).astype(np.int64)  # exact: all products divisible by 256
+    assert w.sum() == 256
+    blk = img[4:8, 4:8, 1].astype(np.int64)
+    s = int((blk * w).sum())
+    expect = int(np.clip(int(s / 256) if s >= 0 else -int(-s / 256), 0, 255))
+    assert out[1, 1, 1] == expect
+
+
+# --------------------------------------------------------------------------------------- tests/transforms.zig
+def test_rotate_orthogonal_shapes_and_content():  # :160-209
+    img = np.arange(1, 13, dtype=np.uint8).reshape(3, 4)
+    r0 = zo.rotate(img, 0.0, "bilinear", "mirror")
+    assert r0.shape == (3, 4) and np.array_equal(r0, img)
+    r90 = zo.rotate(img, np.pi / 2, "bilinear", "mirror")
+    assert r90.shape == (4, 3) and r90[3, 0] == 1 and np.array_equal(r90, np.rot90(img, 1))
+    r180 = zo.rotate(img, np.pi, "bilinear", "mirror")
+    assert r180.shape == (3, 4) and np.array_equal(r180, np.rot90(img, 2))
+    r270 = zo.rotate(img, 3 * np.pi / 2, "bilinear", "mirror")
+    assert r270.shape == (4, 3) and np.array_equal(r270, np.rot90(img, 3))
+
+
+def test_rotate_45_grows():  # :211-229
+    img = _checker(10, 10)
+    out = zo.rotate(img, np.pi / 4, "bilinear", "mirror")
+    assert out.shape[0] > 10 and out.shape[1] > 10
+    assert zo.rotate_bounds(1080, 1920, np.float32(np.pi / 4)) == (2122, 2122)
+
+
+def test_warp_identity_and_translation():
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (9, 11, 4), dtype=np.uint8)
+    out = zo.warp(img, np.zeros_like(img), "affine", [1, 0, 0, 1, 0, 0], "bilinear")
+    assert np.array_equal(out, img)
+    out = zo.warp(img, np.zeros_like(img), "affine", [1, 0, 0, 1, 2, 1], "nearest")
+    assert np.array_equal(out[:8, :9], img[1:9, 2:11])
+    outp = zo.warp(img, np.zeros_like(img), "projective", [2, 0, 0, 0, 2, 0, 0, 0, 2], "bilinear")
+    assert np.array_equal(outp, img)
+
+
+# --------------------------------------------------------------------------------------- matrix/svd.zig:498-636
+def test_svd_wikipedia():
+    a = np.array([[1, 0, 0, 0], [0, 0, 0, 2], [0, 3, 0, 0], [0, 0, 0, 0], [2, 0, 0, 0]], np.float64)
+    u, s, v, rc = zo.svd(a, "full_u", True)
+    assert rc == 0 and u.shape == (5, 5) and v.shape == (4, 4)
+    assert np.all(s >= 0) and np.all(np.diff(s) <= 0)
+    assert np.allclose(s, [3, np.sqrt(5), 2, 0], atol=1e-12)
+    assert np.allclose(u[:, :4] @ np.diag(s) @ v.T, a, atol=1e-12)
+    assert np.allclose(u.T @ u, np.eye(5), atol=1e-12)
+
+
+def test_svd_modes_agree():  # :546-589
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((6, 4))
+    _, s_full, _, _ = zo.svd(a, "full_u", True)
+    u_sk, s_sk, v_sk, _ = zo.svd(a, "skinny_u", True)
+    _, s_no, _, _ = zo.svd(a, "no_u", False)
+    tol = np.sqrt(np.finfo(np.float64).eps)
+    assert np.allclose(s_full, s_sk, rtol=tol) and np.allclose(s_full, s_no, rtol=tol)
+    assert np.allclose(u_sk @ np.diag(s_sk) @ v_sk.T, a, atol=1e-12)
+    assert np.allclose(s_sk, np.linalg.svd(a, compute_uv=False), rtol=1e-12)
+
+
+def test_svd_identity_and_rank1():  # :591-636
+    _, s, _, rc = zo.svd(np.eye(3), "full_u", True)
+    assert rc == 0 and np.allclose(s, 1.0, rtol=np.sqrt(np.finfo(float).eps))
+    a = np.array([[1, 2, 3], [2, 4, 6], [1, 2, 3]], np.float64)
+    _, s, _, _ = zo.svd(a, "full_u", True)
+    assert np.count_nonzero(s < np.sqrt(np.finfo(float).eps)) == 2
+
+
+def test_svd_f32():
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((8, 5)).astype(np.float32)
+    u, s, v, rc = zo.svd(a, "skinny_u", True)
+    assert rc == 0
+    assert np.allclose(u @ np.diag(s) @ v.T, a, atol=2e-5)
+
+
+# --------------------------------------------------------------------------------------- matrix/test_ops_gemm.zig:246-299
+def test_gemm_9x9_known_values():
+    a = np.repeat(np.arange(1, 10, dtype=np.float32)[:, None], 9, axis=1)
+    r1 = zo.gemm(a, a)
+    assert r1[0, 0] == 45 and r1[1, 0] == 90 and r1[8, 8] == 405
+    r2 = zo.gemm(a, a, trans_a=True)
+    assert r2[0, 0] == 285 and r2[8, 8] == 285
+    r3 = zo.gemm(a, a, trans_b=True)
+    assert r3[0, 0] == 9 and r3[1, 1] == 36 and r3[8, 8] == 729
+    r4 = zo.gemm(a, a, trans_a=True, trans_b=True)
+    assert r4[0, 0] == 45 and r4[0, 8] == 405 and r4[8, 0] == 45 and r4[8, 8] == 405
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("big", [False, True])
+def test_gemm_matches_numpy(ta, tb, big):
+    rng = np.random.default_rng(10)
+    m, k, n = (13, 11, 9) if big else (2, 3, 2)
+    a = rng.standard_normal((k, m) if ta else (m, k))
+    b = rng.standard_normal((n, k) if tb else (k, n))
+    c = rng.standard_normal((m, n))
+    out = zo.gemm(a, b, ta, tb, alpha=0.5, beta=2.0, c=c)
+    ref = 0.5 * ((a.T if ta else a) @ (b.T if tb else b)) + 2.0 * c
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        zo.gemm(rng.standard_normal((3, 4)), rng.standard_normal((5, 2)))
+
+
+# --------------------------------------------------------------------------------------- fdm.zig:325-604
+def test_fdm_gray_mean_exact():  # :429-464
+    src = np.arange(100, dtype=np.uint8).reshape(100, 1)
+    tgt = (100 + np.arange(100)).astype(np.uint8).reshape(100, 1)
+    out = zo.fdm_match(src, tgt)
+    assert out.astype(np.float64).mean() == 149.5
+
+
+def test_fdm_color_mean_and_variance():  # :325-427
+    i = np.arange(2500)
+    x, y = i % 50, i // 50
+    src = np.stack([100 + x % 20, 150 + y % 15, 80 + (x + y) % 25], -1).astype(np.uint8).reshape(50, 50, 3)
+    tgt = np.stack([50 + x % 30, 70 + y % 20, 90 + (x + y) % 35], -1).astype(np.uint8).reshape(50, 50, 3)
+    out = zo.fdm_match(src, tgt).reshape(-1, 3).astype(np.float64)
+    t = tgt.reshape(-1, 3).astype(np.float64)
+    assert np.all(np.abs(out.mean(0) - t.mean(0)) <= 2.0)
+    assert np.all(np.abs(out.var(0) - t.var(0)) <= 1.0)
+
+
+def test_fdm_gray_target_on_color_source():  # :531-581
+    rng = np.random.default_rng(11)
+    src = rng.integers(0, 256, (20, 20, 3), dtype=np.uint8)
+    g = rng.integers(60, 200, (20, 20), dtype=np.uint8)
+    tgt = np.repeat(g[..., None], 3, axis=2)
+    out = zo.fdm_match(src, tgt)
+    assert np.array_equal(out[..., 0], out[..., 1]) and np.array_equal(out[..., 1], out[..., 2])
+    assert abs(out[..., 0].astype(float).mean() - g.astype(float).mean()) <= 2.0
+
+
+def test_fdm_stats_match_numpy():
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (31, 17, 3), dtype=np.uint8)
+    mean, cov, gray = zo.fdm_stats(img)
+    x = img.reshape(-1, 3).astype(np.float64) / 255.0
+    assert np.allclose(mean, x.mean(0), rtol=1e-12)
+    assert np.allclose(cov, np.cov(x.T), rtol=1e-10)
+    assert not gray
+
+
+# --------------------------------------------------------------------------------------- pca.zig:431-671
+def _reconstruct(mean, comps, coeffs):
+    return mean + comps @ coeffs
+
+
+def test_pca_2d_reconstruct():  # :441-475
+    data = np.array([[1, 2], [3, 4], [5, 6], [7, 8]], np.float64)
+    mean, comps, eig = zo.pca_fit(data)
+    v = np.array([4.0, 5.0])
+    coeffs = comps.T @ (v - mean)
+    assert np.allclose(_reconstruct(mean, comps, coeffs), v, atol=1e-10)
+
+
+def test_pca_gram_path():  # :519-557
+    data = np.array([[1, 0, 0], [3, 0, 0]], np.float64)
+    mean, comps, eig = zo.pca_fit(data, 1)
+    assert abs(eig[0] - 2.0) < 1e-9
+    assert abs(abs(comps[0, 0]) - 1.0) < 1e-9 and abs(comps[1, 0]) < 1e-12 and abs(comps[2, 0]) < 1e-12
+    t = zo.pca_transform(data, mean, comps)
+    assert abs(t[0, 0] - (comps[:, 0] @ (data[0] - mean))) < 1e-12
+
+
+def test_pca_10d_reconstruct():  # :559-588
+    i, j = np.mgrid[0:5, 0:10]
+    data = (i + j).astype(np.float64)
+    mean, comps, eig = zo.pca_fit(data)
+    v = np.arange(10, dtype=np.float64)
+    coeffs = comps.T @ (v - mean)
+    assert np.allclose(_reconstruct(mean, comps, coeffs), v, atol=1e-10)

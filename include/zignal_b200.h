@@ -1,0 +1,228 @@
+/*
+ * zignal_b200.h -- C ABI of libzignal_b200.so: the B200 (sm_100a) implementation of zignal's
+ * per-pixel image hot path.  This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types.  A host shim in the reference's language (zig/zignal_b200.zig; C++ mirror in
+ * zignal_b200/host/zignal.hpp; Python ctypes mirror in zignal_b200/) maps zignal's own
+ * Image(T)/Matrix(T) method signatures onto these entry points.
+ *
+ * The reference has no FFI on this path (callers invoke monomorphised Zig generics), so each entry
+ * point cites the reference *method* it replaces, file:line under arrufat/zignal src/.
+ *
+ * Conventions
+ *  - zb_image mirrors Image(T) (image.zig:97-102): row-major, `stride` in PIXELS, views allowed.
+ *  - `pixfmt` replaces the comptime pixel type T.
+ *  - zb_* image ops take DEVICE pointers and enqueue on `stream` (a cudaStream_t, NULL = default
+ *    stream); they return after enqueueing.  zb_host_* twins take HOST pointers, stage through the
+ *    library's device scratch and return when the result is back in host memory (the literal drop-in
+ *    for an `Image.data` that lives in host memory).
+ *  - Every function returns a zb_status (0 = ok) named after the Zig error it maps to.
+ *  - Transcendental inputs (Gaussian taps, cos/sin of a rotation angle, Lanczos LUT) are computed
+ *    on the host and cross the boundary as data, so every consumer sees identical values.
+ */
+#ifndef ZIGNAL_B200_H
+#define ZIGNAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_VERSION_MAJOR 0
+#define ZB_VERSION_MINOR 1
+
+typedef void* zb_stream; /* cudaStream_t */
+
+/* Image(T): image.zig:97-102.  data: device pointer (zb_*) or host pointer (zb_host_*). */
+typedef struct zb_image {
+    void*    data;
+    uint32_t rows;
+    uint32_t cols;
+    uint64_t stride; /* in pixels; == cols when contiguous (image.zig:355) */
+} zb_image;
+
+/* comptime pixel type T -> runtime tag */
+typedef enum zb_pixfmt {
+    ZB_PIX_U8 = 0,      /* Image(u8)                                                         */
+    ZB_PIX_F32 = 1,     /* Image(f32)                                                        */
+    ZB_PIX_RGB8 = 2,    /* Image(Rgb(u8)):  3 bytes r,g,b          color.zig:286-290         */
+    ZB_PIX_RGBA8 = 3,   /* Image(Rgba(u8)): packed r,g,b,a         color.zig:400-405         */
+    ZB_PIX_RGBAF32 = 4  /* Image(Rgba(f32)): 16-byte packed struct; filters act per channel  */
+} zb_pixfmt;
+
+/* BorderMode: border.zig:10-19 */
+typedef enum zb_border { ZB_BORDER_ZERO = 0, ZB_BORDER_REPLICATE = 1, ZB_BORDER_MIRROR = 2, ZB_BORDER_WRAP = 3 } zb_border;
+
+/* Interpolation: interpolation.zig:53-68 (union tag order; mitchell carries b, c) */
+typedef enum zb_interp {
+    ZB_INTERP_NEAREST = 0, ZB_INTERP_BILINEAR = 1, ZB_INTERP_BICUBIC = 2,
+    ZB_INTERP_CATMULL_ROM = 3, ZB_INTERP_MITCHELL = 4, ZB_INTERP_LANCZOS = 5
+} zb_interp;
+
+/* geometry/transforms.zig:10,118,197 */
+typedef enum zb_xform { ZB_XFORM_SIMILARITY = 0, ZB_XFORM_AFFINE = 1, ZB_XFORM_PROJECTIVE = 2 } zb_xform;
+
+/* svd.zig:6-17 */
+typedef enum zb_svd_mode { ZB_SVD_NO_U = 0, ZB_SVD_SKINNY_U = 1, ZB_SVD_FULL_U = 2 } zb_svd_mode;
+
+/* Zig error names (image.zig:637,970,531-536; Matrix.zig:52-62; fdm.zig:114,142-143; pca.zig) */
+typedef enum zb_status {
+    ZB_OK = 0,
+    ZB_ERR_DIMENSION_MISMATCH = 1, /* error.DimensionMismatch */
+    ZB_ERR_INVALID_SIGMA = 2,      /* error.InvalidSigma      */
+    ZB_ERR_UNSUPPORTED = 3,        /* (compile error in Zig: type not supported by this op) */
+    ZB_ERR_NOT_CONVERGED = 4,      /* error.NotConverged / error.SvdFailed */
+    ZB_ERR_INVALID_ARGUMENT = 5,
+    ZB_ERR_OUT_OF_MEMORY = 6,      /* error.OutOfMemory       */
+    ZB_ERR_DEVICE_FAILURE = 7,     /* CUDA / NCCL failure (new: error.DeviceFailure) */
+    ZB_ERR_INVALID_SCALE_FACTOR = 8, /* error.InvalidScaleFactor (image.zig:531) */
+    ZB_ERR_INVALID_DIMENSIONS = 9, /* error.InvalidDimensions (image.zig:536) */
+    ZB_ERR_NO_TARGET_SET = 10,     /* fdm.zig:142 */
+    ZB_ERR_NO_SOURCE_SET = 11,     /* fdm.zig:143 */
+    ZB_ERR_INSUFFICIENT_DATA = 12, /* pca.zig:114-115 NoVectors / InsufficientData */
+    ZB_ERR_INVALID_COMPONENTS = 13 /* pca.zig:123 */
+} zb_status;
+
+/* ------------------------------------------------------------------------------------------------
+ * Runtime: device, streams, memory.  These back the Zig `std.mem.Allocator` vtable of the shim
+ * (Image(T).init(dev_alloc, ...) / deinit, image.zig:124-158) and the pinned-host allocator.
+ * ---------------------------------------------------------------------------------------------- */
+int         zb_version(void);                 /* major*1000 + minor */
+const char* zb_status_name(int status);
+const char* zb_last_error(void);              /* thread-local text of the last CUDA failure */
+int zb_device_count(int* count);
+int zb_set_device(int ordinal);
+int zb_get_device(int* ordinal);
+int zb_sm_count(int* count);
+int zb_stream_create(zb_stream* out);
+int zb_stream_destroy(zb_stream s);
+int zb_stream_synchronize(zb_stream s);
+int zb_malloc(void** out, size_t bytes, zb_stream s);      /* cudaMallocAsync (stream-ordered pool) */
+int zb_free(void* p, zb_stream s);                         /* cudaFreeAsync */
+int zb_malloc_host(void** out, size_t bytes);              /* pinned host memory */
+int zb_free_host(void* p);
+/* Image-shaped copies (row pitch honoured on both sides); direction from the pointer kinds. */
+int zb_upload(const zb_image* host_src, zb_image* dev_dst, int pixfmt, zb_stream s);
+int zb_download(const zb_image* dev_src, zb_image* host_dst, int pixfmt, zb_stream s);
+int zb_copy(const zb_image* dev_src, zb_image* dev_dst, int pixfmt, zb_stream s); /* Image.copy, image.zig:375-392 */
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t zb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Filters
+ * ---------------------------------------------------------------------------------------------- */
+/* Host helper, image.zig:972-990: radius = ceil(3 sigma); taps exp(-x^2/(2 sigma^2)) in f32,
+ * normalised by a sequential f32 sum.  Returns the tap count in *n (0 for sigma == 0). */
+int zb_gaussian_taps(float sigma, float* taps, int cap, int* n);
+
+/* Image.convolveSeparable(out, allocator, kernel_x, kernel_y, border)   image.zig:935-951,
+ * convolution.zig:313-438.  kx/ky are HOST arrays.  In-place (src->data == dst->data) is allowed. */
+int zb_conv_separable(const zb_image* src, zb_image* dst, int pixfmt,
+                      const float* kx, int nx, const float* ky, int ny, int border, zb_stream s);
+/* Image.convolve(out, allocator, kernel, border)   image.zig:917-931, convolution.zig:198-301.
+ * kernel: HOST kh*kw row-major f32 (the comptime 2-D array after `as(f32, .)`). */
+int zb_convolve(const zb_image* src, zb_image* dst, int pixfmt,
+                const float* kernel, int kh, int kw, int border, zb_stream s);
+/* Image.gaussianBlur(out, allocator, sigma)   image.zig:954-994 (always .mirror). */
+int zb_gaussian_blur(const zb_image* src, zb_image* dst, int pixfmt, float sigma, zb_stream s);
+/* Image.boxBlur(out, allocator, radius)   image.zig:635-648, integral.zig:148-269. */
+int zb_box_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, zb_stream s);
+/* Image.sharpen(out, allocator, radius)   image.zig:785-799, integral.zig:273-422. */
+int zb_sharpen(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, zb_stream s);
+/* Image.integral: one f32 summed-area plane of a scalar image (integral.zig:41-78). sat: device rows*cols f32. */
+int zb_integral_plane(const zb_image* src, int pixfmt, float* sat, zb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Resampling and geometry
+ * ---------------------------------------------------------------------------------------------- */
+/* Image.resize(out, allocator, method)   image.zig:523-525, interpolation.zig:89-191. */
+int zb_resize(const zb_image* src, zb_image* dst, int pixfmt, int method, float mitchell_b, float mitchell_c, zb_stream s);
+/* Image.rotateBounds(angle)   image.zig:570, transforms.zig:112-149 (host math). */
+int zb_rotate_bounds(uint32_t rows, uint32_t cols, float angle, uint32_t* out_rows, uint32_t* out_cols);
+/* Image.rotateInto(out, angle, method, border)   image.zig:564, transforms.zig:163-212. */
+int zb_rotate_into(const zb_image* src, zb_image* dst, int pixfmt, float angle,
+                   int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
+/* Same, with cos(angle) / sin(angle) supplied by the caller (transforms.zig:190-191 computes them with
+ * Zig's @cos/@sin; passing them as data makes every consumer use identical values).  `angle` still
+ * selects the orthogonal fast paths (transforms.zig:165-187). */
+int zb_rotate_into_cs(const zb_image* src, zb_image* dst, int pixfmt, float angle, float cos_a, float sin_a,
+                      int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
+/* Batched rotateInto: n images of identical shape stored back to back (image i starts
+ * i*image_pitch_px pixels after image 0).  Same arithmetic per image as zb_rotate_into_cs. */
+int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_image* dst0, uint64_t dst_image_pitch_px,
+                         uint32_t n_images, int pixfmt, float angle, float cos_a, float sin_a,
+                         int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
+/* Image.warp(out, transform, method)   image.zig:621, transforms.zig:522-531 with
+ * {Similarity,Affine,Projective}Transform.project  geometry/transforms.zig:39,147,224.
+ * m (HOST): similarity/affine {m00,m01,m10,m11,b0,b1}; projective 9 values row-major. */
+int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m,
+            int method, float mitchell_b, float mitchell_c, zb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear algebra behind fdm / pca
+ * ---------------------------------------------------------------------------------------------- */
+/* Matrix.gemm(trans_a, other, trans_b, alpha, beta, c)   Matrix.zig:696-822.
+ * All matrices DEVICE, row-major, contiguous.  c may be NULL.  out is a_rows x b_cols. */
+int zb_gemm_f32(const float* a, uint32_t a_rows, uint32_t a_cols, int trans_a,
+                const float* b, uint32_t b_rows, uint32_t b_cols, int trans_b,
+                float alpha, float beta, const float* c, float* out, zb_stream s);
+int zb_gemm_f64(const double* a, uint32_t a_rows, uint32_t a_cols, int trans_a,
+                const double* b, uint32_t b_rows, uint32_t b_cols, int trans_b,
+                double alpha, double beta, const double* c, double* out, zb_stream s);
+/* Matrix.svd / SMatrix.svd   Matrix.zig:1570, SMatrix.zig:804, svd.zig:80-496.  HOST matrices
+ * (the decomposition is sequential; callers on this path pass 3x3 .. dim x dim covariance matrices).
+ * a: m x n row-major, m >= n.  u: m x (mode==FULL ? m : n) or NULL; s: n; v: n x n or NULL.
+ * *converged receives 0 or the failing index (svd.zig:79). */
+int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged);
+int zb_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v, float* u, float* s, float* v, uint64_t* converged);
+
+/* ------------------------------------------------------------------------------------------------
+ * Feature distribution matching   fdm.zig:19-275
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct zb_fdm zb_fdm;                       /* FeatureDistributionMatching(T) state, fdm.zig:22-39 */
+int zb_fdm_create(zb_fdm** out, int pixfmt);        /* .init   fdm.zig:42 ; pixfmt in {U8, RGB8, RGBA8} (fdm.zig:20) */
+int zb_fdm_destroy(zb_fdm* f);                      /* .deinit fdm.zig:61 */
+int zb_fdm_set_target(zb_fdm* f, const zb_image* target, zb_stream s);  /* fdm.zig:68  (device image, contiguous) */
+int zb_fdm_set_source(zb_fdm* f, zb_image* source);                      /* fdm.zig:127 */
+int zb_fdm_update(zb_fdm* f, zb_stream s);                               /* fdm.zig:141 (in place on source) */
+int zb_fdm_match(zb_fdm* f, zb_image* source, const zb_image* target, zb_stream s); /* fdm.zig:133 */
+/* The statistics pass alone: exact integer moment sums of a u8 image (n, sum x_i, sum x_i x_j, is_gray)
+ * -- the quantities one all-reduce combines across GPUs.  sums: HOST u64[11] =
+ * {n, Sr, Sg, Sb, Srr, Srg, Srb, Sgg, Sgb, Sbb, non_gray_count}.  as_luma selects fdm.zig:157-162. */
+int zb_fdm_moments(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums11, zb_stream s);
+/* Install externally reduced moments (multi-GPU: after the all-reduce) as target / source statistics. */
+int zb_fdm_set_target_moments(zb_fdm* f, const uint64_t* sums11);
+int zb_fdm_update_with_moments(zb_fdm* f, const uint64_t* source_sums11, zb_stream s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-pointer twins (H2D + op + D2H inside the call; returns when dst is valid on the host).
+ * ---------------------------------------------------------------------------------------------- */
+int zb_host_conv_separable(const zb_image* src, zb_image* dst, int pixfmt,
+                           const float* kx, int nx, const float* ky, int ny, int border);
+int zb_host_convolve(const zb_image* src, zb_image* dst, int pixfmt, const float* kernel, int kh, int kw, int border);
+int zb_host_gaussian_blur(const zb_image* src, zb_image* dst, int pixfmt, float sigma);
+int zb_host_box_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius);
+int zb_host_sharpen(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius);
+int zb_host_resize(const zb_image* src, zb_image* dst, int pixfmt, int method, float mitchell_b, float mitchell_c);
+int zb_host_rotate_into(const zb_image* src, zb_image* dst, int pixfmt, float angle, int method,
+                        float mitchell_b, float mitchell_c, int border);
+int zb_host_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m,
+                 int method, float mitchell_b, float mitchell_c);
+int zb_host_fdm_match(zb_image* source, const zb_image* target, int pixfmt);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tuning / introspection (not part of the drop-in surface)
+ * ---------------------------------------------------------------------------------------------- */
+/* Selects the arithmetic of the fused f32 separable kernel: 0 = FFMA (default, <= 1e-6 rel. from the
+ * reference), 1 = unfused mul+add in the reference's order (bit-exact with it for finite data). */
+int zb_set_exact_f32(int on);
+/* Forces the generic (two-pass through HBM) separable path; used by tests to cross-check kernels. */
+int zb_set_force_generic(int on);
+/* Name of the kernel variant the last zb_conv_separable call selected on this thread. */
+const char* zb_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIGNAL_B200_H */

@@ -1,0 +1,21 @@
+// zb_conv.h -- internal interface between the convolution translation units.
+#pragma once
+#include "zb_internal.h"
+
+namespace zb {
+
+constexpr int kMaxTaps = 1023;     // per separable axis (generic path)
+constexpr int kMaxTaps2D = 1024;   // kh*kw (generic dense path)
+
+// zb_conv_generic.cu
+int conv_separable_generic(const zb_image* src, zb_image* dst, int pixfmt, const float* kx, int nx, const float* ky, int ny,
+                           int border, cudaStream_t s);
+int convolve_generic(const zb_image* src, zb_image* dst, int pixfmt, const float* kernel, int kh, int kw, int border, cudaStream_t s);
+
+// zb_conv_fused.cu: single-pass (read once, write once) separable convolution of interleaved RGBA f32.
+// Returns ZB_ERR_UNSUPPORTED when the configuration is outside the fused kernel's envelope; the caller
+// then uses the generic path.  *used (optional) reports whether the fused kernel was launched.
+int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
+                                 bool exact, cudaStream_t s);
+
+}  // namespace zb

@@ -1,0 +1,339 @@
+// zb_conv_fused.cu -- single-pass separable convolution of interleaved RGBA f32 for sm_100a.
+//
+// Replaces convolveSeparablePlane(f32) (reference convolution.zig:441-647) applied per channel.  The
+// reference streams the image three times (src -> temp -> dst, with a full temp plane in DRAM); this
+// kernel reads every input pixel once and writes every output pixel once:
+//
+//   * work unit = (band of `band_rows` rows) x (strip of TW=256 pixels); units are ordered band-major
+//     so that the CTAs resident at one time cover neighbouring strips of the same band (their x-halos
+//     and the 2*8 halo rows between consecutive bands are then L2 hits, not DRAM reads);
+//   * a persistent CTA (one per SM, 256 threads) walks its units in chunks of 8 rows:
+//       TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B, zero OOB fill) lands chunk i+2 in a 2-stage ring
+//       while the SM runs   H(i): stage -> 24-row shared ring of horizontally filtered rows
+//       and                 V(i-2): ring -> registers -> 128-bit coalesced global stores;
+//   * both passes are register-blocked 8 outputs per thread along the filter axis (a thread loads
+//     8+2*HALF float4 and issues 8*K float4 FMAs), which keeps shared-memory traffic (~120 B/px) and
+//     FP32 issue (120 FFMA/px) both under the HBM time per pixel;
+//   * shared-memory accesses are conflict-free: the TMA box is {8 px, 34 groups, 8 rows} with the
+//     128-byte hardware swizzle keyed on (row*34+group)&7 and a quarter-warp reads 8 consecutive
+//     groups; the ring is XOR-swizzled on (x>>3)&7 by hand;
+//   * taps are kernel parameters (constant bank operands of the FFMAs), zero-padded to 2*HALF+1.
+//
+// Arithmetic: acc = 0; acc += px*k, taps ascending, horizontal pass first and its result rounded to
+// f32 before the vertical pass -- the reference's order.  EXACT=true keeps mul and add unfused
+// (bit-identical to the reference for finite data), EXACT=false uses FFMA (<= 1 ulp per step).
+// Border pixels: TMA zero-fills out-of-range coordinates; for replicate / mirror / wrap (and for the
+// ragged right edge when cols % 8 != 0) the few out-of-range stage entries are patched with
+// resolveIndex()-ed global loads before the horizontal pass (reference border.zig:46-63), so the
+// filter code itself has no border branches.
+#include "zb_conv.h"
+#include "zb_device.cuh"
+
+namespace zb {
+
+namespace {
+
+constexpr int TW = 256;                  // strip width in pixels
+constexpr int CHUNK = 8;                 // rows per pipeline step
+constexpr int G = TW / 8 + 2;            // 8-pixel groups per stage row (one halo group each side)
+constexpr int STAGE_BYTES = G * CHUNK * 128;          // 34816
+constexpr int RING_ROWS = 24;
+constexpr int RING_ROW_BYTES = TW * 16;               // 4096
+constexpr int RING_BYTES = RING_ROWS * RING_ROW_BYTES;  // 98304
+constexpr int NTHREADS = 256;
+constexpr int MAX_HALF = 8;
+constexpr int MAXK = 2 * MAX_HALF + 1;
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + RING_BYTES + 64 + 1024;
+
+struct FusedParams {
+    float kx[MAXK];
+    float ky[MAXK];
+    const float4* src;
+    float4* dst;
+    unsigned long long src_pitch_px, dst_pitch_px;
+    int rows, cols, border;
+    int ngroups;     // floor(cols / 8): pixel groups the tensor map covers
+    int n_strips, n_bands, band_rows;
+    int fix_rows;    // 1 if out-of-range rows need patching (border != zero)
+    int fix_left;    // 1 if x < 0 needs patching
+    int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {
+    if constexpr (EXACT) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, k));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, k));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, k));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, k));
+    } else {
+        acc.x = fmaf(v.x, k, acc.x);
+        acc.y = fmaf(v.y, k, acc.y);
+        acc.z = fmaf(v.z, k, acc.z);
+        acc.w = fmaf(v.w, k, acc.w);
+    }
+}
+
+// Patch the stage entries TMA could not provide (out-of-range rows / columns) per the border mode.
+__device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, const FusedParams& p) {
+    const int xlimit = p.ngroups * 8;
+    for (int idx = threadIdx.x; idx < CHUNK * G * 8; idx += NTHREADS) {
+        const int rr = idx / (G * 8);
+        const int xx = idx - rr * (G * 8);
+        const int y = y0 + rr, x = xs0 + xx;
+        const bool provided = (y >= 0 && y < p.rows && x >= 0 && x < xlimit);
+        if (provided) continue;
+        const int ry = resolve_index(y, p.rows, p.border);
+        const int rx = resolve_index(x, p.cols, p.border);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ry >= 0 && rx >= 0) v = __ldg(p.src + (size_t)ry * p.src_pitch_px + rx);
+        const uint32_t line = (uint32_t)(rr * G + (xx >> 3));
+        sts128(stage + line * 128 + ((((uint32_t)xx & 7u) ^ (line & 7u)) << 4), v);
+    }
+}
+
+template <int HALF, bool EXACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int NLOAD = CHUNK + 2 * HALF;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = smem0 + 2 * STAGE_BYTES;
+    const uint32_t bar0 = ring + RING_BYTES;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // H-pass role: lane -> pixel group (8 consecutive pixels), warp -> row of the chunk
+    const int ht = tid & 31, hr = tid >> 5;
+    // V-pass role: thread -> pixel column, 8 consecutive output rows
+    const int vx = tid;
+    const uint32_t v_col = ring + (uint32_t)(vx >> 3) * 128u + ((((uint32_t)vx & 7u) ^ (((uint32_t)vx >> 3) & 7u)) << 4);
+    const uint32_t h_ring_col = ring + (uint32_t)ht * 128u;
+    const uint32_t h_key = (uint32_t)ht & 7u;
+
+    uint32_t uses0 = 0, uses1 = 0;  // completed waits per stage barrier (phase parity)
+    const int n_units = p.n_strips * p.n_bands;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
+        const int x0 = strip * TW;
+        const int ra = band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.rows);
+        const int n_out = (rb - ra + CHUNK - 1) / CHUNK;  // output chunks
+        const int n_in = n_out + 2;                       // input chunks: chunk i covers rows [ra-8+8i, ra+8i)
+        const int g0 = x0 / 8 - 1;
+
+        if (tid == 0) {
+            fence_proxy_async();
+            for (int i = 0; i < 2; ++i) {
+                mbar_arrive_expect_tx(bar0 + 8 * i, STAGE_BYTES);
+                tma_load_3d(smem0 + STAGE_BYTES * i, &tmap, 0, g0, ra - CHUNK + CHUNK * i, bar0 + 8 * i);
+            }
+        }
+
+        for (int i = 0; i < n_in; ++i) {
+            const int st = i & 1;
+            const uint32_t stage = smem0 + (uint32_t)(st * STAGE_BYTES);
+            const uint32_t bar = bar0 + (uint32_t)(st * 8);
+            const uint32_t parity = (st ? uses1 : uses0) & 1u;
+            while (!mbar_try_wait(bar, parity)) {}
+            if (st) uses1++; else uses0++;
+            const int y0 = ra - CHUNK + CHUNK * i;
+            const bool fix = (p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows)) || (p.fix_left && g0 < 0) ||
+                             (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
+            if (fix) {
+                fixup_stage(stage, y0, g0 * 8, p);
+                __syncthreads();
+            }
+
+            // ---------------- H(i): stage -> ring rows [(i%3)*8, +8) ----------------
+            {
+                float4 acc[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t line0 = (uint32_t)(hr * G + ht);
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) {
+                    const int pidx = 8 - HALF + j;  // pixel index relative to the start of group `ht` of the stage row
+                    const uint32_t line = line0 + (uint32_t)(pidx >> 3);
+                    const float4 v = lds128(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int ti = j - o;
+                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.kx[ti]);
+                    }
+                }
+                const uint32_t rrow = h_ring_col + (uint32_t)(((i % 3) * CHUNK + hr) * RING_ROW_BYTES);
+#pragma unroll
+                for (int o = 0; o < 8; ++o) sts128(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+            }
+            __syncthreads();  // ring slot complete; stage `st` is free again
+
+            if (tid == 0 && i + 2 < n_in) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                tma_load_3d(stage, &tmap, 0, g0, ra - CHUNK + CHUNK * (i + 2), bar);
+            }
+
+            // ---------------- V(i-2): ring -> global rows [ra+8c, ra+8c+8) ----------------
+            if (i >= 2) {
+                const int c = i - 2;
+                float4 acc[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) {
+                    uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                    if (sr >= RING_ROWS) sr -= RING_ROWS;
+                    const float4 v = lds128(v_col + sr * (uint32_t)RING_ROW_BYTES);
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int ti = j - o;
+                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
+                    }
+                }
+                const int x = x0 + vx;
+                if (x < p.cols) {
+                    const int yb = ra + CHUNK * c;
+                    float4* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o)
+                        if (yb + o < rb) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
+                }
+            }
+            __syncthreads();  // V(i-2) done reading the slot H(i+1) will overwrite
+        }
+    }
+}
+
+template <int HALF>
+int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool exact, cudaStream_t s) {
+    auto k0 = fused_sep_rgbaf32_kernel<HALF, false>;
+    auto k1 = fused_sep_rgbaf32_kernel<HALF, true>;
+    auto k = exact ? k1 : k0;
+    ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));  // per device; cheap
+    k<<<grid, NTHREADS, SMEM_BYTES, s>>>(tmap, p);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+}  // namespace
+
+int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
+                                 bool exact, cudaStream_t s) {
+    const int half_x = nx / 2, half_y = ny / 2;
+    const int half = half_x > half_y ? half_x : half_y;
+    if (half < 1 || half > MAX_HALF) return ZB_ERR_UNSUPPORTED;
+    if (src->cols < 16 || src->rows < 16) return ZB_ERR_UNSUPPORTED;  // tiny images: generic path
+    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;             // in place: generic path (temp plane)
+    if (((uintptr_t)src->data & 15u) || ((uintptr_t)dst->data & 15u)) return ZB_ERR_UNSUPPORTED;
+    // taps with |k| < 1e-10 are skipped by the reference only in the interior (convolution.zig:459-467): generic path
+    for (int i = 0; i < nx; ++i) if (fabsf(kx[i]) < 1e-10f) return ZB_ERR_UNSUPPORTED;
+    for (int i = 0; i < ny; ++i) if (fabsf(ky[i]) < 1e-10f) return ZB_ERR_UNSUPPORTED;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return ZB_ERR_UNSUPPORTED;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (di.smem_optin < (size_t)SMEM_BYTES) return ZB_ERR_UNSUPPORTED;
+
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    // tap i of an n-tap kernel acts at offset i - n/2 (convolution.zig:527,542): place it at index i + (half - n/2)
+    for (int i = 0; i < nx; ++i) p.kx[i + (half - half_x)] = kx[i];
+    for (int i = 0; i < ny; ++i) p.ky[i + (half - half_y)] = ky[i];
+    p.src = (const float4*)src->data;
+    p.dst = (float4*)dst->data;
+    p.src_pitch_px = src->stride;
+    p.dst_pitch_px = dst->stride;
+    p.rows = (int)src->rows;
+    p.cols = (int)src->cols;
+    p.border = border;
+    p.ngroups = p.cols / 8;
+    p.n_strips = (p.cols + TW - 1) / TW;
+    // band height: ~256 rows, then as many bands as fit in the same number of waves
+    int n_bands = (p.rows + 255) / 256;
+    const long long waves = ((long long)n_bands * p.n_strips + di.sm_count - 1) / di.sm_count;
+    int nb2 = (int)((waves * di.sm_count) / p.n_strips);
+    if (nb2 > n_bands) n_bands = nb2;
+    int band_rows = (p.rows + n_bands - 1) / n_bands;
+    band_rows = ((band_rows + CHUNK - 1) / CHUNK) * CHUNK;
+    if (band_rows < 64) band_rows = 64;
+    p.band_rows = band_rows;
+    p.n_bands = (p.rows + band_rows - 1) / band_rows;
+    p.fix_rows = border != ZB_BORDER_ZERO;
+    p.fix_left = border != ZB_BORDER_ZERO;
+    p.fix_right = (border != ZB_BORDER_ZERO) || (p.cols % 8 != 0);
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {32, (cuuint64_t)p.ngroups, (cuuint64_t)p.rows};
+    const cuuint64_t gstr[2] = {128, (cuuint64_t)src->stride * 16};
+    const cuuint32_t box[3] = {32, (cuuint32_t)G, (cuuint32_t)CHUNK};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, src->data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        snprintf(t_last_error, sizeof(t_last_error), "cuTensorMapEncodeTiled failed: %d", (int)cr);
+        return ZB_ERR_UNSUPPORTED;
+    }
+    const int n_units = p.n_strips * p.n_bands;
+    const int grid = n_units < di.sm_count ? n_units : di.sm_count;
+    t_last_kernel = exact ? "fused_sep_rgbaf32_exact" : "fused_sep_rgbaf32";
+    switch (half) {
+        case 1: return launch_fused<1>(tmap, p, grid, exact, s);
+        case 2: return launch_fused<2>(tmap, p, grid, exact, s);
+        case 3: return launch_fused<3>(tmap, p, grid, exact, s);
+        case 4: return launch_fused<4>(tmap, p, grid, exact, s);
+        case 5: return launch_fused<5>(tmap, p, grid, exact, s);
+        case 6: return launch_fused<6>(tmap, p, grid, exact, s);
+        case 7: return launch_fused<7>(tmap, p, grid, exact, s);
+        case 8: return launch_fused<8>(tmap, p, grid, exact, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
+}  // namespace zb

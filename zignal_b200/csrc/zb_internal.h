@@ -1,0 +1,73 @@
+// zb_internal.h -- shared internals of libzignal_b200.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/zignal_b200.h"
+
+namespace zb {
+
+extern std::atomic<uint64_t> g_launches;
+extern thread_local char t_last_error[512];
+extern thread_local const char* t_last_kernel;
+extern std::atomic<int> g_exact_f32;
+extern std::atomic<int> g_force_generic;
+
+int set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+
+#define ZB_CUDA(expr)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) return ::zb::set_cuda_error(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// Count + check a kernel launch.
+#define ZB_LAUNCHED()                                                                      \
+    do {                                                                                   \
+        ::zb::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) return ::zb::set_cuda_error(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceInfo {
+    int ordinal = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+// Lazily initialised per-device state (mempool threshold, SM count, driver entry points).
+int device_info(DeviceInfo* out);
+// cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint (no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+
+static inline int channels_of(int pixfmt) {
+    switch (pixfmt) {
+        case ZB_PIX_U8: case ZB_PIX_F32: return 1;
+        case ZB_PIX_RGB8: return 3;
+        case ZB_PIX_RGBA8: case ZB_PIX_RGBAF32: return 4;
+    }
+    return 0;
+}
+static inline size_t channel_bytes(int pixfmt) { return (pixfmt == ZB_PIX_F32 || pixfmt == ZB_PIX_RGBAF32) ? 4 : 1; }
+static inline size_t pixel_bytes(int pixfmt) { return (size_t)channels_of(pixfmt) * channel_bytes(pixfmt); }
+static inline bool is_float_fmt(int pixfmt) { return pixfmt == ZB_PIX_F32 || pixfmt == ZB_PIX_RGBAF32; }
+
+// RAII stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on the op's stream).
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~Scratch() { if (p) cudaFreeAsync(p, s); }
+    int alloc(size_t bytes, cudaStream_t stream);
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace zb

@@ -1,0 +1,162 @@
+// zb_runtime.cu -- device / stream / memory plumbing behind the C ABI (include/zignal_b200.h).
+// These wrappers are what the Zig shim's DeviceAllocator (std.mem.Allocator vtable) and
+// Image(T).init/deinit (reference image.zig:124-158) sit on.
+#include <mutex>
+
+#include "zb_internal.h"
+
+namespace zb {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local char t_last_error[512] = "";
+thread_local const char* t_last_kernel = "";
+std::atomic<int> g_exact_f32{0};
+std::atomic<int> g_force_generic{0};
+
+int set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+    snprintf(t_last_error, sizeof(t_last_error), "%s: %s (%s:%d)", cudaGetErrorName(e), what, file, line);
+    if (e == cudaErrorMemoryAllocation) return ZB_ERR_OUT_OF_MEMORY;
+    return ZB_ERR_DEVICE_FAILURE;
+}
+
+static std::mutex g_mu;
+static DeviceInfo g_dev[64];
+static EncodeTiledFn g_encode = nullptr;
+
+int device_info(DeviceInfo* out) {
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ZB_ERR_DEVICE_FAILURE;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].ordinal != dev) {
+        cudaDeviceProp prop;
+        ZB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        g_dev[dev].sm_count = prop.multiProcessorCount;
+        g_dev[dev].smem_optin = prop.sharedMemPerBlockOptin;
+        // keep freed scratch cached in the default pool instead of returning it to the driver
+        cudaMemPool_t pool;
+        ZB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thresh = UINT64_MAX;
+        ZB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        g_dev[dev].ordinal = dev;
+    }
+    *out = g_dev[dev];
+    return ZB_OK;
+}
+
+EncodeTiledFn encode_tiled_fn() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+    }
+    return g_encode;
+}
+
+int Scratch::alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    if (bytes == 0) bytes = 16;
+    ZB_CUDA(cudaMallocAsync(&p, bytes, stream));
+    return ZB_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_version(void) { return ZB_VERSION_MAJOR * 1000 + ZB_VERSION_MINOR; }
+
+const char* zb_status_name(int status) {
+    switch (status) {
+        case ZB_OK: return "Ok";
+        case ZB_ERR_DIMENSION_MISMATCH: return "DimensionMismatch";
+        case ZB_ERR_INVALID_SIGMA: return "InvalidSigma";
+        case ZB_ERR_UNSUPPORTED: return "Unsupported";
+        case ZB_ERR_NOT_CONVERGED: return "NotConverged";
+        case ZB_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+        case ZB_ERR_OUT_OF_MEMORY: return "OutOfMemory";
+        case ZB_ERR_DEVICE_FAILURE: return "DeviceFailure";
+        case ZB_ERR_INVALID_SCALE_FACTOR: return "InvalidScaleFactor";
+        case ZB_ERR_INVALID_DIMENSIONS: return "InvalidDimensions";
+        case ZB_ERR_NO_TARGET_SET: return "NoTargetSet";
+        case ZB_ERR_NO_SOURCE_SET: return "NoSourceSet";
+        case ZB_ERR_INSUFFICIENT_DATA: return "InsufficientData";
+        case ZB_ERR_INVALID_COMPONENTS: return "InvalidComponents";
+    }
+    return "Unknown";
+}
+
+const char* zb_last_error(void) { return t_last_error; }
+const char* zb_last_kernel(void) { return t_last_kernel; }
+uint64_t zb_kernel_launch_count(void) { return g_launches.load(); }
+int zb_set_exact_f32(int on) { g_exact_f32.store(on ? 1 : 0); return ZB_OK; }
+int zb_set_force_generic(int on) { g_force_generic.store(on ? 1 : 0); return ZB_OK; }
+
+int zb_device_count(int* count) { ZB_CUDA(cudaGetDeviceCount(count)); return ZB_OK; }
+int zb_set_device(int ordinal) { ZB_CUDA(cudaSetDevice(ordinal)); return ZB_OK; }
+int zb_get_device(int* ordinal) { ZB_CUDA(cudaGetDevice(ordinal)); return ZB_OK; }
+int zb_sm_count(int* count) {
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    *count = di.sm_count;
+    return ZB_OK;
+}
+
+int zb_stream_create(zb_stream* out) {
+    cudaStream_t s;
+    ZB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (zb_stream)s;
+    return ZB_OK;
+}
+int zb_stream_destroy(zb_stream s) { ZB_CUDA(cudaStreamDestroy((cudaStream_t)s)); return ZB_OK; }
+int zb_stream_synchronize(zb_stream s) { ZB_CUDA(cudaStreamSynchronize((cudaStream_t)s)); return ZB_OK; }
+
+int zb_malloc(void** out, size_t bytes, zb_stream s) {
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (bytes == 0) bytes = 16;
+    ZB_CUDA(cudaMallocAsync(out, bytes, (cudaStream_t)s));
+    return ZB_OK;
+}
+int zb_free(void* p, zb_stream s) {
+    if (!p) return ZB_OK;
+    ZB_CUDA(cudaFreeAsync(p, (cudaStream_t)s));
+    return ZB_OK;
+}
+int zb_malloc_host(void** out, size_t bytes) {
+    ZB_CUDA(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+    return ZB_OK;
+}
+int zb_free_host(void* p) {
+    if (!p) return ZB_OK;
+    ZB_CUDA(cudaFreeHost(p));
+    return ZB_OK;
+}
+
+static int copy2d(const zb_image* src, zb_image* dst, int pixfmt, cudaMemcpyKind kind, cudaStream_t s) {
+    if (src->rows != dst->rows || src->cols != dst->cols) return ZB_ERR_DIMENSION_MISMATCH;
+    const size_t pb = pixel_bytes(pixfmt);
+    if (pb == 0) return ZB_ERR_UNSUPPORTED;
+    if (src->rows == 0 || src->cols == 0) return ZB_OK;
+    if (src->data == dst->data) return ZB_OK;  // image.zig:377
+    ZB_CUDA(cudaMemcpy2DAsync(dst->data, dst->stride * pb, src->data, src->stride * pb, (size_t)src->cols * pb, src->rows, kind, s));
+    return ZB_OK;
+}
+int zb_upload(const zb_image* host_src, zb_image* dev_dst, int pixfmt, zb_stream s) {
+    return copy2d(host_src, dev_dst, pixfmt, cudaMemcpyHostToDevice, (cudaStream_t)s);
+}
+int zb_download(const zb_image* dev_src, zb_image* host_dst, int pixfmt, zb_stream s) {
+    return copy2d(dev_src, host_dst, pixfmt, cudaMemcpyDeviceToHost, (cudaStream_t)s);
+}
+int zb_copy(const zb_image* dev_src, zb_image* dev_dst, int pixfmt, zb_stream s) {
+    return copy2d(dev_src, dev_dst, pixfmt, cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+}
+
+}  // extern "C"

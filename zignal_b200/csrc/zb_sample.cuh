@@ -1,0 +1,206 @@
+// zb_sample.cuh -- device samplers: Image.interpolate for every Interpolation variant.
+// Reference: interpolation.zig:72-84 (interpolate), :222-300 (kernels; Lanczos via a 1025-entry LUT
+// with linear interpolation :256-280), :306-311 (nearest), :313-407 (bilinear: integer lerp with
+// fx = round(frac*256) and +32768 rounding for <=16-bit ints, float lerp otherwise), :426-519
+// (interpolateWithKernel: f32 weights wx[i]*wy[j], row-major accumulation, / weight_sum, meta.clamp;
+// out-of-range taps are skipped, so kernel samplers renormalise at .zero borders).
+//
+// This translation unit family is compiled with -fmad=false: every f32 expression below is evaluated
+// exactly as written (separately rounded mul/add), which is what the reference's Zig does.
+#pragma once
+#include "zb_device.cuh"
+
+namespace zb {
+
+template <typename CT, int N>
+struct Pix {
+    CT v[N];
+};
+
+template <typename CT, int N>
+__device__ __forceinline__ Pix<CT, N> load_px(const CT* __restrict__ base, size_t px) {
+    Pix<CT, N> p;
+    if constexpr (sizeof(CT) == 1 && N == 4) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(base + px * 4);
+        p.v[0] = q.x; p.v[1] = q.y; p.v[2] = q.z; p.v[3] = q.w;
+    } else if constexpr (sizeof(CT) == 4 && N == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(base + px * 4);
+        p.v[0] = q.x; p.v[1] = q.y; p.v[2] = q.z; p.v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) p.v[k] = base[px * N + k];
+    }
+    return p;
+}
+
+template <typename CT, int N>
+__device__ __forceinline__ void store_px(CT* __restrict__ base, size_t px, const Pix<CT, N>& p) {
+    if constexpr (sizeof(CT) == 1 && N == 4) {
+        *reinterpret_cast<uchar4*>(base + px * 4) = make_uchar4(p.v[0], p.v[1], p.v[2], p.v[3]);
+    } else if constexpr (sizeof(CT) == 4 && N == 4) {
+        *reinterpret_cast<float4*>(base + px * 4) = make_float4(p.v[0], p.v[1], p.v[2], p.v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) base[px * N + k] = p.v[k];
+    }
+}
+
+template <typename CT, int N>
+__device__ __forceinline__ Pix<CT, N> zero_px() {
+    Pix<CT, N> p;
+#pragma unroll
+    for (int k = 0; k < N; ++k) p.v[k] = (CT)0;
+    return p;
+}
+
+struct SrcView {
+    const void* data;
+    int rows, cols;
+    unsigned long long stride;  // pixels
+};
+
+// interpolation.zig:222-230
+__device__ __forceinline__ float bicubic_kernel(float t) {
+    const float at = fabsf(t);
+    if (at <= 1) return 1 - 2 * at * at + at * at * at;
+    else if (at <= 2) return 4 - 8 * at + 5 * at * at - at * at * at;
+    return 0;
+}
+// interpolation.zig:234-242
+__device__ __forceinline__ float catmull_rom_kernel(float x) {
+    const float ax = fabsf(x);
+    if (ax <= 1) return 1.5f * ax * ax * ax - 2.5f * ax * ax + 1;
+    else if (ax <= 2) return -0.5f * ax * ax * ax + 2.5f * ax * ax - 4 * ax + 2;
+    return 0;
+}
+// interpolation.zig:270-280 (lut: 1025 host-computed entries, :256-267)
+__device__ __forceinline__ float lanczos3_kernel_lut(float x, const float* __restrict__ lut) {
+    const float ax = fabsf(x);
+    if (ax >= 3.0f) return 0;
+    const float step = 1024.0f / 3.0f;
+    const float pos = ax * step;
+    const int idx = (int)truncf(pos);
+    const float frac = pos - (float)idx;
+    return lut[idx] * (1.0f - frac) + lut[idx + 1] * frac;
+}
+// interpolation.zig:284-300
+__device__ __forceinline__ float mitchell_kernel(float x, float m_b, float m_c) {
+    const float ax = fabsf(x);
+    const float ax2 = ax * ax;
+    const float ax3 = ax2 * ax;
+    if (ax < 1) {
+        return ((12 - 9 * m_b - 6 * m_c) * ax3 + (-18 + 12 * m_b + 6 * m_c) * ax2 + (6 - 2 * m_b)) / 6;
+    } else if (ax < 2) {
+        return ((-m_b - 6 * m_c) * ax3 + (6 * m_b + 30 * m_c) * ax2 + (-12 * m_b - 48 * m_c) * ax + (8 * m_b + 24 * m_c)) / 6;
+    }
+    return 0;
+}
+
+// meta.clamp(CT, f32): ints round half away + saturate, floats plain cast
+template <typename CT>
+__device__ __forceinline__ CT clamp_channel(float v) {
+    if constexpr (sizeof(CT) == 1) return clamp_u8_from_float(v);
+    else return v;
+}
+
+// interpolation.zig:353-368 lerpInt, 8-bit fields
+__device__ __forceinline__ uint8_t lerp_int_u8(int tl, int tr, int bl, int br, int fx, int fy) {
+    const int scale = 256;
+    const int top_val = tl * (scale - fx) + tr * fx;
+    const int bottom_val = bl * (scale - fx) + br * fx;
+    const int result = (top_val * (scale - fy) + bottom_val * fy + (scale * scale / 2)) / (scale * scale);
+    return (uint8_t)(result < 0 ? 0 : (result > 255 ? 255 : result));
+}
+
+// interpolation.zig:72-84.  Returns false for null (caller writes zeroes).
+template <typename CT, int N>
+__device__ __forceinline__ bool interpolate(const SrcView& img, float x, float y, int method, float mb, float mc, int border,
+                                            const float* __restrict__ lut, Pix<CT, N>& out) {
+    if (!isfinite(x) || !isfinite(y)) return false;
+    const float range_limit = 4611686018427387904.0f;  // @floatFromInt(maxInt(isize) / 2)
+    if (fabsf(x) > range_limit || fabsf(y) > range_limit) return false;
+    const CT* base = (const CT*)img.data;
+    const long long rows = img.rows, cols = img.cols;
+
+    if (method == ZB_INTERP_NEAREST) {  // :306-311
+        const long long col = resolve_index64((long long)roundf(x), cols, border);
+        if (col < 0) return false;
+        const long long row = resolve_index64((long long)roundf(y), rows, border);
+        if (row < 0) return false;
+        out = load_px<CT, N>(base, (size_t)row * img.stride + (size_t)col);
+        return true;
+    }
+    if (method == ZB_INTERP_BILINEAR) {  // :313-407
+        const float flx = floorf(x), fly = floorf(y);
+        const long long left = (long long)flx, top = (long long)fly;
+        const long long r0 = resolve_index64(top, rows, border), r1 = resolve_index64(top + 1, rows, border);
+        const long long c0 = resolve_index64(left, cols, border), c1 = resolve_index64(left + 1, cols, border);
+        if (border == ZB_BORDER_MIRROR && (r0 < 0 || r1 < 0 || c0 < 0 || c1 < 0)) return false;  // :337-339
+        const Pix<CT, N> z = zero_px<CT, N>();
+        const Pix<CT, N> tl = (r0 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c0) : z;
+        const Pix<CT, N> tr = (r0 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c1) : z;
+        const Pix<CT, N> bl = (r1 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c0) : z;
+        const Pix<CT, N> br = (r1 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c1) : z;
+        const float lr = x - flx;  // as(f32, left) == floor(x) for |x| < 2^62 up to f32 rounding of the i64 -> same value
+        const float tb = y - fly;
+        if constexpr (sizeof(CT) == 1) {
+            const int fx = (int)roundf(lr * 256.0f), fy = (int)roundf(tb * 256.0f);
+#pragma unroll
+            for (int k = 0; k < N; ++k) out.v[k] = lerp_int_u8(tl.v[k], tr.v[k], bl.v[k], br.v[k], fx, fy);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+                out.v[k] = (1 - tb) * ((1 - lr) * tl.v[k] + lr * tr.v[k]) + tb * ((1 - lr) * bl.v[k] + lr * br.v[k]);
+        }
+        return true;
+    }
+    // kernel samplers, :426-519
+    const int window_radius = (method == ZB_INTERP_LANCZOS) ? 3 : 2;
+    const int window_size = window_radius * 2;
+    const float flx = floorf(x), fly = floorf(y);
+    const long long ix = (long long)flx, iy = (long long)fly;
+    const float fx = x - flx, fy = y - fly;
+    float xw[6], yw[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (i < window_size) {
+            const float off = (float)(i - (window_radius - 1));
+            const float ox = off - fx, oy = off - fy;
+            switch (method) {
+                case ZB_INTERP_BICUBIC: xw[i] = bicubic_kernel(ox); yw[i] = bicubic_kernel(oy); break;
+                case ZB_INTERP_CATMULL_ROM: xw[i] = catmull_rom_kernel(ox); yw[i] = catmull_rom_kernel(oy); break;
+                case ZB_INTERP_LANCZOS: xw[i] = lanczos3_kernel_lut(ox, lut); yw[i] = lanczos3_kernel_lut(oy, lut); break;
+                default: xw[i] = mitchell_kernel(ox, mb, mc); yw[i] = mitchell_kernel(oy, mb, mc); break;
+            }
+        }
+    }
+    float sums[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) sums[k] = 0;
+    float weight_sum = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        if (j >= window_size) break;
+        const long long py = resolve_index64(iy - (window_radius - 1) + j, rows, border);
+        if (py < 0) continue;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i >= window_size) break;
+            const long long px = resolve_index64(ix - (window_radius - 1) + i, cols, border);
+            if (px < 0) continue;
+            const Pix<CT, N> pixel = load_px<CT, N>(base, (size_t)py * img.stride + (size_t)px);
+            const float weight = xw[i] * yw[j];
+#pragma unroll
+            for (int k = 0; k < N; ++k) sums[k] += (float)pixel.v[k] * weight;
+            weight_sum += weight;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const float val = weight_sum != 0 ? sums[k] / weight_sum : 0.0f;
+        out.v[k] = clamp_channel<CT>(val);
+    }
+    return true;
+}
+
+}  // namespace zb

@@ -1,0 +1,316 @@
+// zb_warp.cu -- Image.rotateBounds / rotateInto / warp: inverse-mapped gather kernels.
+// Reference: transforms.zig:112-149 (rotateBounds), :163-212 (rotateInto; fast paths within 1e-6 rad
+// of k*pi/2 :165-187), :385-462 (rotate0/90/180/270 with centred placement and zeroed margins),
+// :522-531 (warp, always .mirror), image.zig:322-327 (centre = (cols/2, rows/2) as f32),
+// geometry/transforms.zig:39-42,147-150 (affine project: (m0*x + m1*y) + b, no fusion),
+// :224-231 (projective: multiply by 1/w when w != 0).
+// One thread per destination pixel, 2-D 32x8 thread tiles so that a warp's source footprint stays in
+// a few cache lines for any rotation angle.  Compiled with -fmad=false (coordinate math is the
+// reference's unfused f32 sequence, which the u8 outputs depend on bit for bit).
+#include <cmath>
+#include <mutex>
+
+#include "zb_host_stage.h"
+#include "zb_sample.cuh"
+#include "zb_warp.h"
+
+namespace zb {
+
+namespace {
+
+constexpr float TAU_F = 6.283185307179586f;
+constexpr float PI_F = 3.141592653589793f;
+
+// Zig's float @mod: a = frem(l, r); l < 0 ? frem(a + r, r) : a
+static inline float zig_mod_f32(float l, float r) {
+    const float a = std::fmod(l, r);
+    return l < 0 ? std::fmod(a + r, r) : a;
+}
+// transforms.zig:114-136 / :165-187: 0 general, 1 = 0deg, 2 = 90, 3 = 180, 4 = 270
+static int rotate_class(float angle) {
+    const float n = zig_mod_f32(angle, TAU_F);
+    const float eps = 1e-6f;
+    if (std::fabs(n) < eps || std::fabs(n - TAU_F) < eps) return 1;
+    if (std::fabs(n - PI_F / 2.0f) < eps) return 2;
+    if (std::fabs(n - PI_F) < eps) return 3;
+    if (std::fabs(n - 3.0f * PI_F / 2.0f) < eps) return 4;
+    return 0;
+}
+
+struct RotParams {
+    float cos_a, sin_a, cx, cy, rcx, rcy;
+    int method, border;
+    float mb, mc;
+};
+
+template <typename CT, int N>
+__global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long long src_image_pitch, CT* __restrict__ dst, size_t dst_stride,
+                                                     unsigned long long dst_image_pitch, int dst_rows, int dst_cols, RotParams p,
+                                                     const float* __restrict__ lut) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= dst_cols || r >= dst_rows) return;
+    img.data = (const CT*)img.data + (size_t)blockIdx.z * src_image_pitch * N;
+    dst += (size_t)blockIdx.z * dst_image_pitch * N;
+    const float x = (float)c, y = (float)r;          // transforms.zig:199-209
+    const float dx = x - p.rcx;
+    const float dy = y - p.rcy;
+    const float rotated_dx = p.cos_a * dx - p.sin_a * dy;
+    const float rotated_dy = p.sin_a * dx + p.cos_a * dy;
+    const float src_x = rotated_dx + p.cx;
+    const float src_y = rotated_dy + p.cy;
+    Pix<CT, N> val;
+    if (!interpolate<CT, N>(img, src_x, src_y, p.method, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+    store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
+}
+
+// transforms.zig:385-462 as a gather over destination pixels
+template <typename CT, int N>
+__global__ void __launch_bounds__(256) rotate_orth_kernel(const CT* __restrict__ src, size_t src_stride, unsigned long long src_image_pitch,
+                                                          int rows, int cols, CT* __restrict__ dst, size_t dst_stride,
+                                                          unsigned long long dst_image_pitch, int dst_rows, int dst_cols, int kind) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= dst_cols || r >= dst_rows) return;
+    src += (size_t)blockIdx.z * src_image_pitch * N;
+    dst += (size_t)blockIdx.z * dst_image_pitch * N;
+    const bool swap = (kind == 2 || kind == 4);
+    const int content_rows = swap ? cols : rows, content_cols = swap ? rows : cols;
+    const int offset_r = (dst_rows > content_rows ? dst_rows - content_rows : 0) / 2;
+    const int offset_c = (dst_cols > content_cols ? dst_cols - content_cols : 0) / 2;
+    const int rr = r - offset_r, cc = c - offset_c;
+    if (rr >= 0 && rr < content_rows && cc >= 0 && cc < content_cols) {
+        int sr, sc;
+        switch (kind) {
+            case 1: sr = rr; sc = cc; break;
+            case 2: sc = cols - 1 - rr; sr = cc; break;              // new_r = cols-1-c, new_c = r
+            case 3: sr = rows - 1 - rr; sc = cols - 1 - cc; break;
+            default: sc = rr; sr = rows - 1 - cc; break;             // new_r = c, new_c = rows-1-r
+        }
+        store_px<CT, N>(dst, (size_t)r * dst_stride + c, load_px<CT, N>(src, (size_t)sr * src_stride + sc));
+    } else if (offset_r != 0 || offset_c != 0) {
+        store_px<CT, N>(dst, (size_t)r * dst_stride + c, zero_px<CT, N>());  // setBorder(inner, zeroes) only when an offset exists
+    }
+}
+
+struct WarpParams {
+    float m[9];
+    int projective, method;
+    float mb, mc;
+};
+
+template <typename CT, int N>
+__global__ void __launch_bounds__(256) warp_kernel(SrcView img, CT* __restrict__ dst, size_t dst_stride, int dst_rows, int dst_cols,
+                                                   WarpParams p, const float* __restrict__ lut) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= dst_cols || r >= dst_rows) return;
+    const float x = (float)c, y = (float)r;
+    float sx, sy;
+    if (p.projective) {  // geometry/transforms.zig:224-231 through SMatrix.gemm's scalar tail (SMatrix.zig:554-560)
+        float d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float a = 0;
+            a += p.m[3 * i + 0] * x;
+            a += p.m[3 * i + 1] * y;
+            a += p.m[3 * i + 2] * 1.0f;
+            d[i] = 0.0f + 1.0f * a;
+        }
+        if (d[2] != 0) {
+            const float s = 1 / d[2];
+            d[0] = d[0] * s;
+            d[1] = d[1] * s;
+        }
+        sx = d[0];
+        sy = d[1];
+    } else {  // :39-42 / :147-150
+        float a0 = 0; a0 += p.m[0] * x; a0 += p.m[1] * y; a0 = 0.0f + 1.0f * a0;
+        float a1 = 0; a1 += p.m[2] * x; a1 += p.m[3] * y; a1 = 0.0f + 1.0f * a1;
+        sx = a0 + p.m[4];
+        sy = a1 + p.m[5];
+    }
+    Pix<CT, N> val;
+    if (!interpolate<CT, N>(img, sx, sy, p.method, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
+    store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
+}
+
+template <typename CT, int N>
+int rotate_typed(const zb_image* src, unsigned long long spitch, zb_image* dst, unsigned long long dpitch, uint32_t n, float angle,
+                 float cos_a, float sin_a, int method, float mb, float mc, int border, const float* lut, cudaStream_t s) {
+    dim3 grid(div_up(dst->cols, 32), div_up(dst->rows, 8), n);
+    const int cls = rotate_class(angle);
+    if (cls != 0) {
+        t_last_kernel = "rotate_orthogonal";
+        rotate_orth_kernel<CT, N><<<grid, 256, 0, s>>>((const CT*)src->data, (size_t)src->stride, spitch, (int)src->rows, (int)src->cols,
+                                                       (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows, (int)dst->cols, cls);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    }
+    RotParams p;
+    p.cos_a = cos_a;
+    p.sin_a = sin_a;
+    p.cx = (float)src->cols / 2.0f;   // image.zig:322-327
+    p.cy = (float)src->rows / 2.0f;
+    const float offset_x = ((float)dst->cols - (float)src->cols) / 2.0f;   // transforms.zig:193-197
+    const float offset_y = ((float)dst->rows - (float)src->rows) / 2.0f;
+    p.rcx = p.cx + offset_x;
+    p.rcy = p.cy + offset_y;
+    p.method = method; p.border = border; p.mb = mb; p.mc = mc;
+    SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
+    t_last_kernel = "rotate_gather";
+    rotate_kernel<CT, N><<<grid, 256, 0, s>>>(v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows, (int)dst->cols, p, lut);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+int rotate_dispatch(const zb_image* src, unsigned long long spitch, zb_image* dst, unsigned long long dpitch, uint32_t n, int pixfmt,
+                    float angle, float cos_a, float sin_a, int method, float mb, float mc, int border, cudaStream_t s) {
+    if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
+    if (channels_of(pixfmt) == 0) return ZB_ERR_UNSUPPORTED;
+    if (method < ZB_INTERP_NEAREST || method > ZB_INTERP_LANCZOS) return ZB_ERR_INVALID_ARGUMENT;
+    if (border < ZB_BORDER_ZERO || border > ZB_BORDER_WRAP) return ZB_ERR_INVALID_ARGUMENT;
+    if (dst->rows == 0 || dst->cols == 0 || n == 0) return ZB_OK;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const float* lut = nullptr;
+    if (method == ZB_INTERP_LANCZOS && (rc = lanczos_lut_device(&lut, s))) return rc;
+    switch (pixfmt) {
+        case ZB_PIX_U8: return rotate_typed<uint8_t, 1>(src, spitch, dst, dpitch, n, angle, cos_a, sin_a, method, mb, mc, border, lut, s);
+        case ZB_PIX_F32: return rotate_typed<float, 1>(src, spitch, dst, dpitch, n, angle, cos_a, sin_a, method, mb, mc, border, lut, s);
+        case ZB_PIX_RGB8: return rotate_typed<uint8_t, 3>(src, spitch, dst, dpitch, n, angle, cos_a, sin_a, method, mb, mc, border, lut, s);
+        case ZB_PIX_RGBA8: return rotate_typed<uint8_t, 4>(src, spitch, dst, dpitch, n, angle, cos_a, sin_a, method, mb, mc, border, lut, s);
+        case ZB_PIX_RGBAF32: return rotate_typed<float, 4>(src, spitch, dst, dpitch, n, angle, cos_a, sin_a, method, mb, mc, border, lut, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
+template <typename CT, int N>
+int warp_typed(const zb_image* src, zb_image* dst, const WarpParams& p, const float* lut, cudaStream_t s) {
+    SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
+    dim3 grid(div_up(dst->cols, 32), div_up(dst->rows, 8));
+    warp_kernel<CT, N><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows, (int)dst->cols, p, lut);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+int warp_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int kind, const float* m, int method, float mb, float mc, cudaStream_t s) {
+    if (!src || !dst || !m) return ZB_ERR_INVALID_ARGUMENT;
+    if (channels_of(pixfmt) == 0) return ZB_ERR_UNSUPPORTED;
+    if (kind < ZB_XFORM_SIMILARITY || kind > ZB_XFORM_PROJECTIVE) return ZB_ERR_INVALID_ARGUMENT;
+    if (method < ZB_INTERP_NEAREST || method > ZB_INTERP_LANCZOS) return ZB_ERR_INVALID_ARGUMENT;
+    if (dst->rows == 0 || dst->cols == 0) return ZB_OK;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    WarpParams p;
+    memset(&p, 0, sizeof(p));
+    p.projective = kind == ZB_XFORM_PROJECTIVE;
+    memcpy(p.m, m, (p.projective ? 9 : 6) * sizeof(float));
+    p.method = method; p.mb = mb; p.mc = mc;
+    const float* lut = nullptr;
+    if (method == ZB_INTERP_LANCZOS && (rc = lanczos_lut_device(&lut, s))) return rc;
+    t_last_kernel = "warp_gather";
+    switch (pixfmt) {
+        case ZB_PIX_U8: return warp_typed<uint8_t, 1>(src, dst, p, lut, s);
+        case ZB_PIX_F32: return warp_typed<float, 1>(src, dst, p, lut, s);
+        case ZB_PIX_RGB8: return warp_typed<uint8_t, 3>(src, dst, p, lut, s);
+        case ZB_PIX_RGBA8: return warp_typed<uint8_t, 4>(src, dst, p, lut, s);
+        case ZB_PIX_RGBAF32: return warp_typed<float, 4>(src, dst, p, lut, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// interpolation.zig:256-267: lut[i] = lanczosKernel(i / (1024/3), 3) in f32, computed on the host
+int lanczos_lut_device(const float** out, cudaStream_t s) {
+    static std::mutex mu;
+    static float* dev_lut[64] = {nullptr};
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!dev_lut[dev]) {
+        float h[1025];
+        const float step = 1024.0f / 3.0f;
+        for (int i = 0; i < 1025; ++i) {
+            const float x = (float)i / step;
+            float v;
+            if (x == 0) v = 1;
+            else if (std::fabs(x) >= 3.0f) v = 0;
+            else {
+                const float pi_x = 3.14159265358979323846f * x;
+                const float pi_x_over_a = pi_x / 3.0f;
+                v = (3.0f * std::sin(pi_x) * std::sin(pi_x_over_a)) / (pi_x * pi_x);
+            }
+            h[i] = v;
+        }
+        float* d = nullptr;
+        ZB_CUDA(cudaMalloc(&d, sizeof(h)));
+        ZB_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+        dev_lut[dev] = d;
+    }
+    *out = dev_lut[dev];
+    return ZB_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_rotate_bounds(uint32_t rows, uint32_t cols, float angle, uint32_t* out_rows, uint32_t* out_cols) {
+    if (!out_rows || !out_cols) return ZB_ERR_INVALID_ARGUMENT;
+    const int cls = rotate_class(angle);
+    if (cls == 1 || cls == 3) { *out_rows = rows; *out_cols = cols; return ZB_OK; }
+    if (cls == 2 || cls == 4) { *out_rows = cols; *out_cols = rows; return ZB_OK; }
+    const float cos_abs = std::fabs(std::cos(angle)), sin_abs = std::fabs(std::sin(angle));  // transforms.zig:139-148
+    const float w = (float)cols, h = (float)rows;
+    const float new_w = w * cos_abs + h * sin_abs;
+    const float new_h = h * cos_abs + w * sin_abs;
+    *out_cols = (uint32_t)std::ceil(new_w);
+    *out_rows = (uint32_t)std::ceil(new_h);
+    return ZB_OK;
+}
+
+int zb_rotate_into_cs(const zb_image* src, zb_image* dst, int pixfmt, float angle, float cos_a, float sin_a, int method, float mb,
+                      float mc, int border, zb_stream s) {
+    return rotate_dispatch(src, 0, dst, 0, 1, pixfmt, angle, cos_a, sin_a, method, mb, mc, border, (cudaStream_t)s);
+}
+
+int zb_rotate_into(const zb_image* src, zb_image* dst, int pixfmt, float angle, int method, float mb, float mc, int border, zb_stream s) {
+    return rotate_dispatch(src, 0, dst, 0, 1, pixfmt, angle, std::cos(angle), std::sin(angle), method, mb, mc, border, (cudaStream_t)s);
+}
+
+int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_image* dst0, uint64_t dst_image_pitch_px, uint32_t n_images,
+                         int pixfmt, float angle, float cos_a, float sin_a, int method, float mb, float mc, int border, zb_stream s) {
+    if (n_images > 65535) return ZB_ERR_INVALID_ARGUMENT;
+    return rotate_dispatch(src0, src_image_pitch_px, dst0, dst_image_pitch_px, n_images, pixfmt, angle, cos_a, sin_a, method, mb, mc, border,
+                           (cudaStream_t)s);
+}
+
+int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m, int method, float mb, float mc, zb_stream s) {
+    return warp_dispatch(src, dst, pixfmt, xform_kind, m, method, mb, mc, (cudaStream_t)s);
+}
+
+int zb_host_rotate_into(const zb_image* src, zb_image* dst, int pixfmt, float angle, int method, float mb, float mc, int border) {
+    if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
+    HostStage st;
+    int rc;
+    if ((rc = st.begin(src, dst, pixfmt))) return rc;
+    if ((rc = zb_rotate_into(&st.dsrc, &st.ddst, pixfmt, angle, method, mb, mc, border, st.stream))) return rc;
+    return st.finish(dst, pixfmt);
+}
+
+int zb_host_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m, int method, float mb, float mc) {
+    if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
+    HostStage st;
+    int rc;
+    if ((rc = st.begin(src, dst, pixfmt))) return rc;
+    if ((rc = zb_warp(&st.dsrc, &st.ddst, pixfmt, xform_kind, m, method, mb, mc, st.stream))) return rc;
+    return st.finish(dst, pixfmt);
+}
+
+}  // extern "C"

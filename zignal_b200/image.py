@@ -1,0 +1,342 @@
+"""Host-side mirror of zignal's `Image(T)` for the hot path (reference src/image.zig:97-1249).
+
+Same method names, argument meaning and error behaviour as the reference's Zig API (snake_case as in
+the reference's own Python binding, bindings/python/src/image/*.zig); every method body is a call
+through the C ABI in include/zignal_b200.h.  Pixel storage lives in device memory (a torch CUDA
+tensor is used purely as the owner of that memory and of the stream); `Image.from_numpy` /
+`to_numpy` move data across PCIe, and the module-level `host_*` functions are the literal drop-in
+for host-resident `Image.data` (H2D + op + D2H inside one C call).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from enum import IntEnum
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import ZbImage, check, lib
+
+
+class PixFmt(IntEnum):
+    U8 = 0        # Image(u8)
+    F32 = 1       # Image(f32)
+    RGB8 = 2      # Image(Rgb(u8))
+    RGBA8 = 3     # Image(Rgba(u8))
+    RGBAF32 = 4   # Image(Rgba(f32))
+
+
+class BorderMode(IntEnum):  # reference border.zig:10-19
+    ZERO = 0
+    REPLICATE = 1
+    MIRROR = 2
+    WRAP = 3
+
+
+class Interpolation(IntEnum):  # reference interpolation.zig:53-68
+    NEAREST = 0
+    BILINEAR = 1
+    BICUBIC = 2
+    CATMULL_ROM = 3
+    MITCHELL = 4
+    LANCZOS = 5
+
+
+_CH = {PixFmt.U8: 1, PixFmt.F32: 1, PixFmt.RGB8: 3, PixFmt.RGBA8: 4, PixFmt.RGBAF32: 4}
+_NP = {PixFmt.U8: np.uint8, PixFmt.F32: np.float32, PixFmt.RGB8: np.uint8, PixFmt.RGBA8: np.uint8, PixFmt.RGBAF32: np.float32}
+
+
+def pixfmt_of_array(a) -> PixFmt:
+    dt = np.dtype(str(a.dtype).replace("torch.", ""))
+    nd = a.ndim
+    ch = a.shape[2] if nd == 3 else 1
+    if dt == np.uint8 and nd == 2:
+        return PixFmt.U8
+    if dt == np.uint8 and ch == 3:
+        return PixFmt.RGB8
+    if dt == np.uint8 and ch == 4:
+        return PixFmt.RGBA8
+    if dt == np.float32 and nd == 2:
+        return PixFmt.F32
+    if dt == np.float32 and ch == 4:
+        return PixFmt.RGBAF32
+    raise TypeError(f"unsupported pixel array: dtype={a.dtype} shape={tuple(a.shape)}")
+
+
+def _np_image(a: np.ndarray) -> ZbImage:
+    """zb_image over a (possibly row-strided) numpy array."""
+    px_bytes = a.dtype.itemsize * (a.shape[2] if a.ndim == 3 else 1)
+    if a.ndim == 3:
+        assert a.strides[2] == a.dtype.itemsize and a.strides[1] == px_bytes, "pixels must be packed"
+    elif a.shape[1] > 1:
+        assert a.strides[1] == a.dtype.itemsize
+    row = a.strides[0] if a.shape[0] > 1 else a.shape[1] * px_bytes
+    assert row % px_bytes == 0
+    return ZbImage(a.ctypes.data, a.shape[0], a.shape[1], row // px_bytes)
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _mitchell(method, b, c):
+    return int(method), C.c_float(b), C.c_float(c)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def current_stream() -> int:
+    torch = _torch()
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class Rectangle:  # reference geometry/Rectangle.zig: l, t, r, b (exclusive r, b)
+    l: int
+    t: int
+    r: int
+    b: int
+
+
+class Image:
+    """Device-resident mirror of zignal's Image(T) {rows, cols, data, stride} (image.zig:97-102)."""
+
+    def __init__(self, tensor, pixfmt: PixFmt, rows: int, cols: int, stride: int, offset_px: int = 0):
+        self._t = tensor          # torch tensor that owns the storage (flat, channel elements)
+        self.pixfmt = PixFmt(pixfmt)
+        self.rows, self.cols, self.stride = int(rows), int(cols), int(stride)
+        self._off = int(offset_px)
+
+    # ---- construction (image.zig:124-184) -------------------------------------------------------
+    @classmethod
+    def init(cls, rows: int, cols: int, pixfmt: PixFmt, device=None) -> "Image":
+        torch = _torch()
+        lib()  # fail loudly if the CUDA library is missing
+        dt = torch.uint8 if _NP[PixFmt(pixfmt)] == np.uint8 else torch.float32
+        t = torch.empty(int(rows) * int(cols) * _CH[PixFmt(pixfmt)], dtype=dt, device=device or "cuda")
+        return cls(t, pixfmt, rows, cols, cols)
+
+    @classmethod
+    def init_like(cls, other: "Image") -> "Image":
+        return cls.init(other.rows, other.cols, other.pixfmt, other._t.device)
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, device=None) -> "Image":
+        torch = _torch()
+        lib()
+        fmt = pixfmt_of_array(a)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device or "cuda").reshape(-1)
+        return cls(t, fmt, a.shape[0], a.shape[1], a.shape[1])
+
+    @classmethod
+    def from_tensor(cls, t) -> "Image":
+        """Wrap a contiguous CUDA tensor of shape (rows, cols[, ch]) without copying."""
+        fmt = pixfmt_of_array(t)
+        assert t.is_cuda and t.is_contiguous()
+        return cls(t.reshape(-1), fmt, t.shape[0], t.shape[1], t.shape[1])
+
+    def to_numpy(self) -> np.ndarray:
+        ch = _CH[self.pixfmt]
+        full = self._t.cpu().numpy()
+        if self.rows == 0 or self.cols == 0:
+            return np.zeros((self.rows, self.cols) + ((ch,) if ch > 1 else ()), _NP[self.pixfmt])
+        idx = (self._off + np.arange(self.rows)[:, None] * self.stride + np.arange(self.cols)[None, :])
+        if ch == 1:
+            return full[idx]
+        return full.reshape(-1, ch)[idx]
+
+    def tensor(self):
+        """The (rows, cols[, ch]) CUDA tensor of a contiguous, non-view image."""
+        assert self.is_contiguous() and self._off == 0
+        ch = _CH[self.pixfmt]
+        return self._t.view(self.rows, self.cols, ch) if ch > 1 else self._t.view(self.rows, self.cols)
+
+    # ---- views (image.zig:332-357) --------------------------------------------------------------
+    def view(self, rect: Rectangle) -> "Image":
+        l, t = max(0, rect.l), max(0, rect.t)
+        r, b = min(self.cols, rect.r), min(self.rows, rect.b)
+        if r <= l or b <= t:
+            return Image(self._t, self.pixfmt, 0, 0, 0, 0)
+        return Image(self._t, self.pixfmt, b - t, r - l, self.stride, self._off + t * self.stride + l)
+
+    def is_contiguous(self) -> bool:
+        return self.cols == self.stride
+
+    def has_same_shape(self, other) -> bool:
+        return self.rows == other.rows and self.cols == other.cols
+
+    def get_center(self) -> Tuple[float, float]:  # image.zig:322-327
+        return (np.float32(self.cols) / np.float32(2), np.float32(self.rows) / np.float32(2))
+
+    def _zb(self) -> ZbImage:
+        esz = self._t.element_size() * _CH[self.pixfmt]
+        return ZbImage(self._t.data_ptr() + self._off * esz, self.rows, self.cols, self.stride)
+
+    def copy(self, dst: "Image") -> None:  # image.zig:375-392
+        assert self.has_same_shape(dst)
+        a, d = self._zb(), dst._zb()
+        check(lib().zb_copy(a, d, int(self.pixfmt), current_stream()))
+
+    def dupe(self) -> "Image":  # image.zig:367-371
+        out = Image.init_like(self)
+        self.copy(out)
+        return out
+
+    def _out(self, out: Optional["Image"]) -> "Image":
+        return Image.init_like(self) if out is None else out
+
+    # ---- filters (image.zig:635-648, 785-799, 917-994) --------------------------------------------
+    def box_blur(self, radius: int, out: Optional["Image"] = None) -> "Image":
+        out = self._out(out)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_box_blur(a, d, int(self.pixfmt), int(radius), current_stream()))
+        return out
+
+    def sharpen(self, radius: int, out: Optional["Image"] = None) -> "Image":
+        out = self._out(out)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_sharpen(a, d, int(self.pixfmt), int(radius), current_stream()))
+        return out
+
+    def convolve(self, kernel, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
+        k = np.ascontiguousarray(kernel, dtype=np.float32)
+        if k.ndim != 2:
+            raise ValueError("Kernel must be a 2D array")  # convolution.zig:200
+        out = self._out(out)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_convolve(a, d, int(self.pixfmt), _fptr(k), k.shape[0], k.shape[1], int(border), current_stream()))
+        return out
+
+    def convolve_separable(self, kernel_x, kernel_y, border: BorderMode = BorderMode.MIRROR,
+                           out: Optional["Image"] = None) -> "Image":
+        kx = np.ascontiguousarray(kernel_x, dtype=np.float32)
+        ky = np.ascontiguousarray(kernel_y, dtype=np.float32)
+        out = self._out(out)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_conv_separable(a, d, int(self.pixfmt), _fptr(kx), kx.size, _fptr(ky), ky.size, int(border),
+                                      current_stream()))
+        return out
+
+    def gaussian_blur(self, sigma: float, out: Optional["Image"] = None) -> "Image":
+        out = self._out(out)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_gaussian_blur(a, d, int(self.pixfmt), C.c_float(sigma), current_stream()))
+        return out
+
+    # ---- resampling (image.zig:523-541) -----------------------------------------------------------
+    def resize(self, out: "Image", method: Interpolation = Interpolation.BILINEAR, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        a, d = self._zb(), out._zb()
+        check(lib().zb_resize(a, d, int(self.pixfmt), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        return out
+
+    def scale(self, factor: float, method: Interpolation = Interpolation.BILINEAR) -> "Image":
+        if factor <= 0:
+            raise _ffi.ZignalError(8, "InvalidScaleFactor")       # image.zig:531
+        new_rows = int(_round_half_away(np.float32(self.rows) * np.float32(factor)))
+        new_cols = int(_round_half_away(np.float32(self.cols) * np.float32(factor)))
+        if new_rows == 0 or new_cols == 0:
+            raise _ffi.ZignalError(9, "InvalidDimensions")        # image.zig:536
+        return self.resize(Image.init(new_rows, new_cols, self.pixfmt, self._t.device), method)
+
+    # ---- geometry (image.zig:558-623) -------------------------------------------------------------
+    def rotate_bounds(self, angle: float) -> Tuple[int, int]:
+        r, c = C.c_uint32(), C.c_uint32()
+        check(lib().zb_rotate_bounds(self.rows, self.cols, C.c_float(angle), C.byref(r), C.byref(c)))
+        return r.value, c.value
+
+    def rotate_into(self, out: "Image", angle: float, method: Interpolation = Interpolation.BILINEAR,
+                    border: BorderMode = BorderMode.ZERO, cos_sin=None, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        a, d = self._zb(), out._zb()
+        if cos_sin is None:
+            check(lib().zb_rotate_into(a, d, int(self.pixfmt), C.c_float(angle), int(method), C.c_float(b), C.c_float(c),
+                                       int(border), current_stream()))
+        else:
+            check(lib().zb_rotate_into_cs(a, d, int(self.pixfmt), C.c_float(angle), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
+                                          int(method), C.c_float(b), C.c_float(c), int(border), current_stream()))
+        return out
+
+    def rotate(self, angle: float, method: Interpolation = Interpolation.BILINEAR, border: BorderMode = BorderMode.ZERO,
+               cos_sin=None) -> "Image":
+        rows, cols = self.rotate_bounds(angle)
+        out = Image.init(rows, cols, self.pixfmt, self._t.device)
+        return self.rotate_into(out, angle, method, border, cos_sin)
+
+    def warp(self, out: "Image", transform, method: Interpolation = Interpolation.BILINEAR, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        kind, m = transform.as_f32()
+        a, d = self._zb(), out._zb()
+        check(lib().zb_warp(a, d, int(self.pixfmt), kind, _fptr(m), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        return out
+
+
+def _round_half_away(v) -> float:
+    v = float(v)
+    return math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host-resident drop-ins: numpy in, numpy out; H2D + kernel + D2H happen inside one C-ABI call.
+# ---------------------------------------------------------------------------------------------------
+def _host_call(fn_name, src: np.ndarray, out: np.ndarray, *args):
+    a, d = _np_image(src), _np_image(out)
+    check(getattr(lib(), fn_name)(a, d, int(pixfmt_of_array(src)), *args))
+    return out
+
+
+def host_gaussian_blur(src: np.ndarray, sigma: float, out: Optional[np.ndarray] = None) -> np.ndarray:
+    out = np.empty_like(src) if out is None else out
+    return _host_call("zb_host_gaussian_blur", src, out, C.c_float(sigma))
+
+
+def host_conv_separable(src, kx, ky, border=BorderMode.MIRROR, out=None) -> np.ndarray:
+    out = np.empty_like(src) if out is None else out
+    kx = np.ascontiguousarray(kx, dtype=np.float32)
+    ky = np.ascontiguousarray(ky, dtype=np.float32)
+    return _host_call("zb_host_conv_separable", src, out, _fptr(kx), kx.size, _fptr(ky), ky.size, int(border))
+
+
+def host_convolve(src, kernel, border=BorderMode.MIRROR, out=None) -> np.ndarray:
+    out = np.empty_like(src) if out is None else out
+    k = np.ascontiguousarray(kernel, dtype=np.float32)
+    return _host_call("zb_host_convolve", src, out, _fptr(k), k.shape[0], k.shape[1], int(border))
+
+
+def host_box_blur(src, radius, out=None) -> np.ndarray:
+    out = np.empty_like(src) if out is None else out
+    return _host_call("zb_host_box_blur", src, out, int(radius))
+
+
+def host_sharpen(src, radius, out=None) -> np.ndarray:
+    out = np.empty_like(src) if out is None else out
+    return _host_call("zb_host_sharpen", src, out, int(radius))
+
+
+def host_resize(src, out_shape, method=Interpolation.BILINEAR, b=1 / 3, c=1 / 3, out=None) -> np.ndarray:
+    if out is None:
+        out = np.zeros((out_shape[0], out_shape[1]) + tuple(src.shape[2:]), dtype=src.dtype)
+    return _host_call("zb_host_resize", src, out, int(method), C.c_float(b), C.c_float(c))
+
+
+def host_rotate(src, angle, method=Interpolation.BILINEAR, border=BorderMode.ZERO) -> np.ndarray:
+    r, c = C.c_uint32(), C.c_uint32()
+    check(lib().zb_rotate_bounds(src.shape[0], src.shape[1], C.c_float(angle), C.byref(r), C.byref(c)))
+    out = np.zeros((r.value, c.value) + tuple(src.shape[2:]), dtype=src.dtype)
+    return _host_call("zb_host_rotate_into", src, out, C.c_float(angle), int(method), C.c_float(1 / 3), C.c_float(1 / 3), int(border))
+
+
+def host_warp(src, out, transform, method=Interpolation.BILINEAR) -> np.ndarray:
+    kind, m = transform.as_f32()
+    return _host_call("zb_host_warp", src, out, kind, _fptr(m), int(method), C.c_float(1 / 3), C.c_float(1 / 3))
+
+
+def gaussian_taps(sigma: float) -> np.ndarray:
+    """Host math of gaussianBlur (image.zig:972-990)."""
+    n = C.c_int()
+    buf = np.zeros(8192, np.float32)
+    check(lib().zb_gaussian_taps(C.c_float(sigma), _fptr(buf), buf.size, C.byref(n)))
+    return buf[: n.value].copy()

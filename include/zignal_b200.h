@@ -219,6 +219,8 @@ int zb_host_fdm_match(zb_image* source, const zb_image* target, int pixfmt);
 int zb_set_exact_f32(int on);
 /* Forces the generic (two-pass through HBM) separable path; used by tests to cross-check kernels. */
 int zb_set_force_generic(int on);
+/* Kernel tuning knobs for experiments ("conv.stages" 2|3, "conv.f32x2" 0|1, "conv.band_rows" >= 64). */
+int zb_tune(const char* key, int value);
 /* Name of the kernel variant the last zb_conv_separable call selected on this thread. */
 const char* zb_last_kernel(void);
 

@@ -1,0 +1,151 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol the public
+header declares, and its host-side entry points (no device work) agree with the oracle."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as zo
+import zignal_b200 as zb
+from zignal_b200 import _ffi
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = zb.lib()
+    names = zb.declared_symbols()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"header declares symbols the library does not export: {missing}"
+    assert L.zb_version() == 1
+
+
+def test_enums_match_between_product_header_and_oracle_header():
+    prod = (_ffi.ROOT / "include" / "zignal_b200.h").read_text()
+    orac = (_ffi.ROOT / "oracle" / "zignal_oracle.h").read_text()
+    for suffix in ("BORDER_ZERO", "BORDER_REPLICATE", "BORDER_MIRROR", "BORDER_WRAP", "INTERP_NEAREST", "INTERP_BILINEAR",
+                   "INTERP_BICUBIC", "INTERP_CATMULL_ROM", "INTERP_MITCHELL", "INTERP_LANCZOS", "PIX_U8", "PIX_F32", "PIX_RGB8",
+                   "PIX_RGBA8", "PIX_RGBAF32", "XFORM_SIMILARITY", "XFORM_AFFINE", "XFORM_PROJECTIVE", "SVD_NO_U", "SVD_SKINNY_U",
+                   "SVD_FULL_U"):
+        a = re.search(rf"ZB_{suffix}\s*=\s*(\d+)", prod)
+        b = re.search(rf"ZO_{suffix}\s*=\s*(\d+)", orac)
+        assert a and b and a.group(1) == b.group(1), suffix
+
+
+def test_status_names_follow_zig_error_names():
+    L = zb.lib()
+    want = {0: "Ok", 1: "DimensionMismatch", 2: "InvalidSigma", 4: "NotConverged", 6: "OutOfMemory", 7: "DeviceFailure",
+            8: "InvalidScaleFactor", 9: "InvalidDimensions", 10: "NoTargetSet", 11: "NoSourceSet"}
+    for k, v in want.items():
+        assert L.zb_status_name(k).decode() == v
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = _ffi.PKG
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.hpp")):
+        text = path.read_text()
+        assert "oracle_lib" not in text and "zignal_oracle" not in text and "libzignal_oracle" not in text, path
+
+
+def test_gaussian_taps_match_oracle_bit_for_bit():
+    for sigma in (0.5, 1.0, 1.4, 2.0, 2.25, 3.3, 7.0):
+        assert np.array_equal(zb.gaussian_taps(sigma), zo.gaussian_taps(sigma)), sigma
+    assert zb.gaussian_taps(0.0).size == 0
+    n = C.c_int()
+    assert zb.lib().zb_gaussian_taps(C.c_float(-1.0), None, 0, C.byref(n)) == 2  # InvalidSigma
+
+
+def test_rotate_bounds_match_oracle():
+    L = zb.lib()
+    rng = np.random.default_rng(0)
+    angles = [0.0, np.pi / 2, np.pi, 3 * np.pi / 2, 2 * np.pi, np.pi / 4, -0.3, 1e-7, 7.0] + list(rng.uniform(-10, 10, 20))
+    for a in angles:
+        for (r, c) in [(3, 4), (1080, 1920), (17, 1)]:
+            orr, occ = C.c_uint32(), C.c_uint32()
+            assert L.zb_rotate_bounds(r, c, C.c_float(a), C.byref(orr), C.byref(occ)) == 0
+            assert (orr.value, occ.value) == zo.rotate_bounds(r, c, np.float32(a)), (a, r, c)
+    orr, occ = C.c_uint32(), C.c_uint32()
+    L.zb_rotate_bounds(1080, 1920, C.c_float(np.float32(np.pi / 4)), C.byref(orr), C.byref(occ))
+    assert (orr.value, occ.value) == (2122, 2122)
+
+
+def _svd_prod(a, mode, with_v):
+    a = np.ascontiguousarray(a)
+    m, n = a.shape
+    modes = {"no_u": 0, "skinny_u": 1, "full_u": 2}
+    u = np.zeros((m, m if mode == "full_u" else n), a.dtype)
+    s = np.zeros(n, a.dtype)
+    v = np.zeros((n, n), a.dtype)
+    conv = C.c_uint64(99)
+    if a.dtype == np.float64:
+        P = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        rc = zb.lib().zb_svd_f64(P(a), m, n, modes[mode], int(with_v), P(u), P(s), P(v), C.byref(conv))
+    else:
+        P = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        rc = zb.lib().zb_svd_f32(P(a), m, n, modes[mode], int(with_v), P(u), P(s), P(v), C.byref(conv))
+    assert rc == 0
+    return u, s, v, conv.value
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(3, 3), (5, 4), (9, 9), (40, 17), (2, 2), (1, 1)])
+@pytest.mark.parametrize("mode", ["no_u", "skinny_u", "full_u"])
+def test_host_svd_is_bit_identical_to_oracle(dtype, shape, mode):
+    rng = np.random.default_rng(hash((shape, mode)) % 2**32)
+    a = rng.standard_normal(shape).astype(dtype)
+    u, s, v, conv = _svd_prod(a, mode, True)
+    uo, so, vo, rco = zo.svd(a, mode, True)
+    assert conv == rco == 0
+    assert np.array_equal(s, so)
+    assert np.array_equal(v, vo)
+    if mode != "no_u":
+        assert np.array_equal(u, uo)
+        k = min(shape)
+        tol = 1e-10 if dtype == np.float64 else 2e-4
+        assert np.allclose(u[:, :k] @ np.diag(s) @ v.T, a, atol=tol)
+
+
+def test_host_svd_rank_deficient_and_wikipedia():
+    a = np.array([[1, 0, 0, 0], [0, 0, 0, 2], [0, 3, 0, 0], [0, 0, 0, 0], [2, 0, 0, 0]], np.float64)
+    u, s, v, conv = _svd_prod(a, "full_u", True)
+    assert conv == 0 and np.allclose(s, [3, np.sqrt(5), 2, 0], atol=1e-12)
+    a = np.array([[1, 2, 3], [2, 4, 6], [1, 2, 3]], np.float64)
+    _, s, _, _ = _svd_prod(a, "full_u", True)
+    assert np.count_nonzero(s < np.sqrt(np.finfo(float).eps)) == 2
+    assert zb.lib().zb_svd_f64(None, 2, 3, 1, 0, None, None, None, None) != 0
+
+
+def test_argument_errors_are_reported_before_touching_the_device():
+    L = zb.lib()
+    a = np.zeros((4, 4), np.uint8)
+    b = np.zeros((4, 5), np.uint8)
+    ia, ib = zb.image._np_image(a), zb.image._np_image(b)
+    k = np.ones(3, np.float32) / 3
+    fp = k.ctypes.data_as(C.POINTER(C.c_float))
+    assert L.zb_conv_separable(ia, ib, 0, fp, 3, fp, 3, 2, None) == 1      # DimensionMismatch (image.zig:947)
+    assert L.zb_gaussian_blur(ia, ib, 0, C.c_float(1.0), None) == 1          # image.zig:962
+    assert L.zb_gaussian_blur(ia, ia, 0, C.c_float(-1.0), None) == 2         # InvalidSigma (image.zig:970)
+    assert L.zb_box_blur(ia, ib, 0, 1, None) == 1                            # image.zig:636
+    assert L.zb_sharpen(ia, ib, 0, 1, None) == 1                             # image.zig:786
+    assert L.zb_convolve(ia, ib, 0, fp, 1, 3, 0, None) == 1                  # image.zig:927
+    assert L.zb_conv_separable(ia, ia, 99, fp, 3, fp, 3, 2, None) == 3       # unsupported pixel type
+    f = C.c_void_p()
+    assert L.zb_fdm_create(C.byref(f), 1) == 3                               # fdm.zig:20: only u8 / Rgb / Rgba
+    assert L.zb_fdm_create(C.byref(f), 2) == 0
+    assert L.zb_fdm_update(f, None) == 10                                    # NoTargetSet (fdm.zig:142, :583-604)
+    assert L.zb_fdm_destroy(f) == 0
+    assert L.zb_tune(b"conv.stages", 7) == 5
+
+
+def test_scale_shapes_and_errors_host_logic():
+    # tests/resize.zig:258-298: factors .5 / 2 / 1.5 on 100x100 -> 50 / 200 / 150; errors for <= 0 and zero-size
+    img = zb.Image(None, zb.PixFmt.U8, 100, 100, 100)
+    from zignal_b200.image import _round_half_away
+    for f, n in [(0.5, 50), (2.0, 200), (1.5, 150)]:
+        assert int(_round_half_away(np.float32(100) * np.float32(f))) == n
+    with pytest.raises(zb.ZignalError) as e:
+        img.scale(0.0)
+    assert e.value.name == "InvalidScaleFactor"
+    with pytest.raises(zb.ZignalError) as e:
+        img.scale(0.001)
+    assert e.value.name == "InvalidDimensions"

@@ -1,0 +1,233 @@
+"""Parity of the CUDA convolution paths (generic two-pass, fused TMA kernel, dense 2-D) against the
+oracle, through the C ABI.  Integer formats: bit-exact.  f32: bit-exact for the generic path and the
+fused kernel's exact mode, <= 1e-5 relative (north_star tolerance) for the fused FFMA mode."""
+import numpy as np
+import pytest
+
+import oracle_lib as zo
+from gpu_utils import BORDERS, border_enum, golden, rand_image, rel_err, sha
+
+pytestmark = pytest.mark.gpu
+TOL_F32 = 1e-5  # BASELINE.json north_star: "within 1e-5 relative for f32 paths"
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import torch
+    assert torch.cuda.is_available()
+    import zignal_b200 as zb
+    yield zb
+    zb.lib().zb_set_exact_f32(0)
+    zb.lib().zb_set_force_generic(0)
+
+
+def _taps(rng, n):
+    k = (rng.random(n) + 0.05).astype(np.float32)
+    return (k / k.sum()).astype(np.float32)
+
+
+FORMATS = [((37, 53), np.uint8), ((31, 47, 3), np.uint8), ((40, 41, 4), np.uint8), ((37, 53), np.float32), ((33, 29, 4), np.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", FORMATS)
+@pytest.mark.parametrize("border", BORDERS)
+def test_generic_separable_bit_exact(zb, shape, dtype, border):
+    rng = np.random.default_rng(abs(hash((shape, str(dtype), border))) % 2**32)
+    zb.lib().zb_set_force_generic(1)
+    try:
+        for nx, ny in [(1, 1), (3, 5), (7, 7), (4, 6), (15, 15), (31, 3)]:
+            img = rand_image(rng, shape, dtype)
+            kx, ky = _taps(rng, nx), _taps(rng, ny)
+            got = zb.Image.from_numpy(img).convolve_separable(kx, ky, border_enum(zb, border)).to_numpy()
+            assert np.array_equal(got, zo.conv_separable(img, kx, ky, border)), (nx, ny)
+    finally:
+        zb.lib().zb_set_force_generic(0)
+
+
+def test_generic_separable_extreme_taps_use_wide_accumulators(zb):
+    rng = np.random.default_rng(5)
+    img = rand_image(rng, (20, 23), np.uint8)
+    for scale in (1.0, 300.0, 40000.0):  # i32 / mixed / i64 accumulator paths, saturated i32 temp
+        kx = (rng.standard_normal(5) * scale).astype(np.float32)
+        ky = (rng.standard_normal(5) * scale).astype(np.float32)
+        got = zb.Image.from_numpy(img).convolve_separable(kx, ky, zb.BorderMode.MIRROR).to_numpy()
+        assert np.array_equal(got, zo.conv_separable(img, kx, ky, "mirror")), scale
+
+
+def test_negligible_taps_follow_interior_only_skip_rule(zb):
+    # convolution.zig:459-467: |k| < 1e-10 skipped in the interior only; finite data -> identical either way
+    rng = np.random.default_rng(6)
+    img = rand_image(rng, (30, 40, 4), np.float32)
+    k = np.array([0.25, 1e-12, 0.5, 0.0, 0.25], np.float32)
+    got = zb.Image.from_numpy(img).convolve_separable(k, k, zb.BorderMode.MIRROR).to_numpy()
+    assert zb.lib().zb_last_kernel().decode().startswith("sep_generic")
+    assert np.array_equal(got, zo.conv_separable(img, k, k, "mirror"))
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 64), (96, 520), (300, 777), (513, 1030), (40, 16), (257, 263)])
+@pytest.mark.parametrize("border", BORDERS)
+def test_fused_rgbaf32_exact_and_fma(zb, rows, cols, border):
+    rng = np.random.default_rng(rows * 131 + cols)
+    L = zb.lib()
+    for half in (1, 2, 4, 7, 8):
+        img = rand_image(rng, (rows, cols, 4), np.float32)
+        k = _taps(rng, 2 * half + 1)
+        want = zo.conv_separable(img, k, k, border)
+        dev = zb.Image.from_numpy(img)
+        L.zb_set_exact_f32(1)
+        got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+        assert L.zb_last_kernel().decode() == "fused_sep_rgbaf32_exact"
+        assert np.array_equal(got, want), ("exact", half)
+        L.zb_set_exact_f32(0)
+        for stages in (2, 3):
+            for f2 in (0, 1):
+                L.zb_tune(b"conv.stages", stages)
+                L.zb_tune(b"conv.f32x2", f2)
+                got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+                assert L.zb_last_kernel().decode() == "fused_sep_rgbaf32"
+                assert rel_err(got, want) <= TOL_F32, ("fma", half, stages, f2)
+    L.zb_tune(b"conv.stages", 3)
+    L.zb_tune(b"conv.f32x2", 0)
+
+
+def test_fused_handles_views_even_and_unequal_kernels(zb):
+    rng = np.random.default_rng(7)
+    L = zb.lib()
+    img = rand_image(rng, (200, 300, 4), np.float32)
+    big = zb.Image.from_numpy(img)
+    v = big.view(zb.Rectangle(8, 5, 290, 190))
+    crop = np.ascontiguousarray(img[5:190, 8:290])
+    out_big = zb.Image.from_numpy(np.full((220, 310, 4), 7.0, np.float32))
+    out_v = out_big.view(zb.Rectangle(3, 2, 285, 187))
+    for kx, ky in [(_taps(rng, 6), _taps(rng, 5)), (_taps(rng, 3), _taps(rng, 15)), (_taps(rng, 16), _taps(rng, 2))]:
+        L.zb_set_exact_f32(1)
+        v.convolve_separable(kx, ky, zb.BorderMode.MIRROR, out=out_v)
+        assert L.zb_last_kernel().decode() == "fused_sep_rgbaf32_exact"
+        got_full = out_big.to_numpy()
+        assert np.array_equal(got_full[2:187, 3:285], zo.conv_separable(crop, kx, ky, "mirror"))
+        mask = np.ones(got_full.shape[:2], bool)
+        mask[2:187, 3:285] = False
+        assert np.all(got_full[mask] == 7.0), "pixels outside the destination view were touched"
+    L.zb_set_exact_f32(0)
+
+
+def test_in_place_separable(zb):
+    rng = np.random.default_rng(8)
+    for shape, dtype in [((64, 70, 4), np.float32), ((50, 61, 4), np.uint8)]:
+        img = rand_image(rng, shape, dtype)
+        k = _taps(rng, 7)
+        dev = zb.Image.from_numpy(img)
+        dev.convolve_separable(k, k, zb.BorderMode.REPLICATE, out=dev)
+        assert np.array_equal(dev.to_numpy(), zo.conv_separable(img, k, k, "replicate"))
+
+
+@pytest.mark.parametrize("shape,dtype", [((37, 53), np.uint8), ((31, 47, 3), np.uint8), ((40, 41, 4), np.uint8), ((37, 53), np.float32)])
+@pytest.mark.parametrize("border", BORDERS)
+def test_dense_convolve_bit_exact(zb, shape, dtype, border):
+    rng = np.random.default_rng(abs(hash((shape, border))) % 2**32)
+    for kh, kw in [(3, 3), (5, 3), (1, 7), (4, 4), (15, 15)]:
+        img = rand_image(rng, shape, dtype)
+        k = rng.standard_normal((kh, kw)).astype(np.float32) / (kh * kw)
+        got = zb.Image.from_numpy(img).convolve(k, border_enum(zb, border)).to_numpy()
+        assert np.array_equal(got, zo.convolve(img, k, border)), (kh, kw)
+
+
+def test_reference_kats_through_the_gpu(zb):
+    ident = np.zeros((3, 3), np.float32)
+    ident[1, 1] = 1
+    rng = np.random.default_rng(9)
+    for shape in [(5, 5), (7, 9, 3), (6, 8, 4)]:  # filters.zig:370-398, :662-699
+        img = rand_image(rng, shape, np.uint8)
+        assert np.array_equal(zb.Image.from_numpy(img).convolve(ident, zb.BorderMode.ZERO).to_numpy(), img)
+    img = np.full((5, 5, 3), 255, np.uint8)  # filters.zig:571-600
+    out = zb.Image.from_numpy(img).convolve(np.full((3, 3), 1 / 9, np.float32), zb.BorderMode.ZERO).to_numpy()
+    assert abs(int(out[0, 0, 0]) - 113) <= 1
+    img = np.ones((10, 20), np.uint8)  # filters.zig:1302-1342
+    k = np.array([[1, 1, 1], [1, 0, 1], [1, 1, 1]], np.float32)
+    out = zb.Image.from_numpy(img).convolve(k, zb.BorderMode.ZERO).to_numpy()
+    assert np.all(out[1:9, 0] == 5) and np.all(out[1:9, 1] == 8)
+    img = np.zeros((7, 7), np.float32)  # filters.zig:469-491
+    img[3, 3] = 1
+    out = zb.Image.from_numpy(img).convolve_separable([0.25, 0.5, 0.25], [0.25, 0.5, 0.25], zb.BorderMode.ZERO).to_numpy()
+    assert out[3, 3] == np.float32(0.25) and out[3, 2] == np.float32(0.125)
+    img = rand_image(rng, (9, 9, 4), np.uint8)  # filters.zig:1159-1180: sigma == 0 is a copy
+    assert np.array_equal(zb.Image.from_numpy(img).gaussian_blur(0.0).to_numpy(), img)
+    with pytest.raises(zb.ZignalError) as e:
+        zb.Image.from_numpy(img).gaussian_blur(-1.0)
+    assert e.value.name == "InvalidSigma"
+
+
+@pytest.mark.parametrize("shape,dtype", FORMATS)
+def test_gaussian_blur_matches_oracle(zb, shape, dtype):
+    rng = np.random.default_rng(10)
+    img = rand_image(rng, shape, dtype)
+    for sigma in (0.5, 1.0, 2.25, 4.0):
+        got = zb.Image.from_numpy(img).gaussian_blur(sigma).to_numpy()
+        want = zo.gaussian_blur(img, sigma)
+        if dtype == np.uint8:
+            assert np.array_equal(got, want), sigma
+        else:
+            assert rel_err(got, want) <= TOL_F32, sigma
+
+
+def test_host_twins_with_strided_views_and_sentinels(zb):
+    rng = np.random.default_rng(11)
+    base = rand_image(rng, (40, 50, 4), np.uint8)
+    src = base[3:33, 4:44]                      # strided host view
+    outbuf = np.full((44, 60, 4), 0xAA, np.uint8)
+    dst = outbuf[5:35, 6:46]
+    taps = zb.gaussian_taps(1.4)
+    zb.host_conv_separable(src, taps, taps, zb.BorderMode.MIRROR, out=dst)
+    assert np.array_equal(dst, zo.conv_separable(np.ascontiguousarray(src), taps, taps, "mirror"))
+    mask = np.ones(outbuf.shape[:2], bool)
+    mask[5:35, 6:46] = False
+    assert np.all(outbuf[mask] == 0xAA)
+    imgf = rand_image(rng, (70, 90, 4), np.float32)
+    got = zb.host_gaussian_blur(imgf, 2.25)
+    assert rel_err(got, zo.gaussian_blur(imgf, 2.25)) <= TOL_F32
+    k = rng.standard_normal((3, 3)).astype(np.float32)
+    assert np.array_equal(zb.host_convolve(src, k, zb.BorderMode.WRAP), zo.convolve(np.ascontiguousarray(src), k, "wrap"))
+
+
+def test_golden_fixtures(zb):
+    g = golden()
+    L = zb.lib()
+    for name, case in g["conv"].items():
+        rng = np.random.default_rng(case["seed"])
+        dtype = np.uint8 if case["dtype"] == "u8" else np.float32
+        img = rand_image(rng, tuple(case["shape"]), dtype)
+        taps = zb.gaussian_taps(case["sigma"])
+        L.zb_set_exact_f32(1)
+        got = zb.Image.from_numpy(img).gaussian_blur(case["sigma"]).to_numpy()
+        L.zb_set_exact_f32(0)
+        assert sha(img) == case["input_sha256"], name
+        assert sha(got) == case["output_sha256"], name
+
+
+def test_full_size_c2_properties(zb):
+    """BASELINE config 2: 15x15 Gaussian on 8192x8192 RGBA f32.  The oracle would need minutes for the whole
+    image, so full size is checked through size-independent properties: a row band cropped with its halo must
+    equal the oracle on that band (interior rows are independent of the rest), image borders likewise, and a
+    constant image must stay constant."""
+    import torch
+    R = C = 8192
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand(R, C, 4, device="cuda", dtype=torch.float32, generator=gen)
+    src = zb.Image.from_tensor(x)
+    taps = zb.gaussian_taps(2.25)
+    assert taps.size == 15
+    out = src.gaussian_blur(2.25).tensor()
+    assert zb.lib().zb_last_kernel().decode() == "fused_sep_rgbaf32"
+    for (r0, r1, c0, c1) in [(0, 40, 0, 600), (4000, 4060, 3800, 4500), (R - 40, R, C - 600, C), (250, 270, 0, C)]:
+        # halo of 7 around the window, clipped at the image border (where the mirror rule then matches the oracle's)
+        hr0, hr1, hc0, hc1 = max(r0 - 7, 0), min(r1 + 7, R), max(c0 - 7, 0), min(c1 + 7, C)
+        crop = x[hr0:hr1, hc0:hc1].cpu().numpy()
+        want = zo.conv_separable(crop, taps, taps, "mirror")
+        a, b = r0 - hr0, c0 - hc0
+        # only compare pixels whose support lies in the crop or at a true image border
+        sub_w = want[a:a + (r1 - r0), b:b + (c1 - c0)]
+        sub_g = out[r0:r1, c0:c1].cpu().numpy()
+        assert rel_err(sub_g, sub_w) <= TOL_F32, (r0, c0)
+    const = torch.full((R, C, 4), 0.625, device="cuda", dtype=torch.float32)
+    oc = zb.Image.from_tensor(const).gaussian_blur(2.25).tensor()
+    assert float((oc - 0.625).abs().max()) <= 0.625 * 1e-5

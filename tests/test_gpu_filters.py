@@ -1,0 +1,109 @@
+"""Box blur / sharpen / integral image on the GPU vs the oracle: bit-exact for every pixel format,
+including images whose f32 summed-area table exceeds 2^24 (where the summation order is part of the
+result, reference integral.zig:41-78)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as zo
+from gpu_utils import rand_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import torch
+    assert torch.cuda.is_available()
+    import zignal_b200 as zb
+    return zb
+
+
+CASES = [((5, 5), np.uint8), ((21, 13), np.uint8), ((64, 70, 3), np.uint8), ((33, 47, 4), np.uint8), ((40, 37), np.float32),
+         ((31, 29, 4), np.float32), ((1, 9), np.uint8), ((9, 1), np.uint8), ((600, 700), np.uint8), ((520, 530, 4), np.uint8)]
+
+
+@pytest.mark.parametrize("shape,dtype", CASES)
+@pytest.mark.parametrize("radius", [1, 2, 3, 7, 50])
+def test_box_blur_bit_exact(zb, shape, dtype, radius):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1] + radius)
+    img = rand_image(rng, shape, dtype)
+    if shape[0] >= 500 and dtype == np.uint8:
+        img |= 0xC0  # bright: SAT values pass 2^24, f32 adds become inexact
+    got = zb.Image.from_numpy(img).box_blur(radius).to_numpy()
+    assert np.array_equal(got, zo.box_blur(img, radius))
+
+
+@pytest.mark.parametrize("shape,dtype", CASES)
+@pytest.mark.parametrize("radius", [1, 3, 9])
+def test_sharpen_bit_exact(zb, shape, dtype, radius):
+    rng = np.random.default_rng(shape[0] * 77 + shape[1] + radius)
+    img = rand_image(rng, shape, dtype)
+    got = zb.Image.from_numpy(img).sharpen(radius).to_numpy()
+    assert np.array_equal(got, zo.sharpen(img, radius))
+
+
+def test_integral_plane_bit_exact(zb):
+    import torch
+    rng = np.random.default_rng(3)
+    for shape, dtype in [((21, 13), np.uint8), ((300, 517), np.uint8), ((129, 65), np.float32), ((1000, 1100), np.uint8)]:
+        img = rand_image(rng, shape, dtype)
+        if shape[0] >= 1000:
+            img |= 0xF0
+        dev = zb.Image.from_numpy(img)
+        sat = torch.empty(shape, dtype=torch.float32, device="cuda")
+        a = dev._zb()
+        zb._ffi.check(zb.lib().zb_integral_plane(a, int(dev.pixfmt), C.cast(sat.data_ptr(), C.POINTER(C.c_float)), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(sat.cpu().numpy(), zo.integral_plane(img))
+    ones = np.ones((21, 13), np.uint8)  # tests/integral.zig:11-28
+    r, c = np.mgrid[0:21, 0:13]
+    assert np.array_equal(zo.integral_plane(ones), ((r + 1) * (c + 1)).astype(np.float32))
+
+
+def test_reference_kats_and_views(zb):
+    img = np.full((5, 5), 128, np.uint8)  # filters.zig:87-103
+    assert np.all(zb.Image.from_numpy(img).box_blur(1).to_numpy() == 128)
+    img = np.full((12, 12), 200, np.uint8)  # :186-207
+    assert np.all(zb.Image.from_numpy(img).box_blur(3).to_numpy() == 200)
+    img = np.full((5, 5), 100, np.uint8)  # :327-343
+    assert np.all(zb.Image.from_numpy(img).sharpen(1).to_numpy() == 100)
+    rng = np.random.default_rng(4)
+    for size in (8, 32):  # :234-264 alpha preserved
+        im = rand_image(rng, (size, size, 4), np.uint8)
+        im[..., 3] = 255
+        for r in (1, 3):
+            assert np.all(zb.Image.from_numpy(im).box_blur(r).to_numpy()[..., 3] == 255)
+    # radius 0 = copy, views on both sides (:50-75, :105-126)
+    base = rand_image(rng, (30, 40, 3), np.uint8)
+    dev = zb.Image.from_numpy(base)
+    v = dev.view(zb.Rectangle(5, 4, 35, 24))
+    out_big = zb.Image.from_numpy(np.full((30, 40, 3), 9, np.uint8))
+    ov = out_big.view(zb.Rectangle(2, 3, 32, 23))
+    v.box_blur(0, out=ov)
+    assert np.array_equal(out_big.to_numpy()[3:23, 2:32], base[4:24, 5:35])
+    v.box_blur(2, out=ov)
+    full = out_big.to_numpy()
+    assert np.array_equal(full[3:23, 2:32], zo.box_blur(np.ascontiguousarray(base[4:24, 5:35]), 2))
+    mask = np.ones((30, 40), bool)
+    mask[3:23, 2:32] = False
+    assert np.all(full[mask] == 9)
+    # in place (examples/src/face_alignment.zig:95,97 use boxBlur / sharpen in place)
+    img = rand_image(rng, (50, 60, 4), np.uint8)
+    d = zb.Image.from_numpy(img)
+    d.box_blur(2, out=d)
+    assert np.array_equal(d.to_numpy(), zo.box_blur(img, 2))
+    d = zb.Image.from_numpy(img)
+    d.sharpen(2, out=d)
+    assert np.array_equal(d.to_numpy(), zo.sharpen(img, 2))
+    # host twins
+    assert np.array_equal(zb.host_box_blur(img, 3), zo.box_blur(img, 3))
+    assert np.array_equal(zb.host_sharpen(img, 3), zo.sharpen(img, 3))
+
+
+def test_config1_box_blur_512_u8(zb):
+    """BASELINE config 1: 3x3 box blur (radius 1) on 512x512 u8."""
+    rng = np.random.default_rng(1)
+    img = rand_image(rng, (512, 512), np.uint8)
+    assert np.array_equal(zb.Image.from_numpy(img).box_blur(1).to_numpy(), zo.box_blur(img, 1))

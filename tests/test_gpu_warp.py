@@ -1,0 +1,141 @@
+"""Image.rotate / rotateInto / warp on the GPU vs the oracle (bit-exact for u8 formats given identical
+cos/sin inputs; f32 expected bit-identical as well)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as zo
+from gpu_utils import BORDERS, METHODS, border_enum, method_enum, rand_image, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import torch
+    assert torch.cuda.is_available()
+    import zignal_b200 as zb
+    return zb
+
+
+FORMATS = [((23, 31), np.uint8), ((20, 27, 3), np.uint8), ((25, 33, 4), np.uint8), ((19, 22), np.float32), ((17, 21, 4), np.float32)]
+
+
+def _cs(angle):
+    a = np.float32(angle)
+    return np.float32(np.cos(np.float64(a))), np.float32(np.sin(np.float64(a)))
+
+
+@pytest.mark.parametrize("shape,dtype", FORMATS)
+@pytest.mark.parametrize("method", METHODS)
+def test_rotate_general(zb, shape, dtype, method):
+    rng = np.random.default_rng(METHODS.index(method) + shape[0])
+    img = rand_image(rng, shape, dtype)
+    dev = zb.Image.from_numpy(img)
+    for angle in (np.pi / 4, 0.3, -1.1, 2.5):
+        for border in BORDERS:
+            cs = _cs(angle)
+            got = dev.rotate(np.float32(angle), method_enum(zb, method), border_enum(zb, border), cos_sin=cs).to_numpy()
+            want = zo.rotate(img, np.float32(angle), method, border, cos_sin=cs)
+            assert got.shape == want.shape
+            if dtype == np.uint8:
+                assert np.array_equal(got, want), (angle, border)
+            else:
+                assert rel_err(got, want) <= 1e-5 and np.array_equal(got, want), (angle, border)
+
+
+@pytest.mark.parametrize("shape,dtype", FORMATS)
+def test_rotate_orthogonal_fast_paths(zb, shape, dtype):
+    rng = np.random.default_rng(5)
+    img = rand_image(rng, shape, dtype)
+    dev = zb.Image.from_numpy(img)
+    for k, angle in enumerate([0.0, np.pi / 2, np.pi, 3 * np.pi / 2, 2 * np.pi, -np.pi / 2]):
+        got = dev.rotate(np.float32(angle)).to_numpy()
+        want = zo.rotate(img, np.float32(angle))
+        assert np.array_equal(got, want), angle
+    # rotateInto a larger / smaller destination: centred content, zeroed margins only when an offset exists
+    for out_shape in [(shape[0] + 6, shape[1] + 4), (shape[0] - 3, shape[1] + 5), (shape[1] + 1, shape[0])]:
+        for angle in (0.0, np.pi / 2, np.pi):
+            fill = rand_image(rng, out_shape + tuple(shape[2:]), dtype)
+            out = zb.Image.from_numpy(fill)
+            dev.rotate_into(out, np.float32(angle))
+            want = zo.rotate_into(img, fill.copy(), np.float32(angle))
+            assert np.array_equal(out.to_numpy(), want), (out_shape, angle)
+
+
+def test_rotate_kats(zb):
+    img = np.arange(1, 13, dtype=np.uint8).reshape(3, 4)  # tests/transforms.zig:160-209
+    dev = zb.Image.from_numpy(img)
+    for angle, k in [(0.0, 0), (np.pi / 2, 1), (np.pi, 2), (3 * np.pi / 2, 3)]:
+        assert np.array_equal(dev.rotate(np.float32(angle), zb.Interpolation.BILINEAR, zb.BorderMode.MIRROR).to_numpy(), np.rot90(img, k))
+    chk = (np.indices((10, 10)).sum(0) % 2 == 0).astype(np.uint8) * 255  # :211-229
+    out = zb.Image.from_numpy(chk).rotate(np.float32(np.pi / 4), zb.Interpolation.BILINEAR, zb.BorderMode.MIRROR)
+    assert out.rows > 10 and out.cols > 10
+
+
+def test_rotate_batch_and_config4_shape(zb):
+    """BASELINE config 4 (batch of 1920x1080 RGBA, 45 degrees, bilinear, zero border) on a small batch: every image of the
+    batch must equal the oracle's single-image result; output shape 2122x2122."""
+    import torch
+    n, R, Cc = 3, 1080, 1920
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randint(0, 256, (n, R, Cc, 4), device="cuda", dtype=torch.uint8, generator=gen)
+    angle = np.float32(np.pi / 4)
+    cs = _cs(angle)
+    orows, ocols = zb.Image.from_tensor(x[0]).rotate_bounds(angle)
+    assert (orows, ocols) == (2122, 2122)
+    y = torch.empty((n, orows, ocols, 4), device="cuda", dtype=torch.uint8)
+    src0 = zb.Image.from_tensor(x[0])._zb()
+    dst0 = zb.Image.from_tensor(y[0])._zb()
+    zb._ffi.check(zb.lib().zb_rotate_into_batch(src0, R * Cc, dst0, orows * ocols, n, int(zb.PixFmt.RGBA8), C.c_float(angle), C.c_float(cs[0]),
+                                                C.c_float(cs[1]), int(zb.Interpolation.BILINEAR), C.c_float(1 / 3), C.c_float(1 / 3),
+                                                int(zb.BorderMode.ZERO), zb.image.current_stream()))
+    torch.cuda.synchronize()
+    for i in (0, n - 1):
+        want = zo.rotate(x[i].cpu().numpy(), angle, "bilinear", "zero", cos_sin=cs)
+        assert np.array_equal(y[i].cpu().numpy(), want), i
+
+
+class _Xf:
+    def __init__(self, kind, m):
+        self.kind, self.m = kind, np.asarray(m, np.float32)
+
+    def as_f32(self):
+        return {"similarity": 0, "affine": 1, "projective": 2}[self.kind], self.m
+
+
+@pytest.mark.parametrize("shape,dtype", FORMATS)
+@pytest.mark.parametrize("method", METHODS)
+def test_warp(zb, shape, dtype, method):
+    rng = np.random.default_rng(METHODS.index(method) + 100)
+    img = rand_image(rng, shape, dtype)
+    dev = zb.Image.from_numpy(img)
+    cases = [("affine", [1, 0, 0, 1, 0, 0]), ("affine", [0.9, -0.2, 0.25, 1.1, 1.5, -2.0]), ("similarity", [0.7, 0.7, -0.7, 0.7, 3, 4]),
+             ("projective", [1.0, 0.05, 2, -0.03, 0.95, 1, 1e-3, -2e-3, 1]), ("projective", [2, 0, 0, 0, 2, 0, 0, 0, 2]),
+             ("projective", [1, 0, 0, 0, 1, 0, 0, 0, 0])]
+    for kind, m in cases:
+        for out_shape in [shape[:2], (shape[0] + 5, shape[1] - 3)]:
+            out = zb.Image.init(out_shape[0], out_shape[1], dev.pixfmt)
+            got = dev.warp(out, _Xf(kind, m), method_enum(zb, method)).to_numpy()
+            want = zo.warp(img, np.zeros(out_shape + tuple(shape[2:]), dtype), kind, m, method)
+            if dtype == np.uint8:
+                assert np.array_equal(got, want), (kind, m)
+            else:
+                assert rel_err(got, want) <= 1e-5 and np.array_equal(got, want), (kind, m)
+
+
+def test_host_rotate_and_warp(zb):
+    rng = np.random.default_rng(6)
+    img = rand_image(rng, (30, 40, 4), np.uint8)
+    angle = np.float32(0.6)
+    got = zb.host_rotate(img, angle)
+    # the library computes cos/sin with the host libm, exactly like the oracle's default
+    import math
+    cs = (np.float32(math.cos(float(angle))), np.float32(math.sin(float(angle))))
+    want = zo.rotate(img, angle, "bilinear", "zero")
+    assert got.shape == want.shape
+    assert np.mean(got != want) < 1e-3  # cosf/sinf (library) vs numpy cos (oracle default) may differ by an ulp
+    out = np.zeros((25, 35, 4), np.uint8)
+    m = [0.9, -0.2, 0.25, 1.1, 1.5, -2.0]
+    assert np.array_equal(zb.host_warp(img, out, _Xf("affine", m)), zo.warp(img, np.zeros_like(out), "affine", m, "bilinear"))

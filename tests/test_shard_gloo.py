@@ -1,0 +1,87 @@
+"""world_size-2 (and 3) gloo tests of the multi-GPU host logic on CPU: the halo exchange + global-border fill
+must let every rank reproduce its rows of the single-image result, and the moment all-reduce must equal
+the global moments.  The local operator here is the CPU oracle (the CUDA kernels cannot run without a GPU);
+what is under test is zignal_b200.shard."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as zo
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, border, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zignal_b200 import BorderMode, PixFmt, shard
+        rows, cols, halo = 24, 19, 7
+        rng = np.random.default_rng(42)
+        full = rng.random((rows * world, cols, 4), dtype=np.float32)
+        taps = zo.gaussian_taps(2.25)
+        want = zo.conv_separable(full, taps, taps, border)
+        blk = shard.RowBlock(rows, cols, PixFmt.RGBAF32, halo, "cpu", rank, world)
+        blk.interior_tensor().copy_(torch.from_numpy(full[rank * rows:(rank + 1) * rows]))
+        blk.exchange_halo(BorderMode[border.upper()])
+        ext = blk.extended_tensor().numpy()
+        out_ext = zo.conv_separable(np.ascontiguousarray(ext), taps, taps, border)
+        got = out_ext[halo:halo + rows]
+        ok_conv = bool(np.array_equal(got, want[rank * rows:(rank + 1) * rows]))
+        # fdm moments: per-shard integer sums, one all-reduce
+        img = np.random.default_rng(7).integers(0, 256, (rows * world, cols, 3), dtype=np.uint8)
+        part = img[rank * rows:(rank + 1) * rows].reshape(-1, 3).astype(np.int64)
+        r, g, b = part[:, 0], part[:, 1], part[:, 2]
+        sums = np.array([len(r), r.sum(), g.sum(), b.sum(), (r * r).sum(), (r * g).sum(), (r * b).sum(), (g * g).sum(), (g * b).sum(),
+                         (b * b).sum(), np.count_nonzero((r != g) | (g != b))], dtype=np.uint64)
+        tot = shard.allreduce_moments(sums)
+        allp = img.reshape(-1, 3).astype(np.int64)
+        ok_mom = int(tot[0]) == allp.shape[0] and int(tot[5]) == int((allp[:, 0] * allp[:, 1]).sum()) and int(tot[9]) == int((allp[:, 2] ** 2).sum())
+        lo, hi = shard.split_batch(10, rank, world)
+        q.put((rank, ok_conv, ok_mom, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("border", ["mirror", "zero", "replicate", "wrap"])
+def test_row_block_halo_exchange_reproduces_single_image_result(world, border):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, border, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert all(ok for _, ok, _, _ in res), f"conv rows differ: {res}"
+    assert all(ok for _, _, ok, _ in res), f"moment all-reduce differs: {res}"
+    spans = [s for *_, s in res]
+    assert spans[0][0] == 0 and spans[-1][1] == 10 and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_single_rank_wrap_and_mirror_fill():
+    from zignal_b200 import BorderMode, PixFmt, shard
+    rng = np.random.default_rng(1)
+    full = rng.random((20, 9, 4), dtype=np.float32)
+    taps = zo.gaussian_taps(1.0)
+    for border in ("mirror", "wrap", "replicate", "zero"):
+        blk = shard.RowBlock(20, 9, PixFmt.RGBAF32, 3, "cpu", 0, 1)
+        blk.interior_tensor().copy_(torch.from_numpy(full))
+        blk.exchange_halo(BorderMode[border.upper()])
+        out = zo.conv_separable(np.ascontiguousarray(blk.extended_tensor().numpy()), taps, taps, border)[3:23]
+        assert np.array_equal(out, zo.conv_separable(full, taps, taps, border)), border

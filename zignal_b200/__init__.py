@@ -8,4 +8,6 @@ from .image import (BorderMode, Image, Interpolation, PixFmt, Rectangle, gaussia
                     host_conv_separable, host_convolve, host_gaussian_blur, host_resize, host_rotate, host_sharpen,
                     host_warp)
 
+from . import fdm, matrix, pca  # noqa: F401,E402
+
 __version__ = "0.1.0"

@@ -117,6 +117,7 @@ def _declare(L):
         "zb_host_fdm_match": ([img, img, i], i),
         "zb_set_exact_f32": ([i], i),
         "zb_set_force_generic": ([i], i),
+        "zb_tune": ([C.c_char_p, i], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name, None)

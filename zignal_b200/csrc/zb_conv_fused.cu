@@ -43,11 +43,13 @@ constexpr int RING_BYTES = RING_ROWS * RING_ROW_BYTES;  // 98304
 constexpr int NTHREADS = 256;
 constexpr int MAX_HALF = 8;
 constexpr int MAXK = 2 * MAX_HALF + 1;
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + RING_BYTES + 64 + 1024;
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + RING_BYTES + 64 + 1024; }
 
 struct FusedParams {
     float kx[MAXK];
     float ky[MAXK];
+    unsigned long long kx2[MAXK];  // {k, k} bit patterns for the packed f32x2 FMA
+    unsigned long long ky2[MAXK];
     const float4* src;
     float4* dst;
     unsigned long long src_pitch_px, dst_pitch_px;
@@ -67,6 +69,24 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+struct U2 {  // one RGBA f32 pixel as two packed f32x2 registers
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ U2 lds128_u2(uint32_t addr) {
+    U2 v;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128_u2(uint32_t addr, const U2& v) {
+    asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg128_cs_u2(void* ptr, const U2& v) {
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(ptr), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void mac_u2(U2& acc, const U2& v, unsigned long long k2) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.lo) : "l"(v.lo), "l"(k2));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.hi) : "l"(v.hi), "l"(k2));
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -127,24 +147,46 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, const 
     }
 }
 
-template <int HALF, bool EXACT>
+// F2: use the packed fma.rn.f32x2 (FFMA2) -- two lanes per issued instruction, same IEEE result as FFMA.
+template <int HALF, bool EXACT, int STAGES, bool F2>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+    static_assert(!(EXACT && F2), "exact mode is scalar");
     constexpr int K = 2 * HALF + 1;
     constexpr int NLOAD = CHUNK + 2 * HALF;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t ring = smem0 + 2 * STAGE_BYTES;
+    const uint32_t ring = smem0 + STAGES * STAGE_BYTES;
     const uint32_t bar0 = ring + RING_BYTES;
 
     const int tid = threadIdx.x;
+    const int n_units = p.n_strips * p.n_bands;
+
+    // ---- producer (thread 0): a cursor over this CTA's (unit, chunk) sequence, STAGES chunks ahead ----
+    int pu = blockIdx.x, pi = 0;
+    uint32_t pcount = 0;
+    auto produce = [&]() {
+        if (pu >= n_units) return;
+        const int band = pu / p.n_strips, strip = pu - band * p.n_strips;
+        const int ra = band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.rows);
+        const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
+        const uint32_t st = pcount % STAGES;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar0 + 8 * st, STAGE_BYTES);
+        tma_load_3d(smem0 + st * STAGE_BYTES, &tmap, 0, strip * (TW / 8) - 1, ra - CHUNK + CHUNK * pi, bar0 + 8 * st);
+        ++pcount;
+        if (++pi == n_in) { pi = 0; pu += gridDim.x; }
+    };
+
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
+        for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
         fence_barrier_init();
     }
     __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < STAGES; ++i) produce();
 
     // H-pass role: lane -> pixel group (8 consecutive pixels), warp -> row of the chunk
     const int ht = tid & 31, hr = tid >> 5;
@@ -154,8 +196,7 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     const uint32_t h_ring_col = ring + (uint32_t)ht * 128u;
     const uint32_t h_key = (uint32_t)ht & 7u;
 
-    uint32_t uses0 = 0, uses1 = 0;  // completed waits per stage barrier (phase parity)
-    const int n_units = p.n_strips * p.n_bands;
+    uint32_t ccount = 0;  // chunks consumed by this CTA
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
@@ -166,21 +207,10 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         const int n_in = n_out + 2;                       // input chunks: chunk i covers rows [ra-8+8i, ra+8i)
         const int g0 = x0 / 8 - 1;
 
-        if (tid == 0) {
-            fence_proxy_async();
-            for (int i = 0; i < 2; ++i) {
-                mbar_arrive_expect_tx(bar0 + 8 * i, STAGE_BYTES);
-                tma_load_3d(smem0 + STAGE_BYTES * i, &tmap, 0, g0, ra - CHUNK + CHUNK * i, bar0 + 8 * i);
-            }
-        }
-
-        for (int i = 0; i < n_in; ++i) {
-            const int st = i & 1;
-            const uint32_t stage = smem0 + (uint32_t)(st * STAGE_BYTES);
-            const uint32_t bar = bar0 + (uint32_t)(st * 8);
-            const uint32_t parity = (st ? uses1 : uses0) & 1u;
-            while (!mbar_try_wait(bar, parity)) {}
-            if (st) uses1++; else uses0++;
+        for (int i = 0; i < n_in; ++i, ++ccount) {
+            const uint32_t st = ccount % STAGES;
+            const uint32_t stage = smem0 + st * STAGE_BYTES;
+            while (!mbar_try_wait(bar0 + 8 * st, (ccount / STAGES) & 1u)) {}
             const int y0 = ra - CHUNK + CHUNK * i;
             const bool fix = (p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows)) || (p.fix_left && g0 < 0) ||
                              (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
@@ -191,58 +221,95 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 
             // ---------------- H(i): stage -> ring rows [(i%3)*8, +8) ----------------
             {
-                float4 acc[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const uint32_t line0 = (uint32_t)(hr * G + ht);
-#pragma unroll
-                for (int j = 0; j < NLOAD; ++j) {
-                    const int pidx = 8 - HALF + j;  // pixel index relative to the start of group `ht` of the stage row
-                    const uint32_t line = line0 + (uint32_t)(pidx >> 3);
-                    const float4 v = lds128(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const int ti = j - o;
-                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.kx[ti]);
-                    }
-                }
                 const uint32_t rrow = h_ring_col + (uint32_t)(((i % 3) * CHUNK + hr) * RING_ROW_BYTES);
+                if constexpr (F2) {
+                    U2 acc[8];
 #pragma unroll
-                for (int o = 0; o < 8; ++o) sts128(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                    for (int o = 0; o < 8; ++o) acc[o].lo = acc[o].hi = 0ull;
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        const int pidx = 8 - HALF + j;
+                        const uint32_t line = line0 + (uint32_t)(pidx >> 3);
+                        const U2 v = lds128_u2(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac_u2(acc[o], v, p.kx2[ti]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sts128_u2(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                } else {
+                    float4 acc[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        const int pidx = 8 - HALF + j;  // pixel index relative to the start of group `ht` of the stage row
+                        const uint32_t line = line0 + (uint32_t)(pidx >> 3);
+                        const float4 v = lds128(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.kx[ti]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sts128(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                }
             }
             __syncthreads();  // ring slot complete; stage `st` is free again
 
-            if (tid == 0 && i + 2 < n_in) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                tma_load_3d(stage, &tmap, 0, g0, ra - CHUNK + CHUNK * (i + 2), bar);
-            }
+            if (tid == 0) produce();  // refill the stage just drained (the chunk STAGES ahead, possibly of the next unit)
 
             // ---------------- V(i-2): ring -> global rows [ra+8c, ra+8c+8) ----------------
             if (i >= 2) {
                 const int c = i - 2;
-                float4 acc[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
-#pragma unroll
-                for (int j = 0; j < NLOAD; ++j) {
-                    uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
-                    if (sr >= RING_ROWS) sr -= RING_ROWS;
-                    const float4 v = lds128(v_col + sr * (uint32_t)RING_ROW_BYTES);
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const int ti = j - o;
-                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
-                    }
-                }
                 const int x = x0 + vx;
-                if (x < p.cols) {
-                    const int yb = ra + CHUNK * c;
-                    float4* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+                const int yb = ra + CHUNK * c;
+                float4* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+                if constexpr (F2) {
+                    U2 acc[8];
 #pragma unroll
-                    for (int o = 0; o < 8; ++o)
-                        if (yb + o < rb) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
+                    for (int o = 0; o < 8; ++o) acc[o].lo = acc[o].hi = 0ull;
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                        if (sr >= RING_ROWS) sr -= RING_ROWS;
+                        const U2 v = lds128_u2(v_col + sr * (uint32_t)RING_ROW_BYTES);
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac_u2(acc[o], v, p.ky2[ti]);
+                        }
+                    }
+                    if (x < p.cols) {
+#pragma unroll
+                        for (int o = 0; o < 8; ++o)
+                            if (yb + o < rb) stg128_cs_u2(out + (size_t)o * p.dst_pitch_px, acc[o]);
+                    }
+                } else {
+                    float4 acc[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                        if (sr >= RING_ROWS) sr -= RING_ROWS;
+                        const float4 v = lds128(v_col + sr * (uint32_t)RING_ROW_BYTES);
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
+                        }
+                    }
+                    if (x < p.cols) {
+#pragma unroll
+                        for (int o = 0; o < 8; ++o)
+                            if (yb + o < rb) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
+                    }
                 }
             }
             __syncthreads();  // V(i-2) done reading the slot H(i+1) will overwrite
@@ -250,15 +317,21 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     }
 }
 
-template <int HALF>
-int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool exact, cudaStream_t s) {
-    auto k0 = fused_sep_rgbaf32_kernel<HALF, false>;
-    auto k1 = fused_sep_rgbaf32_kernel<HALF, true>;
-    auto k = exact ? k1 : k0;
-    ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));  // per device; cheap
-    k<<<grid, NTHREADS, SMEM_BYTES, s>>>(tmap, p);
+template <int HALF, bool EXACT, int STAGES, bool F2>
+int launch_one(const CUtensorMap& tmap, const FusedParams& p, int grid, cudaStream_t s) {
+    auto k = fused_sep_rgbaf32_kernel<HALF, EXACT, STAGES, F2>;
+    ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES)));  // per device; cheap
+    k<<<grid, NTHREADS, smem_bytes(STAGES), s>>>(tmap, p);
     ZB_LAUNCHED();
     return ZB_OK;
+}
+
+template <int HALF>
+int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool exact, cudaStream_t s) {
+    if (exact) return launch_one<HALF, true, 3, false>(tmap, p, grid, s);
+    const int stages = g_tune_stages.load(), f2 = g_tune_f2.load();
+    if (stages == 2) return f2 ? launch_one<HALF, false, 2, true>(tmap, p, grid, s) : launch_one<HALF, false, 2, false>(tmap, p, grid, s);
+    return f2 ? launch_one<HALF, false, 3, true>(tmap, p, grid, s) : launch_one<HALF, false, 3, false>(tmap, p, grid, s);
 }
 
 }  // namespace
@@ -279,13 +352,20 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    if (di.smem_optin < (size_t)SMEM_BYTES) return ZB_ERR_UNSUPPORTED;
+    if (di.smem_optin < (size_t)smem_bytes(3)) return ZB_ERR_UNSUPPORTED;
 
     FusedParams p;
     memset(&p, 0, sizeof(p));
     // tap i of an n-tap kernel acts at offset i - n/2 (convolution.zig:527,542): place it at index i + (half - n/2)
     for (int i = 0; i < nx; ++i) p.kx[i + (half - half_x)] = kx[i];
     for (int i = 0; i < ny; ++i) p.ky[i + (half - half_y)] = ky[i];
+    for (int i = 0; i < MAXK; ++i) {
+        uint32_t bx, by;
+        memcpy(&bx, &p.kx[i], 4);
+        memcpy(&by, &p.ky[i], 4);
+        p.kx2[i] = ((unsigned long long)bx << 32) | bx;
+        p.ky2[i] = ((unsigned long long)by << 32) | by;
+    }
     p.src = (const float4*)src->data;
     p.dst = (float4*)dst->data;
     p.src_pitch_px = src->stride;
@@ -296,7 +376,8 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
     p.ngroups = p.cols / 8;
     p.n_strips = (p.cols + TW - 1) / TW;
     // band height: ~256 rows, then as many bands as fit in the same number of waves
-    int n_bands = (p.rows + 255) / 256;
+    const int band_target = g_tune_band_rows.load();
+    int n_bands = (p.rows + band_target - 1) / band_target;
     const long long waves = ((long long)n_bands * p.n_strips + di.sm_count - 1) / di.sm_count;
     int nb2 = (int)((waves * di.sm_count) / p.n_strips);
     if (nb2 > n_bands) n_bands = nb2;

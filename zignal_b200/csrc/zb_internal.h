@@ -17,6 +17,9 @@ extern thread_local char t_last_error[512];
 extern thread_local const char* t_last_kernel;
 extern std::atomic<int> g_exact_f32;
 extern std::atomic<int> g_force_generic;
+extern std::atomic<int> g_tune_stages;     // fused conv: TMA pipeline depth (2 or 3)
+extern std::atomic<int> g_tune_f2;         // fused conv: packed f32x2 FMA
+extern std::atomic<int> g_tune_band_rows;  // fused conv: target rows per work unit
 
 int set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 

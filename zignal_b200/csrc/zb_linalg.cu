@@ -1,0 +1,392 @@
+// zb_linalg.cu -- Matrix.gemm on the device and the Golub-Reinsch SVD on the host.
+//
+// GEMM (reference Matrix.zig:696-822): C = alpha * op(A) * op(B) + beta * C, all four transpose
+// combinations, row-major.  The reference is a dot-product loop with f32 (or f64) accumulators whose
+// summation order depends on the host's SIMD width (Matrix.zig:653-683), so it is only reproducible
+// to rounding; this kernel accumulates every dot product in f64 (so an f32 GEMM is accurate to ~1e-7
+// relative even for the K ~ 1e6 contractions of PCA's X^T X), tiles 64x64x16 through shared memory,
+// and splits K across CTAs deterministically (partials reduced in a fixed order -- no atomics).
+//
+// SVD (reference svd.zig:80-496, dlib svd4 lineage): Householder bidiagonalisation + implicit-shift
+// QR, descending sort.  Inherently sequential and tiny on this path (3x3 for fdm, dim x dim for pca),
+// so it runs on the host; the arithmetic order is the algorithm's, which is what fixes the signs of
+// the singular vectors that fdm's colour transform depends on.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "zb_internal.h"
+#include "zb_linalg.h"
+
+namespace zb {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_kernel(const T* __restrict__ A, int lda, bool ta, const T* __restrict__ B, int ldb, bool tb,
+                                                   int M, int N, int K, int k_per_split, double* __restrict__ partial /* [split][M][N] */) {
+    __shared__ T As[BK][BM + 1];
+    __shared__ T Bs[BK][BN + 1];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i;
+            // op(A)[m][k]: contiguous along m when transposed, along k otherwise
+            int m, k;
+            if (ta) { m = idx & (BM - 1); k = idx >> 6; } else { k = idx & (BK - 1); m = idx >> 4; }
+            const int gm = m0 + m, gk = k0 + k;
+            T v = 0;
+            if (gm < M && gk < kend) v = ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+            int n, kk;
+            if (!tb) { n = idx & (BN - 1); kk = idx >> 6; } else { kk = idx & (BK - 1); n = idx >> 4; }
+            const int gn = n0 + n, gkb = k0 + kk;
+            T w = 0;
+            if (gn < N && gkb < kend) w = tb ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
+            Bs[kk][n] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = (double)As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = (double)Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    double* out = partial + (size_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+            if (gm < M && gn < N) out[(size_t)gm * N + gn] = acc[i][j];
+        }
+}
+
+// out = beta*c + alpha*sum_splits(partial)   (Matrix.zig:728-738, :681)
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_finish(const double* __restrict__ partial, int splits, size_t mn, T alpha, T beta,
+                                                   const T* __restrict__ c, T* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mn) return;
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * mn + i];
+    const T prod = (T)((double)alpha * s);
+    out[i] = (c != nullptr && beta != (T)0) ? (T)(beta * c[i] + prod) : prod;
+}
+
+template <typename T>
+int gemm_device(const T* a, uint32_t ar, uint32_t ac, int ta, const T* b, uint32_t br, uint32_t bc, int tb, T alpha, T beta, const T* c,
+                T* out, cudaStream_t s) {
+    const uint32_t a_rows = ta ? ac : ar, a_cols = ta ? ar : ac;
+    const uint32_t b_rows = tb ? bc : br, b_cols = tb ? br : bc;
+    if (a_cols != b_rows) return ZB_ERR_DIMENSION_MISMATCH;  // Matrix.zig:717
+    if (!a || !b || !out) return ZB_ERR_INVALID_ARGUMENT;
+    const int M = (int)a_rows, N = (int)b_cols, K = (int)a_cols;
+    if (M == 0 || N == 0) return ZB_OK;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const int tiles = div_up(M, BM) * div_up(N, BN);
+    int splits = 1;
+    if (K > 4 * BK) {
+        splits = (2 * di.sm_count + tiles - 1) / tiles;
+        const int max_splits = std::max(1, K / (8 * BK));
+        splits = std::max(1, std::min(splits, max_splits));
+    }
+    int k_per_split = (K + splits - 1) / splits;
+    k_per_split = ((k_per_split + BK - 1) / BK) * BK;
+    splits = K == 0 ? 1 : (K + k_per_split - 1) / k_per_split;
+    Scratch part;
+    if ((rc = part.alloc((size_t)splits * M * N * sizeof(double), s))) return rc;
+    if (alpha == (T)0 || K == 0) {  // Matrix.zig:741: product skipped
+        ZB_CUDA(cudaMemsetAsync(part.p, 0, (size_t)splits * M * N * sizeof(double), s));
+    } else {
+        dim3 grid(div_up(N, BN), div_up(M, BM), splits);
+        gemm_kernel<T><<<grid, 256, 0, s>>>(a, (int)ac, ta != 0, b, (int)bc, tb != 0, M, N, K, k_per_split, part.as<double>());
+        ZB_LAUNCHED();
+    }
+    const size_t mn = (size_t)M * N;
+    gemm_finish<T><<<div_up(mn, 256), 256, 0, s>>>(part.as<double>(), splits, mn, alpha, beta, c, out);
+    ZB_LAUNCHED();
+    t_last_kernel = sizeof(T) == 4 ? "gemm_f32_acc64" : "gemm_f64";
+    return ZB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Golub-Reinsch SVD, host.  u: m x ucols row-major; q: n singular values; v: n x n.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+uint64_t svd_golub_reinsch(const T* a, uint32_t m_, uint32_t n_, int mode, bool with_v, T* u, uint32_t ucols_, T* q, T* v) {
+    const size_t m = m_, n = n_, ucols = ucols_;
+    auto U = [&](size_t i, size_t j) -> T& { return u[i * ucols + j]; };
+    auto V = [&](size_t i, size_t j) -> T& { return v[i * n + j]; };
+    std::vector<T> e(n, (T)0);
+    T eps = std::numeric_limits<T>::epsilon();
+    const T tol = std::numeric_limits<T>::min() / eps;
+    const size_t max_iterations = 300;  // svd.zig:178
+    uint64_t failed = 0;
+    T c = 0, f = 0, g = 0, h = 0, s = 0, x = 0, y = 0, z = 0;
+    size_t l = 0;
+
+    for (size_t i = 0; i < m; ++i)
+        for (size_t j = 0; j < n; ++j) U(i, j) = a[i * n + j];
+
+    // 1. Householder reduction to bidiagonal form: q holds the diagonal, e the super-diagonal
+    for (size_t i = 0; i < n; ++i) {
+        e[i] = g;
+        l = i + 1;
+        s = 0;
+        for (size_t j = i; j < m; ++j) s += U(j, i) * U(j, i);
+        if (s < tol) {
+            g = 0;
+        } else {
+            f = U(i, i);
+            g = f < 0 ? std::sqrt(s) : -std::sqrt(s);
+            h = f * g - s;
+            U(i, i) = f - g;
+            for (size_t j = l; j < n; ++j) {
+                s = 0;
+                for (size_t k = i; k < m; ++k) s += U(k, i) * U(k, j);
+                f = s / h;
+                for (size_t k = i; k < m; ++k) U(k, j) += f * U(k, i);
+            }
+        }
+        q[i] = g;
+        s = 0;
+        for (size_t j = l; j < n; ++j) s += U(i, j) * U(i, j);
+        if (s < tol) {
+            g = 0;
+        } else {
+            f = U(i, i + 1);
+            g = f < 0 ? std::sqrt(s) : -std::sqrt(s);
+            h = f * g - s;
+            U(i, i + 1) = f - g;
+            for (size_t j = l; j < n; ++j) e[j] = U(i, j) / h;
+            for (size_t j = l; j < m; ++j) {
+                s = 0;
+                for (size_t k = l; k < n; ++k) s += U(j, k) * U(i, k);
+                for (size_t k = l; k < n; ++k) U(j, k) += s * e[k];
+            }
+        }
+        y = std::fabs(q[i]) + std::fabs(e[i]);
+        x = std::max(x, y);
+    }
+    // 2. accumulate the right-hand transformations
+    if (with_v) {
+        for (size_t i = n; i-- > 0;) {
+            if (g != 0) {
+                h = U(i, i + 1) * g;
+                for (size_t j = l; j < n; ++j) V(j, i) = U(i, j) / h;
+                for (size_t j = l; j < n; ++j) {
+                    s = 0;
+                    for (size_t k = l; k < n; ++k) s += U(i, k) * V(k, j);
+                    for (size_t k = l; k < n; ++k) V(k, j) += s * V(k, i);
+                }
+            }
+            for (size_t j = l; j < n; ++j) V(i, j) = V(j, i) = 0;
+            V(i, i) = 1;
+            g = e[i];
+            l = i;
+        }
+    }
+    // 3. accumulate the left-hand transformations
+    if (mode != ZB_SVD_NO_U) {
+        for (size_t i = n; i < m; ++i) {
+            for (size_t j = n; j < ucols; ++j) U(i, j) = 0;
+            if (i < ucols) U(i, i) = 1;
+        }
+        for (size_t i = n; i-- > 0;) {
+            l = i + 1;
+            g = q[i];
+            for (size_t j = l; j < ucols; ++j) U(i, j) = 0;
+            if (g != 0) {
+                h = U(i, i) * g;
+                for (size_t j = l; j < ucols; ++j) {
+                    s = 0;
+                    for (size_t k = l; k < m; ++k) s += U(k, i) * U(k, j);
+                    f = s / h;
+                    for (size_t k = i; k < m; ++k) U(k, j) += f * U(k, i);
+                }
+                for (size_t j = i; j < m; ++j) U(j, i) /= g;
+            } else {
+                for (size_t j = i; j < m; ++j) U(j, i) = 0;
+            }
+            U(i, i) += 1;
+        }
+    }
+    // 4. diagonalise the bidiagonal form with implicitly shifted QR sweeps
+    eps *= x;
+    for (size_t k = n; k-- > 0;) {
+        size_t iter = 0;
+        for (;;) {
+            // test for splitting
+            bool cancel = false;
+            for (l = k;; --l) {
+                if (std::fabs(e[l]) <= eps) break;           // e[0] == 0, so l never underflows
+                if (std::fabs(q[l - 1]) <= eps) { cancel = true; break; }
+            }
+            if (cancel) {  // cancellation of e[l], l > 0
+                c = 0;
+                s = 1;
+                const size_t l1 = l - 1;
+                for (size_t i = l; i <= k; ++i) {
+                    f = s * e[i];
+                    e[i] *= c;
+                    if (std::fabs(f) <= eps) break;
+                    g = q[i];
+                    h = std::sqrt(f * f + g * g);
+                    q[i] = h;
+                    c = g / h;
+                    s = -f / h;
+                    if (mode != ZB_SVD_NO_U)
+                        for (size_t j = 0; j < m; ++j) {
+                            y = U(j, l1);
+                            z = U(j, i);
+                            U(j, l1) = y * c + z * s;
+                            U(j, i) = -y * s + z * c;
+                        }
+                }
+            }
+            // test for convergence
+            z = q[k];
+            if (l == k) {
+                if (z < 0) {  // make the singular value non-negative
+                    q[k] = -z;
+                    if (with_v)
+                        for (size_t j = 0; j < n; ++j) V(j, k) = -V(j, k);
+                }
+                break;
+            }
+            if (++iter > max_iterations) { failed = k; break; }
+            // shift from the bottom 2x2 minor
+            x = q[l];
+            y = q[k - 1];
+            g = e[k - 1];
+            h = e[k];
+            f = ((y - z) * (y + z) + (g - h) * (g + h)) / (2 * h * y);
+            g = std::sqrt(f * f + (T)1);
+            f = ((x - z) * (x + z) + h * (y / (f < 0 ? f - g : f + g) - h)) / x;
+            // next QR transformation
+            c = s = 1;
+            for (size_t i = l + 1; i <= k; ++i) {
+                g = e[i];
+                y = q[i];
+                h = s * g;
+                g *= c;
+                z = std::sqrt(f * f + h * h);
+                e[i - 1] = z;
+                c = f / z;
+                s = h / z;
+                f = x * c + g * s;
+                g = -x * s + g * c;
+                h = y * s;
+                y *= c;
+                if (with_v)
+                    for (size_t j = 0; j < n; ++j) {
+                        x = V(j, i - 1);
+                        z = V(j, i);
+                        V(j, i - 1) = x * c + z * s;
+                        V(j, i) = -x * s + z * c;
+                    }
+                z = std::sqrt(f * f + h * h);
+                q[i - 1] = z;
+                if (z != 0) {
+                    c = f / z;
+                    s = h / z;
+                }
+                f = c * g + s * y;
+                x = -s * g + c * y;
+                if (mode != ZB_SVD_NO_U)
+                    for (size_t j = 0; j < m; ++j) {
+                        y = U(j, i - 1);
+                        z = U(j, i);
+                        U(j, i - 1) = y * c + z * s;
+                        U(j, i) = -y * s + z * c;
+                    }
+            }
+            e[l] = 0;
+            e[k] = f;
+            q[k] = x;
+        }
+    }
+    // 5. selection-sort the singular values into descending order, permuting the vectors with them
+    for (size_t i = 0; i < n; ++i) {
+        size_t best = i;
+        for (size_t j = i + 1; j < n; ++j)
+            if (q[j] > q[best]) best = j;
+        if (best == i) continue;
+        std::swap(q[i], q[best]);
+        if (mode != ZB_SVD_NO_U)
+            for (size_t r = 0; r < m; ++r) std::swap(U(r, i), U(r, best));
+        if (with_v)
+            for (size_t r = 0; r < n; ++r) std::swap(V(r, i), V(r, best));
+    }
+    return failed;
+}
+
+template uint64_t svd_golub_reinsch<float>(const float*, uint32_t, uint32_t, int, bool, float*, uint32_t, float*, float*);
+template uint64_t svd_golub_reinsch<double>(const double*, uint32_t, uint32_t, int, bool, double*, uint32_t, double*, double*);
+
+template <typename T>
+static int svd_entry(const T* a, uint32_t m, uint32_t n, int mode, int with_v, T* u, T* s, T* v, uint64_t* converged) {
+    if (!a || !s) return ZB_ERR_INVALID_ARGUMENT;
+    if (m < n) return ZB_ERR_DIMENSION_MISMATCH;  // svd.zig:86
+    if (mode < ZB_SVD_NO_U || mode > ZB_SVD_FULL_U) return ZB_ERR_INVALID_ARGUMENT;
+    if (mode != ZB_SVD_NO_U && !u) return ZB_ERR_INVALID_ARGUMENT;
+    if (with_v && !v) return ZB_ERR_INVALID_ARGUMENT;
+    const uint32_t ucols = mode == ZB_SVD_FULL_U ? m : n;
+    std::vector<T> ubuf((size_t)m * ucols, (T)0), vbuf(with_v ? (size_t)n * n : 1, (T)0);
+    for (uint32_t i = 0; i < n; ++i) s[i] = 0;
+    const uint64_t failed = svd_golub_reinsch<T>(a, m, n, mode, with_v != 0, ubuf.data(), ucols, s, vbuf.data());
+    if (mode != ZB_SVD_NO_U) std::copy(ubuf.begin(), ubuf.end(), u);
+    if (with_v) std::copy(vbuf.begin(), vbuf.end(), v);
+    if (converged) *converged = failed;
+    return ZB_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_gemm_f32(const float* a, uint32_t ar, uint32_t ac, int ta, const float* b, uint32_t br, uint32_t bc, int tb, float alpha, float beta,
+                const float* c, float* out, zb_stream s) {
+    return gemm_device<float>(a, ar, ac, ta, b, br, bc, tb, alpha, beta, c, out, (cudaStream_t)s);
+}
+int zb_gemm_f64(const double* a, uint32_t ar, uint32_t ac, int ta, const double* b, uint32_t br, uint32_t bc, int tb, double alpha,
+                double beta, const double* c, double* out, zb_stream s) {
+    return gemm_device<double>(a, ar, ac, ta, b, br, bc, tb, alpha, beta, c, out, (cudaStream_t)s);
+}
+int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged) {
+    return svd_entry<double>(a, m, n, mode, with_v, u, s, v, converged);
+}
+int zb_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v, float* u, float* s, float* v, uint64_t* converged) {
+    return svd_entry<float>(a, m, n, mode, with_v, u, s, v, converged);
+}
+
+}  // extern "C"

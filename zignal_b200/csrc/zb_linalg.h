@@ -1,0 +1,10 @@
+// zb_linalg.h -- host SVD shared with zb_fdm.cu.
+#pragma once
+#include <cstdint>
+
+namespace zb {
+// Golub-Reinsch SVD (reference svd.zig:149-496).  a: m x n row-major (m >= n); u: m x ucols; q: n; v: n x n.
+// Returns 0 or the index of the singular value whose QR iteration failed to converge.
+template <typename T>
+uint64_t svd_golub_reinsch(const T* a, uint32_t m, uint32_t n, int mode, bool with_v, T* u, uint32_t ucols, T* q, T* v);
+}  // namespace zb

@@ -1,0 +1,114 @@
+"""Row-block sharding of one large image across the GPUs of a box (one process per GPU).
+
+The reference is single-process; this is the multi-GPU layer SURVEY.md 8(e) defines for the hot path:
+  * convolution / blur: contiguous row blocks, each stored with `halo` extra rows above and below; one
+    batched send/recv pair per row neighbour fills the halos (NCCL over NVLink on GPUs, gloo on CPU for
+    the host-logic tests); the global top/bottom edges are filled locally per the BorderMode
+    (reference border.zig:46-63).  The op then runs on the extended block and the interior rows are the
+    result -- the outer `halo` output rows are discarded;
+  * resize / rotate / warp: no exchange (output row blocks, or a batch split);
+  * fdm / pca statistics: one all-reduce of the 11 exact integer moments (`allreduce_moments`).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .image import BorderMode, Image, PixFmt, _CH, _NP
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class RowBlock:
+    """Rows [rank*rows, (rank+1)*rows) of a (world*rows) x cols image, with `halo` rows of padding on both sides."""
+
+    def __init__(self, rows: int, cols: int, pixfmt: PixFmt, halo: int, device, rank: int, world: int):
+        import torch
+        self.rows, self.cols, self.halo = int(rows), int(cols), int(halo)
+        self.pixfmt = PixFmt(pixfmt)
+        self.rank, self.world = int(rank), int(world)
+        ch = _CH[self.pixfmt]
+        dt = torch.uint8 if _NP[self.pixfmt] == np.uint8 else torch.float32
+        shape = (self.rows + 2 * self.halo, self.cols) + ((ch,) if ch > 1 else ())
+        self.t = torch.zeros(shape, dtype=dt, device=device)
+
+    # -- views -------------------------------------------------------------------------------------
+    def extended_tensor(self):
+        return self.t
+
+    def interior_tensor(self):
+        return self.t[self.halo:self.halo + self.rows]
+
+    def image(self) -> Image:
+        """The extended block (interior + halos) as an Image for the C ABI."""
+        return Image(self.t.reshape(-1), self.pixfmt, self.rows + 2 * self.halo, self.cols, self.cols)
+
+    def interior_image(self) -> Image:
+        return Image(self.t.reshape(-1), self.pixfmt, self.rows, self.cols, self.cols, self.halo * self.cols)
+
+    # -- the one exchange step of the convolution path ------------------------------------------------
+    def exchange_halo(self, border: BorderMode = BorderMode.MIRROR):
+        h, n = self.halo, self.rows
+        if h == 0:
+            return
+        assert n > h, "row block must be taller than the halo"
+        t = self.t
+        dist = _dist()
+        wrap = BorderMode(border) == BorderMode.WRAP
+        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if wrap else None)
+        down = self.rank + 1 if self.rank < self.world - 1 else (0 if wrap else None)
+        if self.world > 1:
+            # Order matters when up == down (wrap with 2 ranks): the k-th send to a peer pairs with that peer's k-th recv,
+            # so every rank posts (send up, recv from down) first and (send down, recv from up) second.
+            ops = []
+            if up is not None:
+                ops.append(dist.P2POp(dist.isend, t[h:2 * h], up))           # my first rows -> upper neighbour's bottom halo
+            if down is not None:
+                ops.append(dist.P2POp(dist.irecv, t[n + h:n + 2 * h], down))
+                ops.append(dist.P2POp(dist.isend, t[n:n + h], down))         # my last rows -> lower neighbour's top halo
+            if up is not None:
+                ops.append(dist.P2POp(dist.irecv, t[0:h], up))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+        elif wrap:
+            t[0:h] = t[n:n + h].clone()
+            t[n + h:] = t[h:2 * h].clone()
+        # global image edges: resolveIndex(-j) / resolveIndex(rows_total - 1 + j), j = 1..h
+        b = BorderMode(border)
+        if up is None:
+            if b == BorderMode.ZERO:
+                t[0:h].zero_()
+            elif b == BorderMode.REPLICATE:
+                t[0:h] = t[h:h + 1]
+            elif b == BorderMode.MIRROR:      # row -j <- row j
+                t[0:h] = t[h + 1:2 * h + 1].flip(0)
+        if down is None:
+            if b == BorderMode.ZERO:
+                t[n + h:].zero_()
+            elif b == BorderMode.REPLICATE:
+                t[n + h:] = t[n + h - 1:n + h]
+            elif b == BorderMode.MIRROR:      # row (R-1)+j <- row (R-1)-j
+                t[n + h:] = t[n - 1:n + h - 1].flip(0)
+
+
+def allreduce_moments(sums: np.ndarray, device=None) -> np.ndarray:
+    """Sum the 11 exact integer moments (zb_fdm_moments) over all ranks: the single collective of the fdm path."""
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return np.asarray(sums, dtype=np.uint64)
+    t = torch.from_numpy(np.asarray(sums, dtype=np.uint64).astype(np.int64))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def split_batch(n_items: int, rank: int, world: int):
+    """Contiguous share [lo, hi) of a batch for this rank (rotate / resize batches: no exchange)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -170,6 +170,10 @@ int zb_gemm_f32(const float* a, uint32_t a_rows, uint32_t a_cols, int trans_a,
 int zb_gemm_f64(const double* a, uint32_t a_rows, uint32_t a_cols, int trans_a,
                 const double* b, uint32_t b_rows, uint32_t b_cols, int trans_b,
                 double alpha, double beta, const double* c, double* out, zb_stream s);
+/* Pca.fit's centering step (pca.zig:135-154): mean[j] = sum_i x[i][j] / n (when compute_mean != 0; f64 accumulation),
+ * centered = x - mean (skipped when NULL).  Pca.transform (pca.zig:300-308) calls it with compute_mean = 0.  DEVICE pointers. */
+int zb_center_columns_f32(const float* x, uint32_t n, uint32_t dim, float* mean, int compute_mean, float* centered, zb_stream s);
+int zb_center_columns_f64(const double* x, uint32_t n, uint32_t dim, double* mean, int compute_mean, double* centered, zb_stream s);
 /* Matrix.svd / SMatrix.svd   Matrix.zig:1570, SMatrix.zig:804, svd.zig:80-496.  HOST matrices
  * (the decomposition is sequential; callers on this path pass 3x3 .. dim x dim covariance matrices).
  * a: m x n row-major, m >= n.  u: m x (mode==FULL ? m : n) or NULL; s: n; v: n x n or NULL.
@@ -219,7 +223,8 @@ int zb_host_fdm_match(zb_image* source, const zb_image* target, int pixfmt);
 int zb_set_exact_f32(int on);
 /* Forces the generic (two-pass through HBM) separable path; used by tests to cross-check kernels. */
 int zb_set_force_generic(int on);
-/* Kernel tuning knobs for experiments ("conv.stages" 2|3, "conv.f32x2" 0|1, "conv.band_rows" >= 64). */
+/* Kernel tuning knobs for experiments ("conv.stages" 2|3, "conv.f32x2" 0|1, "conv.band_rows" >= 64,
+ * "conv.variant" -1 auto | 0 phase-synchronous | 1 warp-specialised). */
 int zb_tune(const char* key, int value);
 /* Name of the kernel variant the last zb_conv_separable call selected on this thread. */
 const char* zb_last_kernel(void);

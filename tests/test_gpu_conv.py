@@ -78,7 +78,16 @@ def test_fused_rgbaf32_exact_and_fma(zb, rows, cols, border):
         got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
         assert L.zb_last_kernel().decode() == "fused_sep_rgbaf32_exact"
         assert np.array_equal(got, want), ("exact", half)
+        L.zb_tune(b"conv.variant", 0)
+        got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+        assert np.array_equal(got, want), ("exact-sync", half)
+        L.zb_tune(b"conv.variant", 1)  # warp-specialised kernel, exact arithmetic
+        got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+        assert np.array_equal(got, want), ("exact-ws", half)
         L.zb_set_exact_f32(0)
+        got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+        assert rel_err(got, want) <= TOL_F32, ("fma-ws", half)
+        L.zb_tune(b"conv.variant", 0)
         for stages in (2, 3):
             for f2 in (0, 1):
                 L.zb_tune(b"conv.stages", stages)
@@ -86,8 +95,9 @@ def test_fused_rgbaf32_exact_and_fma(zb, rows, cols, border):
                 got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
                 assert L.zb_last_kernel().decode() == "fused_sep_rgbaf32"
                 assert rel_err(got, want) <= TOL_F32, ("fma", half, stages, f2)
-    L.zb_tune(b"conv.stages", 3)
+    L.zb_tune(b"conv.stages", 2)
     L.zb_tune(b"conv.f32x2", 0)
+    L.zb_tune(b"conv.variant", -1)
 
 
 def test_fused_handles_views_even_and_unequal_kernels(zb):

@@ -95,6 +95,8 @@ def _declare(L):
         "zb_warp": ([img, img, i, i, fp, i, f, f, vp], i),
         "zb_gemm_f32": ([fp, u32, u32, i, fp, u32, u32, i, f, f, fp, fp, vp], i),
         "zb_gemm_f64": ([dp, u32, u32, i, dp, u32, u32, i, C.c_double, C.c_double, dp, dp, vp], i),
+        "zb_center_columns_f32": ([fp, u32, u32, fp, i, fp, vp], i),
+        "zb_center_columns_f64": ([dp, u32, u32, dp, i, dp, vp], i),
         "zb_svd_f64": ([dp, u32, u32, i, i, dp, dp, dp, P(u64)], i),
         "zb_svd_f32": ([fp, u32, u32, i, i, fp, fp, fp, P(u64)], i),
         "zb_fdm_create": ([P(vp), i], i),

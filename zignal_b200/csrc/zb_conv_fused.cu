@@ -130,20 +130,95 @@ __device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {
 }
 
 // Patch the stage entries TMA could not provide (out-of-range rows / columns) per the border mode.
-__device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, const FusedParams& p) {
+// Column patches of in-range rows are sourced from the stage itself whenever the resolved column is one
+// TMA delivered (always the case for mirror / replicate): no global-memory latency on the per-chunk path
+// of the edge strips.  Out-of-range rows (image top / bottom only) are fetched from global memory.
+template <int NT>
+__device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool fix_x, bool fix_rows, const FusedParams& p) {
     const int xlimit = p.ngroups * 8;
-    for (int idx = threadIdx.x; idx < CHUNK * G * 8; idx += NTHREADS) {
-        const int rr = idx / (G * 8);
-        const int xx = idx - rr * (G * 8);
-        const int y = y0 + rr, x = xs0 + xx;
-        const bool provided = (y >= 0 && y < p.rows && x >= 0 && x < xlimit);
-        if (provided) continue;
-        const int ry = resolve_index(y, p.rows, p.border);
-        const int rx = resolve_index(x, p.cols, p.border);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ry >= 0 && rx >= 0) v = __ldg(p.src + (size_t)ry * p.src_pitch_px + rx);
+    auto stage_addr = [&](int rr, int xx) {
         const uint32_t line = (uint32_t)(rr * G + (xx >> 3));
-        sts128(stage + line * 128 + ((((uint32_t)xx & 7u) ^ (line & 7u)) << 4), v);
+        return stage + line * 128 + ((((uint32_t)xx & 7u) ^ (line & 7u)) << 4);
+    };
+    if (fix_x) {
+        const int nleft = xs0 < 0 ? min(-xs0, G * 8) : 0;                      // entries [0, nleft) have x < 0
+        const int r0 = max(0, xlimit - xs0);                                    // first entry with x >= xlimit
+        const int r1 = min(G * 8, p.cols - xs0 + MAX_HALF);                     // entries beyond cols + MAX_HALF are never read
+        const int per_row = nleft + max(0, r1 - r0);
+        for (int idx = threadIdx.x; idx < CHUNK * per_row; idx += NT) {
+            const int rr = idx / per_row, e = idx - rr * per_row;
+            const int xx = e < nleft ? e : r0 + (e - nleft);
+            const int y = y0 + rr, x = xs0 + xx;
+            if (y < 0 || y >= p.rows) continue;                                 // handled by the row pass below
+            const int rx = resolve_index(x, p.cols, p.border);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rx >= 0) {
+                const int sx = rx - xs0;
+                if (rx < xlimit && sx >= 0 && sx < G * 8) v = lds128(stage_addr(rr, sx));   // delivered by TMA into this stage
+                else v = __ldg(p.src + (size_t)y * p.src_pitch_px + rx);
+            }
+            sts128(stage_addr(rr, xx), v);
+        }
+    }
+    if (fix_rows) {
+        for (int idx = threadIdx.x; idx < CHUNK * G * 8; idx += NT) {
+            const int rr = idx / (G * 8);
+            const int xx = idx - rr * (G * 8);
+            const int y = y0 + rr, x = xs0 + xx;
+            if (y >= 0 && y < p.rows) continue;
+            const int ry = resolve_index(y, p.rows, p.border);
+            const int rx = resolve_index(x, p.cols, p.border);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ry >= 0 && rx >= 0) v = __ldg(p.src + (size_t)ry * p.src_pitch_px + rx);
+            sts128(stage_addr(rr, xx), v);
+        }
+    }
+}
+
+// Vertical pass of one chunk: 8 output rows from ring rows [SLOT*8 + 8-HALF, SLOT*8 + 16+HALF) (mod 24).
+template <int HALF, bool EXACT, bool F2, int SLOT>
+__device__ __forceinline__ void v_pass(uint32_t v_col, const FusedParams& p, float4* out, bool col_ok, int rows_left) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int NLOAD = CHUNK + 2 * HALF;
+    if constexpr (F2) {
+        U2 acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o].lo = acc[o].hi = 0ull;
+#pragma unroll
+        for (int j = 0; j < NLOAD; ++j) {
+            constexpr int dummy = 0;
+            const int sr = (SLOT * CHUNK + 8 - HALF + j) % RING_ROWS + dummy;
+            const U2 v = lds128_u2(v_col + (uint32_t)(sr * RING_ROW_BYTES));
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int ti = j - o;
+                if (ti >= 0 && ti < K) mac_u2(acc[o], v, p.ky2[ti]);
+            }
+        }
+        if (col_ok) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                if (o < rows_left) stg128_cs_u2(out + (size_t)o * p.dst_pitch_px, acc[o]);
+        }
+    } else {
+        float4 acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NLOAD; ++j) {
+            const int sr = (SLOT * CHUNK + 8 - HALF + j) % RING_ROWS;
+            const float4 v = lds128(v_col + (uint32_t)(sr * RING_ROW_BYTES));
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const int ti = j - o;
+                if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
+            }
+        }
+        if (col_ok) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                if (o < rows_left) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
+        }
     }
 }
 
@@ -212,16 +287,20 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             const uint32_t stage = smem0 + st * STAGE_BYTES;
             while (!mbar_try_wait(bar0 + 8 * st, (ccount / STAGES) & 1u)) {}
             const int y0 = ra - CHUNK + CHUNK * i;
-            const bool fix = (p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows)) || (p.fix_left && g0 < 0) ||
-                             (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
-            if (fix) {
-                fixup_stage(stage, y0, g0 * 8, p);
+            const bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
+            const bool fix_x = (p.fix_left && g0 < 0) || (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
+            if (fix_r || fix_x) {
+                fixup_stage<NTHREADS>(stage, y0, g0 * 8, fix_x, fix_r, p);
                 __syncthreads();
             }
 
             // ---------------- H(i): stage -> ring rows [(i%3)*8, +8) ----------------
             {
                 const uint32_t line0 = (uint32_t)(hr * G + ht);
+                // address of pixel c of stage line l = base(l) ^ (c << 4), base(l) = stage + l*128 + ((l & 7) << 4)  (stage is 1 KB aligned)
+                uint32_t lbase[3];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) lbase[l] = stage + (line0 + l) * 128u + (((line0 + l) & 7u) << 4);
                 const uint32_t rrow = h_ring_col + (uint32_t)(((i % 3) * CHUNK + hr) * RING_ROW_BYTES);
                 if constexpr (F2) {
                     U2 acc[8];
@@ -230,8 +309,7 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 #pragma unroll
                     for (int j = 0; j < NLOAD; ++j) {
                         const int pidx = 8 - HALF + j;
-                        const uint32_t line = line0 + (uint32_t)(pidx >> 3);
-                        const U2 v = lds128_u2(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
+                        const U2 v = lds128_u2(lbase[pidx >> 3] ^ (((uint32_t)pidx & 7u) << 4));
 #pragma unroll
                         for (int o = 0; o < 8; ++o) {
                             const int ti = j - o;
@@ -247,8 +325,7 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 #pragma unroll
                     for (int j = 0; j < NLOAD; ++j) {
                         const int pidx = 8 - HALF + j;  // pixel index relative to the start of group `ht` of the stage row
-                        const uint32_t line = line0 + (uint32_t)(pidx >> 3);
-                        const float4 v = lds128(stage + line * 128u + ((((uint32_t)pidx & 7u) ^ (line & 7u)) << 4));
+                        const float4 v = lds128(lbase[pidx >> 3] ^ (((uint32_t)pidx & 7u) << 4));
 #pragma unroll
                         for (int o = 0; o < 8; ++o) {
                             const int ti = j - o;
@@ -266,50 +343,14 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             // ---------------- V(i-2): ring -> global rows [ra+8c, ra+8c+8) ----------------
             if (i >= 2) {
                 const int c = i - 2;
-                const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
                 const int x = x0 + vx;
                 const int yb = ra + CHUNK * c;
                 float4* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
-                if constexpr (F2) {
-                    U2 acc[8];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) acc[o].lo = acc[o].hi = 0ull;
-#pragma unroll
-                    for (int j = 0; j < NLOAD; ++j) {
-                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
-                        if (sr >= RING_ROWS) sr -= RING_ROWS;
-                        const U2 v = lds128_u2(v_col + sr * (uint32_t)RING_ROW_BYTES);
-#pragma unroll
-                        for (int o = 0; o < 8; ++o) {
-                            const int ti = j - o;
-                            if (ti >= 0 && ti < K) mac_u2(acc[o], v, p.ky2[ti]);
-                        }
-                    }
-                    if (x < p.cols) {
-#pragma unroll
-                        for (int o = 0; o < 8; ++o)
-                            if (yb + o < rb) stg128_cs_u2(out + (size_t)o * p.dst_pitch_px, acc[o]);
-                    }
-                } else {
-                    float4 acc[8];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int j = 0; j < NLOAD; ++j) {
-                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
-                        if (sr >= RING_ROWS) sr -= RING_ROWS;
-                        const float4 v = lds128(v_col + sr * (uint32_t)RING_ROW_BYTES);
-#pragma unroll
-                        for (int o = 0; o < 8; ++o) {
-                            const int ti = j - o;
-                            if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
-                        }
-                    }
-                    if (x < p.cols) {
-#pragma unroll
-                        for (int o = 0; o < 8; ++o)
-                            if (yb + o < rb) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
-                    }
+                const bool col_ok = x < p.cols;
+                switch (c % 3) {  // the ring slot of chunk c is compile-time inside each case: loads use immediate offsets
+                    case 0: v_pass<HALF, EXACT, F2, 0>(v_col, p, out, col_ok, rb - yb); break;
+                    case 1: v_pass<HALF, EXACT, F2, 1>(v_col, p, out, col_ok, rb - yb); break;
+                    default: v_pass<HALF, EXACT, F2, 2>(v_col, p, out, col_ok, rb - yb); break;
                 }
             }
             __syncthreads();  // V(i-2) done reading the slot H(i+1) will overwrite
@@ -326,9 +367,184 @@ int launch_one(const CUtensorMap& tmap, const FusedParams& p, int grid, cudaStre
     return ZB_OK;
 }
 
+
+// ================================================================================================
+// Warp-specialised variant: 8 warps run the horizontal pass, 8 warps the vertical pass, 1 warp issues
+// TMA.  The roles are decoupled by mbarriers (stage full/empty, ring-slot full/empty) instead of
+// CTA-wide barriers, so H(i+1) overlaps V(i-2) and each scheduler has 4 compute warps to hide
+// shared-memory latency behind FFMAs.  The ring has 4 slots (32 rows) so H may run one chunk ahead.
+// ================================================================================================
+constexpr int WS_RING_ROWS = 32;
+constexpr int WS_RING_BYTES = WS_RING_ROWS * RING_ROW_BYTES;  // 131072
+constexpr int WS_THREADS = 544;                               // 256 H + 256 V + 1 producer warp
+constexpr int WS_SMEM_BYTES = 2 * STAGE_BYTES + WS_RING_BYTES + 128 + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct UnitGeom {
+    int x0, ra, rb, n_out, n_in, g0;
+};
+__device__ __forceinline__ UnitGeom unit_geom(int unit, const FusedParams& p) {
+    UnitGeom u;
+    const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
+    u.x0 = strip * TW;
+    u.ra = band * p.band_rows;
+    u.rb = min(u.ra + p.band_rows, p.rows);
+    u.n_out = (u.rb - u.ra + CHUNK - 1) / CHUNK;
+    u.n_in = u.n_out + 2;
+    u.g0 = u.x0 / 8 - 1;
+    return u;
+}
+
+template <int HALF, bool EXACT>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+fused_sep_rgbaf32_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int NLOAD = CHUNK + 2 * HALF;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = smem0 + 2 * STAGE_BYTES;
+    const uint32_t bars = ring + WS_RING_BYTES;
+    const uint32_t full_stage = bars, empty_stage = bars + 16, full_ring = bars + 32, empty_ring = bars + 64;  // 2,2,4,4 x 8 B
+
+    const int tid = threadIdx.x;
+    const int n_units = p.n_strips * p.n_bands;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full_stage + 8 * i, 1); mbar_init(empty_stage + 8 * i, 256); }
+        for (int i = 0; i < 4; ++i) { mbar_init(full_ring + 8 * i, 256); mbar_init(empty_ring + 8 * i, 256); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (tid >= 512) {
+        // ------------------------------- producer warp (one lane) -------------------------------
+        if (tid == 512) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t g = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const UnitGeom u = unit_geom(unit, p);
+                for (int i = 0; i < u.n_in; ++i, ++g) {
+                    const uint32_t st = g & 1u;
+                    if (g >= 2) mbar_wait(empty_stage + 8 * st, ((g >> 1) - 1) & 1u);
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(full_stage + 8 * st, STAGE_BYTES);
+                    tma_load_3d(smem0 + st * STAGE_BYTES, &tmap, 0, u.g0, u.ra - CHUNK + CHUNK * i, full_stage + 8 * st);
+                }
+            }
+        }
+    } else if (tid < 256) {
+        // ------------------------------------- H warps -------------------------------------
+        const int ht = tid & 31, hr = tid >> 5;
+        const uint32_t h_key = (uint32_t)ht & 7u;
+        uint32_t g = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitGeom u = unit_geom(unit, p);
+            for (int i = 0; i < u.n_in; ++i, ++g) {
+                const uint32_t st = g & 1u, slot = g & 3u;
+                const uint32_t stage = smem0 + st * STAGE_BYTES;
+                mbar_wait(full_stage + 8 * st, (g >> 1) & 1u);
+                const int y0 = u.ra - CHUNK + CHUNK * i;
+                const bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
+                const bool fix_x = (p.fix_left && u.g0 < 0) || (p.fix_right && (u.g0 + G) * 8 > p.ngroups * 8);
+                if (fix_r || fix_x) {
+                    fixup_stage<256>(stage, y0, u.g0 * 8, fix_x, fix_r, p);
+                    named_bar_sync(1, 256);
+                }
+                float4 acc[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t line0 = (uint32_t)(hr * G + ht);
+                uint32_t lbase[3];
+#pragma unroll
+                for (int l = 0; l < 3; ++l) lbase[l] = stage + (line0 + l) * 128u + (((line0 + l) & 7u) << 4);
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) {
+                    const int pidx = 8 - HALF + j;
+                    const float4 v = lds128(lbase[pidx >> 3] ^ (((uint32_t)pidx & 7u) << 4));
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int ti = j - o;
+                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.kx[ti]);
+                    }
+                }
+                mbar_arrive(empty_stage + 8 * st);  // all reads of the stage are done (values are in registers)
+                if (g >= 4) mbar_wait(empty_ring + 8 * slot, ((g >> 2) - 1) & 1u);  // V finished with the chunk that used this slot
+                const uint32_t rrow = ring + (uint32_t)ht * 128u + (uint32_t)((slot * CHUNK + hr) * RING_ROW_BYTES);
+#pragma unroll
+                for (int o = 0; o < 8; ++o) sts128(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                mbar_arrive(full_ring + 8 * slot);
+            }
+        }
+    } else {
+        // ------------------------------------- V warps -------------------------------------
+        const int vx = tid - 256;
+        const uint32_t v_col = ring + (uint32_t)(vx >> 3) * 128u + ((((uint32_t)vx & 7u) ^ (((uint32_t)vx >> 3) & 7u)) << 4);
+        const uint32_t ring_end = v_col + WS_RING_BYTES;
+        uint32_t gbase = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitGeom u = unit_geom(unit, p);
+            for (int c = 0; c < u.n_out; ++c) {
+                const uint32_t gl = gbase + c + 2;  // last input chunk V(c) needs
+                mbar_wait(full_ring + 8 * (gl & 3u), (gl >> 2) & 1u);
+                float4 acc[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t a0 = v_col + (uint32_t)((((gbase + c) & 3u) * CHUNK + 8 - HALF) * RING_ROW_BYTES);
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) {
+                    uint32_t a = a0 + (uint32_t)(j * RING_ROW_BYTES);
+                    if (a >= ring_end) a -= WS_RING_BYTES;
+                    const float4 v = lds128(a);
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int ti = j - o;
+                        if (ti >= 0 && ti < K) mac4<EXACT>(acc[o], v, p.ky[ti]);
+                    }
+                }
+                mbar_arrive(empty_ring + 8 * ((gbase + c) & 3u));
+                if (c == u.n_out - 1) {  // the unit's last two input chunks are never the base chunk of a V step
+                    mbar_arrive(empty_ring + 8 * ((gbase + c + 1) & 3u));
+                    mbar_arrive(empty_ring + 8 * ((gbase + c + 2) & 3u));
+                }
+                const int x = u.x0 + vx;
+                const int yb = u.ra + CHUNK * c;
+                if (x < p.cols) {
+                    float4* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o)
+                        if (yb + o < u.rb) __stcs(out + (size_t)o * p.dst_pitch_px, acc[o]);
+                }
+            }
+            gbase += (uint32_t)u.n_in;
+        }
+    }
+}
+
+template <int HALF, bool EXACT>
+int launch_ws(const CUtensorMap& tmap, const FusedParams& p, int grid, cudaStream_t s) {
+    auto k = fused_sep_rgbaf32_ws_kernel<HALF, EXACT>;
+    ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+    k<<<grid, WS_THREADS, WS_SMEM_BYTES, s>>>(tmap, p);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
 template <int HALF>
 int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool exact, cudaStream_t s) {
-    if (exact) return launch_one<HALF, true, 3, false>(tmap, p, grid, s);
+    // variant: the warp-specialised kernel overlaps memory better (wins while the FP32 pipe has slack: <= 11 taps);
+    // from 13 taps on both variants are bound by FFMA issue and the phase-synchronous kernel is as fast.
+    int variant = g_tune_variant.load();
+    if (variant < 0) variant = HALF <= 5 ? 1 : 0;
+    if (variant == 1) return exact ? launch_ws<HALF, true>(tmap, p, grid, s) : launch_ws<HALF, false>(tmap, p, grid, s);
+    if (exact) return launch_one<HALF, true, 2, false>(tmap, p, grid, s);
     const int stages = g_tune_stages.load(), f2 = g_tune_f2.load();
     if (stages == 2) return f2 ? launch_one<HALF, false, 2, true>(tmap, p, grid, s) : launch_one<HALF, false, 2, false>(tmap, p, grid, s);
     return f2 ? launch_one<HALF, false, 3, true>(tmap, p, grid, s) : launch_one<HALF, false, 3, false>(tmap, p, grid, s);

@@ -134,6 +134,64 @@ int gemm_device(const T* a, uint32_t ar, uint32_t ac, int ta, const T* b, uint32
     return ZB_OK;
 }
 
+
+// ---- PCA centering (pca.zig:135-154): column means (f64 accumulation, deterministic two-stage) and X - mean ----
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, uint32_t n, uint32_t dim, uint32_t rows_per_block,
+                                                     double* __restrict__ partial /* [gridDim.y][dim] */) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    const uint32_t r0 = blockIdx.y * rows_per_block;
+    const uint32_t r1 = min(n, r0 + rows_per_block);
+    double s = 0.0;
+    for (uint32_t i = r0; i < r1; ++i) s += (double)x[(size_t)i * dim + j];
+    partial[(size_t)blockIdx.y * dim + j] = s;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) colmean_finish(const double* __restrict__ partial, uint32_t parts, uint32_t n, uint32_t dim,
+                                                      T* __restrict__ mean) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    double s = 0.0;
+    for (uint32_t p = 0; p < parts; ++p) s += partial[(size_t)p * dim + j];
+    mean[j] = (T)(s / (double)n);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) center_kernel(const T* __restrict__ x, const T* __restrict__ mean, size_t total, uint32_t dim,
+                                                     T* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    out[i] = x[i] - mean[i % dim];
+}
+
+template <typename T>
+int center_columns(const T* x, uint32_t n, uint32_t dim, T* mean, int compute_mean, T* centered, cudaStream_t s) {
+    if (!x || !mean) return ZB_ERR_INVALID_ARGUMENT;
+    if (n == 0 || dim == 0) return ZB_OK;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (compute_mean) {
+        const uint32_t col_blocks = div_up(dim, 256);
+        uint32_t parts = std::max<uint32_t>(1, (uint32_t)(4 * di.sm_count) / col_blocks);
+        parts = std::min<uint32_t>(parts, std::max<uint32_t>(1, n / 64));
+        const uint32_t rows_per_block = (n + parts - 1) / parts;
+        parts = (n + rows_per_block - 1) / rows_per_block;
+        Scratch part;
+        if ((rc = part.alloc((size_t)parts * dim * sizeof(double), s))) return rc;
+        colsum_kernel<T><<<dim3(col_blocks, parts), 256, 0, s>>>(x, n, dim, rows_per_block, part.as<double>());
+        ZB_LAUNCHED();
+        colmean_finish<T><<<col_blocks, 256, 0, s>>>(part.as<double>(), parts, n, dim, mean);
+        ZB_LAUNCHED();
+    }
+    if (centered) {
+        const size_t total = (size_t)n * dim;
+        center_kernel<T><<<div_up(total, 256), 256, 0, s>>>(x, mean, total, dim, centered);
+        ZB_LAUNCHED();
+    }
+    return ZB_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -381,6 +439,12 @@ int zb_gemm_f32(const float* a, uint32_t ar, uint32_t ac, int ta, const float* b
 int zb_gemm_f64(const double* a, uint32_t ar, uint32_t ac, int ta, const double* b, uint32_t br, uint32_t bc, int tb, double alpha,
                 double beta, const double* c, double* out, zb_stream s) {
     return gemm_device<double>(a, ar, ac, ta, b, br, bc, tb, alpha, beta, c, out, (cudaStream_t)s);
+}
+int zb_center_columns_f32(const float* x, uint32_t n, uint32_t dim, float* mean, int compute_mean, float* centered, zb_stream s) {
+    return center_columns<float>(x, n, dim, mean, compute_mean, centered, (cudaStream_t)s);
+}
+int zb_center_columns_f64(const double* x, uint32_t n, uint32_t dim, double* mean, int compute_mean, double* centered, zb_stream s) {
+    return center_columns<double>(x, n, dim, mean, compute_mean, centered, (cudaStream_t)s);
 }
 int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged) {
     return svd_entry<double>(a, m, n, mode, with_v, u, s, v, converged);

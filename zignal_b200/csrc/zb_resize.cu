@@ -201,9 +201,9 @@ int launch_plane(const zb_image* src, zb_image* dst, int method, const TapEntry*
 }
 
 // resizeGeneric, interpolation.zig:194-214
-template <typename CT, int N>
+template <typename CT, int N, int METHOD>
 __global__ void __launch_bounds__(256) resize_generic_kernel(SrcView img, CT* __restrict__ dst, size_t dst_stride, int dst_rows,
-                                                             int dst_cols, float scale_x, float scale_y, int method, float mb, float mc,
+                                                             int dst_cols, float scale_x, float scale_y, float mb, float mc,
                                                              const float* __restrict__ lut) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(SrcView img, CT* __
     const float src_y = ((float)r + 0.5f) * scale_y - 0.5f;
     const float src_x = ((float)c + 0.5f) * scale_x - 0.5f;
     Pix<CT, N> val;
-    if (!interpolate<CT, N>(img, src_x, src_y, method, mb, mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD>(img, src_x, src_y, mb, mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 
@@ -221,10 +221,12 @@ int launch_generic(const zb_image* src, zb_image* dst, int method, float mb, flo
     const float scale_x = (float)src->cols / (float)dst->cols;
     const float scale_y = (float)src->rows / (float)dst->rows;
     dim3 grid(div_up(dst->cols, 256), dst->rows);
-    resize_generic_kernel<CT, N><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows, (int)dst->cols, scale_x, scale_y,
-                                                      method, mb, mc, lut);
-    ZB_LAUNCHED();
-    return ZB_OK;
+    return dispatch_method(method, [&](auto m) -> int {
+        resize_generic_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows,
+                                                                              (int)dst->cols, scale_x, scale_y, mb, mc, lut);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    });
 }
 
 }  // namespace

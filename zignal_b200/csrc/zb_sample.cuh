@@ -8,6 +8,9 @@
 // This translation unit family is compiled with -fmad=false: every f32 expression below is evaluated
 // exactly as written (separately rounded mul/add), which is what the reference's Zig does.
 #pragma once
+#include <type_traits>
+
+#include "../../include/zignal_b200.h"
 #include "zb_device.cuh"
 
 namespace zb {
@@ -112,95 +115,137 @@ __device__ __forceinline__ uint8_t lerp_int_u8(int tl, int tr, int bl, int br, i
     return (uint8_t)(result < 0 ? 0 : (result > 255 ? 255 : result));
 }
 
-// interpolation.zig:72-84.  Returns false for null (caller writes zeroes).
-template <typename CT, int N>
-__device__ __forceinline__ bool interpolate(const SrcView& img, float x, float y, int method, float mb, float mc, int border,
-                                            const float* __restrict__ lut, Pix<CT, N>& out) {
-    if (!isfinite(x) || !isfinite(y)) return false;
-    const float range_limit = 4611686018427387904.0f;  // @floatFromInt(maxInt(isize) / 2)
-    if (fabsf(x) > range_limit || fabsf(y) > range_limit) return false;
-    const CT* base = (const CT*)img.data;
-    const long long rows = img.rows, cols = img.cols;
+// Index arithmetic is templated: `int` when the sample coordinates are far inside the i32 range (always,
+// in practice), `long long` otherwise -- the reference uses isize (interpolation.zig:314-322).
+template <typename I>
+__device__ __forceinline__ I resolve_idx(I idx, I length, int border) {
+    if (idx >= 0 && idx < length) return idx;
+    if (border == 0) return -1;
+    if (length <= 0) return -1;
+    if (border == 1) return idx < 0 ? 0 : length - 1;
+    if (border == 2) {
+        if (length == 1) return 0;
+        const I period = 2 * (length - 1);
+        I m = idx % period;
+        if (m < 0) m += period;
+        return m >= length ? period - m : m;
+    }
+    I m = idx % length;
+    if (m < 0) m += length;
+    return m;
+}
 
-    if (method == ZB_INTERP_NEAREST) {  // :306-311
-        const long long col = resolve_index64((long long)roundf(x), cols, border);
+template <typename CT, int N, int METHOD, typename I>
+__device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, float y, float mb, float mc, int border,
+                                                 const float* __restrict__ lut, Pix<CT, N>& out) {
+    const CT* base = (const CT*)img.data;
+    const I rows = (I)img.rows, cols = (I)img.cols;
+
+    if constexpr (METHOD == ZB_INTERP_NEAREST) {  // :306-311
+        const I col = resolve_idx<I>((I)roundf(x), cols, border);
         if (col < 0) return false;
-        const long long row = resolve_index64((long long)roundf(y), rows, border);
+        const I row = resolve_idx<I>((I)roundf(y), rows, border);
         if (row < 0) return false;
         out = load_px<CT, N>(base, (size_t)row * img.stride + (size_t)col);
         return true;
-    }
-    if (method == ZB_INTERP_BILINEAR) {  // :313-407
+    } else if constexpr (METHOD == ZB_INTERP_BILINEAR) {  // :313-407
         const float flx = floorf(x), fly = floorf(y);
-        const long long left = (long long)flx, top = (long long)fly;
-        const long long r0 = resolve_index64(top, rows, border), r1 = resolve_index64(top + 1, rows, border);
-        const long long c0 = resolve_index64(left, cols, border), c1 = resolve_index64(left + 1, cols, border);
+        const I left = (I)flx, top = (I)fly;
+        const I r0 = resolve_idx<I>(top, rows, border), r1 = resolve_idx<I>(top + 1, rows, border);
+        const I c0 = resolve_idx<I>(left, cols, border), c1 = resolve_idx<I>(left + 1, cols, border);
         if (border == ZB_BORDER_MIRROR && (r0 < 0 || r1 < 0 || c0 < 0 || c1 < 0)) return false;  // :337-339
         const Pix<CT, N> z = zero_px<CT, N>();
         const Pix<CT, N> tl = (r0 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c0) : z;
         const Pix<CT, N> tr = (r0 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c1) : z;
         const Pix<CT, N> bl = (r1 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c0) : z;
         const Pix<CT, N> br = (r1 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c1) : z;
-        const float lr = x - flx;  // as(f32, left) == floor(x) for |x| < 2^62 up to f32 rounding of the i64 -> same value
+        const float lr = x - flx;  // == x - as(f32, left): floor(x) is exactly representable
         const float tb = y - fly;
         if constexpr (sizeof(CT) == 1) {
-            const int fx = (int)roundf(lr * 256.0f), fy = (int)roundf(tb * 256.0f);
+            // :349-367.  fx, fy in [0, 256]; every intermediate is non-negative and < 2^25, so unsigned shift == @divTrunc
+            const unsigned fx = (unsigned)(int)roundf(lr * 256.0f), fy = (unsigned)(int)roundf(tb * 256.0f);
 #pragma unroll
-            for (int k = 0; k < N; ++k) out.v[k] = lerp_int_u8(tl.v[k], tr.v[k], bl.v[k], br.v[k], fx, fy);
+            for (int k = 0; k < N; ++k) {
+                const unsigned top_val = (unsigned)tl.v[k] * (256u - fx) + (unsigned)tr.v[k] * fx;
+                const unsigned bottom_val = (unsigned)bl.v[k] * (256u - fx) + (unsigned)br.v[k] * fx;
+                const unsigned result = (top_val * (256u - fy) + bottom_val * fy + 32768u) >> 16;
+                out.v[k] = (uint8_t)(result > 255u ? 255u : result);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < N; ++k)
                 out.v[k] = (1 - tb) * ((1 - lr) * tl.v[k] + lr * tr.v[k]) + tb * ((1 - lr) * bl.v[k] + lr * br.v[k]);
         }
         return true;
-    }
-    // kernel samplers, :426-519
-    const int window_radius = (method == ZB_INTERP_LANCZOS) ? 3 : 2;
-    const int window_size = window_radius * 2;
-    const float flx = floorf(x), fly = floorf(y);
-    const long long ix = (long long)flx, iy = (long long)fly;
-    const float fx = x - flx, fy = y - fly;
-    float xw[6], yw[6];
+    } else {
+        // kernel samplers, :426-519
+        constexpr int window_radius = (METHOD == ZB_INTERP_LANCZOS) ? 3 : 2;
+        constexpr int window_size = window_radius * 2;
+        const float flx = floorf(x), fly = floorf(y);
+        const I ix = (I)flx, iy = (I)fly;
+        const float fx = x - flx, fy = y - fly;
+        float xw[window_size], yw[window_size];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        if (i < window_size) {
+        for (int i = 0; i < window_size; ++i) {
             const float off = (float)(i - (window_radius - 1));
             const float ox = off - fx, oy = off - fy;
-            switch (method) {
-                case ZB_INTERP_BICUBIC: xw[i] = bicubic_kernel(ox); yw[i] = bicubic_kernel(oy); break;
-                case ZB_INTERP_CATMULL_ROM: xw[i] = catmull_rom_kernel(ox); yw[i] = catmull_rom_kernel(oy); break;
-                case ZB_INTERP_LANCZOS: xw[i] = lanczos3_kernel_lut(ox, lut); yw[i] = lanczos3_kernel_lut(oy, lut); break;
-                default: xw[i] = mitchell_kernel(ox, mb, mc); yw[i] = mitchell_kernel(oy, mb, mc); break;
+            if constexpr (METHOD == ZB_INTERP_BICUBIC) { xw[i] = bicubic_kernel(ox); yw[i] = bicubic_kernel(oy); }
+            else if constexpr (METHOD == ZB_INTERP_CATMULL_ROM) { xw[i] = catmull_rom_kernel(ox); yw[i] = catmull_rom_kernel(oy); }
+            else if constexpr (METHOD == ZB_INTERP_LANCZOS) { xw[i] = lanczos3_kernel_lut(ox, lut); yw[i] = lanczos3_kernel_lut(oy, lut); }
+            else { xw[i] = mitchell_kernel(ox, mb, mc); yw[i] = mitchell_kernel(oy, mb, mc); }
+        }
+        float sums[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) sums[k] = 0;
+        float weight_sum = 0;
+#pragma unroll
+        for (int j = 0; j < window_size; ++j) {
+            const I py = resolve_idx<I>(iy - (window_radius - 1) + j, rows, border);
+            if (py < 0) continue;
+#pragma unroll
+            for (int i = 0; i < window_size; ++i) {
+                const I px = resolve_idx<I>(ix - (window_radius - 1) + i, cols, border);
+                if (px < 0) continue;
+                const Pix<CT, N> pixel = load_px<CT, N>(base, (size_t)py * img.stride + (size_t)px);
+                const float weight = xw[i] * yw[j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) sums[k] += (float)pixel.v[k] * weight;
+                weight_sum += weight;
             }
         }
-    }
-    float sums[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) sums[k] = 0;
-    float weight_sum = 0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        if (j >= window_size) break;
-        const long long py = resolve_index64(iy - (window_radius - 1) + j, rows, border);
-        if (py < 0) continue;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i >= window_size) break;
-            const long long px = resolve_index64(ix - (window_radius - 1) + i, cols, border);
-            if (px < 0) continue;
-            const Pix<CT, N> pixel = load_px<CT, N>(base, (size_t)py * img.stride + (size_t)px);
-            const float weight = xw[i] * yw[j];
-#pragma unroll
-            for (int k = 0; k < N; ++k) sums[k] += (float)pixel.v[k] * weight;
-            weight_sum += weight;
+        for (int k = 0; k < N; ++k) {
+            const float val = weight_sum != 0 ? sums[k] / weight_sum : 0.0f;
+            out.v[k] = clamp_channel<CT>(val);
         }
+        return true;
     }
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const float val = weight_sum != 0 ? sums[k] / weight_sum : 0.0f;
-        out.v[k] = clamp_channel<CT>(val);
+}
+
+// interpolation.zig:72-84.  Returns false for null (caller writes zeroes).
+template <typename CT, int N, int METHOD>
+__device__ __forceinline__ bool interpolate(const SrcView& img, float x, float y, float mb, float mc, int border,
+                                            const float* __restrict__ lut, Pix<CT, N>& out) {
+    if (fabsf(x) < 1.0e9f && fabsf(y) < 1.0e9f)  // finite and far inside the i32 range: 32-bit index math
+        return interpolate_impl<CT, N, METHOD, int>(img, x, y, mb, mc, border, lut, out);
+    if (!isfinite(x) || !isfinite(y)) return false;
+    const float range_limit = 4611686018427387904.0f;  // @floatFromInt(maxInt(isize) / 2)
+    if (fabsf(x) > range_limit || fabsf(y) > range_limit) return false;
+    return interpolate_impl<CT, N, METHOD, long long>(img, x, y, mb, mc, border, lut, out);
+}
+
+// Run `f(std::integral_constant<int, METHOD>)` for the runtime interpolation method.
+template <typename F>
+static inline int dispatch_method(int method, F&& f) {
+    switch (method) {
+        case ZB_INTERP_NEAREST: return f(std::integral_constant<int, ZB_INTERP_NEAREST>{});
+        case ZB_INTERP_BILINEAR: return f(std::integral_constant<int, ZB_INTERP_BILINEAR>{});
+        case ZB_INTERP_BICUBIC: return f(std::integral_constant<int, ZB_INTERP_BICUBIC>{});
+        case ZB_INTERP_CATMULL_ROM: return f(std::integral_constant<int, ZB_INTERP_CATMULL_ROM>{});
+        case ZB_INTERP_MITCHELL: return f(std::integral_constant<int, ZB_INTERP_MITCHELL>{});
+        case ZB_INTERP_LANCZOS: return f(std::integral_constant<int, ZB_INTERP_LANCZOS>{});
     }
-    return true;
+    return ZB_ERR_INVALID_ARGUMENT;
 }
 
 }  // namespace zb

@@ -43,7 +43,7 @@ struct RotParams {
     float mb, mc;
 };
 
-template <typename CT, int N>
+template <typename CT, int N, int METHOD>
 __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long long src_image_pitch, CT* __restrict__ dst, size_t dst_stride,
                                                      unsigned long long dst_image_pitch, int dst_rows, int dst_cols, RotParams p,
                                                      const float* __restrict__ lut) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
     const float src_x = rotated_dx + p.cx;
     const float src_y = rotated_dy + p.cy;
     Pix<CT, N> val;
-    if (!interpolate<CT, N>(img, src_x, src_y, p.method, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 
@@ -99,7 +99,7 @@ struct WarpParams {
     float mb, mc;
 };
 
-template <typename CT, int N>
+template <typename CT, int N, int METHOD>
 __global__ void __launch_bounds__(256) warp_kernel(SrcView img, CT* __restrict__ dst, size_t dst_stride, int dst_rows, int dst_cols,
                                                    WarpParams p, const float* __restrict__ lut) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) warp_kernel(SrcView img, CT* __restrict__
         sy = a1 + p.m[5];
     }
     Pix<CT, N> val;
-    if (!interpolate<CT, N>(img, sx, sy, p.method, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD>(img, sx, sy, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 
@@ -159,9 +159,12 @@ int rotate_typed(const zb_image* src, unsigned long long spitch, zb_image* dst, 
     p.method = method; p.border = border; p.mb = mb; p.mc = mc;
     SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
     t_last_kernel = "rotate_gather";
-    rotate_kernel<CT, N><<<grid, 256, 0, s>>>(v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows, (int)dst->cols, p, lut);
-    ZB_LAUNCHED();
-    return ZB_OK;
+    return dispatch_method(method, [&](auto m) -> int {
+        rotate_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows,
+                                                                      (int)dst->cols, p, lut);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    });
 }
 
 int rotate_dispatch(const zb_image* src, unsigned long long spitch, zb_image* dst, unsigned long long dpitch, uint32_t n, int pixfmt,
@@ -190,9 +193,11 @@ template <typename CT, int N>
 int warp_typed(const zb_image* src, zb_image* dst, const WarpParams& p, const float* lut, cudaStream_t s) {
     SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
     dim3 grid(div_up(dst->cols, 32), div_up(dst->rows, 8));
-    warp_kernel<CT, N><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows, (int)dst->cols, p, lut);
-    ZB_LAUNCHED();
-    return ZB_OK;
+    return dispatch_method(p.method, [&](auto m) -> int {
+        warp_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows, (int)dst->cols, p, lut);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    });
 }
 
 int warp_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int kind, const float* m, int method, float mb, float mc, cudaStream_t s) {

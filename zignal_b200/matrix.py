@@ -37,6 +37,17 @@ def gemm_device(a, b, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, c=None)
     return out
 
 
+def center_columns(x, mean, compute_mean: bool, centered):
+    """Pca centering on CUDA tensors: (optionally) mean[j] = column mean of x, centered = x - mean."""
+    import torch
+    n, dim = x.shape
+    stream = torch.cuda.current_stream().cuda_stream
+    if x.dtype == torch.float32:
+        check(lib().zb_center_columns_f32(_ptr(x, C.c_float), n, dim, _ptr(mean, C.c_float), int(compute_mean), _ptr(centered, C.c_float), stream))
+    else:
+        check(lib().zb_center_columns_f64(_ptr(x, C.c_double), n, dim, _ptr(mean, C.c_double), int(compute_mean), _ptr(centered, C.c_double), stream))
+
+
 def gemm(a: np.ndarray, b: np.ndarray, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, c=None) -> np.ndarray:
     """numpy in / numpy out convenience wrapper around `gemm_device`."""
     import torch

@@ -30,9 +30,9 @@ class Pca:
         k = min(num_components if num_components is not None else max_components, max_components)
         self.dim = dim
         x = torch.from_numpy(data).cuda()
-        # pca.zig:135-144: column sums then / n.  (Device reduction order differs from the sequential host loop; tolerance-based.)
-        mean = (x.sum(dim=0, dtype=torch.float64) / n).to(x.dtype)
-        centered = (x - mean).contiguous()
+        mean = torch.empty(dim, dtype=x.dtype, device=x.device)
+        centered = torch.empty_like(x)
+        matrix.center_columns(x, mean, True, centered)  # pca.zig:135-154 (f64-accumulated column means; tolerance-based)
         scale = 1.0 / float(n - 1)
         self.mean = mean.cpu().numpy()
         if n <= dim:  # Gram path, pca.zig:380-425
@@ -62,7 +62,8 @@ class Pca:
         if data.shape[1] != self.dim:
             raise ZignalError(1, "DimensionMismatch")
         x = torch.from_numpy(data).cuda()
-        centered = (x - torch.from_numpy(self.mean).cuda()).contiguous()
+        centered = torch.empty_like(x)
+        matrix.center_columns(x, torch.from_numpy(self.mean).cuda(), False, centered)  # pca.zig:300-308
         comps = torch.from_numpy(np.ascontiguousarray(self.components)).cuda()
         return matrix.gemm_device(centered, comps, False, False, 1.0, 0.0, None).cpu().numpy()
 

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <vector>
 
 #include "zignal_oracle.h"
@@ -27,12 +28,14 @@ struct Img {
 };
 
 // An owning contiguous plane (what `Image(T).init(allocator, rows, cols)` gives, image.zig:124-132).
+// Like the reference's allocator.alloc, the storage is NOT initialised (so a parallel first pass first-touches its own pages).
 template <typename T>
 struct Plane {
-    std::vector<T> buf;
+    std::unique_ptr<T[]> store;
+    T* buf;
     uint32_t rows, cols;
-    Plane(uint32_t r, uint32_t c) : buf((size_t)r * c), rows(r), cols(c) {}
-    Img<T> img() { return Img<T>(buf.data(), rows, cols, cols); }
+    Plane(uint32_t r, uint32_t c) : store(new T[(size_t)r * c + 1]), buf(store.get()), rows(r), cols(c) {}
+    Img<T> img() { return Img<T>(buf, rows, cols, cols); }
 };
 
 // Zig @mod for integers is floored modulo (border.zig:57,61).

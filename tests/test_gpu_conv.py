@@ -100,6 +100,51 @@ def test_fused_rgbaf32_exact_and_fma(zb, rows, cols, border):
     L.zb_tune(b"conv.variant", -1)
 
 
+@pytest.mark.parametrize("rows,cols", [(64, 64), (96, 520), (300, 776), (513, 1032), (40, 16), (257, 260)])
+@pytest.mark.parametrize("border", BORDERS)
+def test_fused_rgba8_bit_exact(zb, rows, cols, border):
+    rng = np.random.default_rng(rows * 7 + cols)
+    L = zb.lib()
+    for half in (1, 2, 4, 7, 8):
+        img = rand_image(rng, (rows, cols, 4), np.uint8)
+        for k in (_taps(rng, 2 * half + 1), (rng.standard_normal(2 * half + 1) * 0.4).astype(np.float32)):  # positive and signed taps
+            got = zb.Image.from_numpy(img).convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+            assert L.zb_last_kernel().decode() == "fused_sep_rgba8", L.zb_last_kernel().decode()
+            assert np.array_equal(got, zo.conv_separable(img, k, k, border)), (half,)
+
+
+def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
+    rng = np.random.default_rng(77)
+    L = zb.lib()
+    img = rand_image(rng, (200, 304, 4), np.uint8)
+    big = zb.Image.from_numpy(img)
+    v = big.view(zb.Rectangle(8, 5, 292, 190))          # offset 8 px = 32 B: still 16-byte aligned, pitch 304 px
+    crop = np.ascontiguousarray(img[5:190, 8:292])
+    out_big = zb.Image.from_numpy(np.full((220, 312, 4), 9, np.uint8))
+    ov = out_big.view(zb.Rectangle(3, 2, 287, 187))
+    kx, ky = _taps(rng, 6), _taps(rng, 15)
+    v.convolve_separable(kx, ky, zb.BorderMode.MIRROR, out=ov)
+    assert L.zb_last_kernel().decode() == "fused_sep_rgba8"
+    full = out_big.to_numpy()
+    assert np.array_equal(full[2:187, 3:287], zo.conv_separable(crop, kx, ky, "mirror"))
+    mask = np.ones(full.shape[:2], bool)
+    mask[2:187, 3:287] = False
+    assert np.all(full[mask] == 9)
+    # a view that breaks TMA alignment (offset 3 px) and taps that need i64 accumulators fall back to the generic path
+    v2 = big.view(zb.Rectangle(3, 0, 299, 100))
+    got = v2.convolve_separable(kx, ky, zb.BorderMode.WRAP).to_numpy()
+    assert L.zb_last_kernel().decode() == "sep_generic_u8"
+    assert np.array_equal(got, zo.conv_separable(np.ascontiguousarray(img[0:100, 3:299]), kx, ky, "wrap"))
+    huge = (rng.standard_normal(5) * 3000).astype(np.float32)
+    got = big.convolve_separable(huge, huge, zb.BorderMode.MIRROR).to_numpy()
+    assert L.zb_last_kernel().decode() == "sep_generic_u8"
+    assert np.array_equal(got, zo.conv_separable(img, huge, huge, "mirror"))
+    for sigma in (0.5, 1.0, 2.25):
+        got = big.gaussian_blur(sigma).to_numpy()
+        assert L.zb_last_kernel().decode() == "fused_sep_rgba8"
+        assert np.array_equal(got, zo.gaussian_blur(img, sigma)), sigma
+
+
 def test_fused_handles_views_even_and_unequal_kernels(zb):
     rng = np.random.default_rng(7)
     L = zb.lib()

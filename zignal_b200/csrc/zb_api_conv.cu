@@ -30,6 +30,10 @@ int conv_separable_dispatch(const zb_image* src, zb_image* dst, int pixfmt, cons
         rc = conv_separable_fused_rgbaf32(src, dst, kx, nx, ky, ny, border, g_exact_f32.load() != 0, s);
         if (rc != ZB_ERR_UNSUPPORTED) return rc;
     }
+    if (pixfmt == ZB_PIX_RGBA8 && !g_force_generic.load()) {
+        rc = conv_separable_fused_rgba8(src, dst, kx, nx, ky, ny, border, s);
+        if (rc != ZB_ERR_UNSUPPORTED) return rc;
+    }
     return conv_separable_generic(src, dst, pixfmt, kx, nx, ky, ny, border, s);
 }
 

@@ -18,4 +18,8 @@ int convolve_generic(const zb_image* src, zb_image* dst, int pixfmt, const float
 int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
                                  bool exact, cudaStream_t s);
 
+// zb_conv_fused_u8.cu: single-pass separable convolution of interleaved Rgba(u8) (i32 accumulators, provably overflow-free taps).
+int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
+                               cudaStream_t s);
+
 }  // namespace zb

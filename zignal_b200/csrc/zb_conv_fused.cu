@@ -28,6 +28,7 @@
 // filter code itself has no border branches.
 #include "zb_conv.h"
 #include "zb_device.cuh"
+#include "zb_tma.cuh"
 
 namespace zb {
 
@@ -60,59 +61,6 @@ struct FusedParams {
     int fix_left;    // 1 if x < 0 needs patching
     int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-struct U2 {  // one RGBA f32 pixel as two packed f32x2 registers
-    unsigned long long lo, hi;
-};
-__device__ __forceinline__ U2 lds128_u2(uint32_t addr) {
-    U2 v;
-    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128_u2(uint32_t addr, const U2& v) {
-    asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(v.lo), "l"(v.hi) : "memory");
-}
-__device__ __forceinline__ void stg128_cs_u2(void* ptr, const U2& v) {
-    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(ptr), "l"(v.lo), "l"(v.hi) : "memory");
-}
-__device__ __forceinline__ void mac_u2(U2& acc, const U2& v, unsigned long long k2) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.lo) : "l"(v.lo), "l"(k2));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.hi) : "l"(v.hi), "l"(k2));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
-}
 
 template <bool EXACT>
 __device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {

@@ -108,6 +108,13 @@ int gemm_device(const T* a, uint32_t ar, uint32_t ac, int ta, const T* b, uint32
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
+    if constexpr (sizeof(T) == 4) {
+        // Pca.fit's covariance step (pca.zig:338): X^T X with the same matrix on both sides -> tensor cores
+        if (ta && !tb && (const void*)a == (const void*)b && !g_force_generic.load()) {
+            rc = gemm_xtx_tensorcore((const float*)a, ar, ac, (float)alpha, (float)beta, (const float*)c, (float*)out, s);
+            if (rc != ZB_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const int tiles = div_up(M, BM) * div_up(N, BN);
     int splits = 1;
     if (K > 4 * BK) {

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(SrcView img, CT* __
     const float src_y = ((float)r + 0.5f) * scale_y - 0.5f;
     const float src_x = ((float)c + 0.5f) * scale_x - 0.5f;
     Pix<CT, N> val;
-    if (!interpolate<CT, N, METHOD>(img, src_x, src_y, mb, mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD, ZB_BORDER_MIRROR>(img, src_x, src_y, mb, mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 

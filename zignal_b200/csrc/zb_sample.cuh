@@ -135,11 +135,13 @@ __device__ __forceinline__ I resolve_idx(I idx, I length, int border) {
     return m;
 }
 
-template <typename CT, int N, int METHOD, typename I>
-__device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, float y, float mb, float mc, int border,
+// BORDER_T >= 0 fixes the border mode at compile time (the hot combinations); -1 keeps it a runtime value.
+template <typename CT, int N, int METHOD, typename I, int BORDER_T = -1>
+__device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, float y, float mb, float mc, int border_rt,
                                                  const float* __restrict__ lut, Pix<CT, N>& out) {
     const CT* base = (const CT*)img.data;
     const I rows = (I)img.rows, cols = (I)img.cols;
+    const int border = BORDER_T >= 0 ? BORDER_T : border_rt;
 
     if constexpr (METHOD == ZB_INTERP_NEAREST) {  // :306-311
         const I col = resolve_idx<I>((I)roundf(x), cols, border);
@@ -151,14 +153,24 @@ __device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, fl
     } else if constexpr (METHOD == ZB_INTERP_BILINEAR) {  // :313-407
         const float flx = floorf(x), fly = floorf(y);
         const I left = (I)flx, top = (I)fly;
-        const I r0 = resolve_idx<I>(top, rows, border), r1 = resolve_idx<I>(top + 1, rows, border);
-        const I c0 = resolve_idx<I>(left, cols, border), c1 = resolve_idx<I>(left + 1, cols, border);
-        if (border == ZB_BORDER_MIRROR && (r0 < 0 || r1 < 0 || c0 < 0 || c1 < 0)) return false;  // :337-339
-        const Pix<CT, N> z = zero_px<CT, N>();
-        const Pix<CT, N> tl = (r0 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c0) : z;
-        const Pix<CT, N> tr = (r0 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c1) : z;
-        const Pix<CT, N> bl = (r1 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c0) : z;
-        const Pix<CT, N> br = (r1 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c1) : z;
+        Pix<CT, N> tl, tr, bl, br;
+        if (left >= 0 && left + 1 < cols && top >= 0 && top + 1 < rows) {  // all four neighbours inside: no border logic
+            const CT* q = base + ((size_t)top * img.stride + (size_t)left) * N;
+            tl = load_px<CT, N>(q, 0);
+            tr = load_px<CT, N>(q, 1);
+            bl = load_px<CT, N>(q, img.stride);
+            br = load_px<CT, N>(q, img.stride + 1);
+        } else {
+            const I r0 = resolve_idx<I>(top, rows, border), r1 = resolve_idx<I>(top + 1, rows, border);
+            const I c0 = resolve_idx<I>(left, cols, border), c1 = resolve_idx<I>(left + 1, cols, border);
+            if (border == ZB_BORDER_MIRROR && (r0 < 0 || r1 < 0 || c0 < 0 || c1 < 0)) return false;  // :337-339
+            const Pix<CT, N> z = zero_px<CT, N>();
+            if (border == ZB_BORDER_ZERO && (r0 < 0 && r1 < 0 || c0 < 0 && c1 < 0)) { out = z; return true; }  // all four are zero
+            tl = (r0 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c0) : z;
+            tr = (r0 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r0 * img.stride + (size_t)c1) : z;
+            bl = (r1 >= 0 && c0 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c0) : z;
+            br = (r1 >= 0 && c1 >= 0) ? load_px<CT, N>(base, (size_t)r1 * img.stride + (size_t)c1) : z;
+        }
         const float lr = x - flx;  // == x - as(f32, left): floor(x) is exactly representable
         const float tb = y - fly;
         if constexpr (sizeof(CT) == 1) {
@@ -223,11 +235,11 @@ __device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, fl
 }
 
 // interpolation.zig:72-84.  Returns false for null (caller writes zeroes).
-template <typename CT, int N, int METHOD>
+template <typename CT, int N, int METHOD, int BORDER_T = -1>
 __device__ __forceinline__ bool interpolate(const SrcView& img, float x, float y, float mb, float mc, int border,
                                             const float* __restrict__ lut, Pix<CT, N>& out) {
     if (fabsf(x) < 1.0e9f && fabsf(y) < 1.0e9f)  // finite and far inside the i32 range: 32-bit index math
-        return interpolate_impl<CT, N, METHOD, int>(img, x, y, mb, mc, border, lut, out);
+        return interpolate_impl<CT, N, METHOD, int, BORDER_T>(img, x, y, mb, mc, border, lut, out);
     if (!isfinite(x) || !isfinite(y)) return false;
     const float range_limit = 4611686018427387904.0f;  // @floatFromInt(maxInt(isize) / 2)
     if (fabsf(x) > range_limit || fabsf(y) > range_limit) return false;

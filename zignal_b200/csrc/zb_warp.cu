@@ -43,7 +43,7 @@ struct RotParams {
     float mb, mc;
 };
 
-template <typename CT, int N, int METHOD>
+template <typename CT, int N, int METHOD, int BORDER_T>
 __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long long src_image_pitch, CT* __restrict__ dst, size_t dst_stride,
                                                      unsigned long long dst_image_pitch, int dst_rows, int dst_cols, RotParams p,
                                                      const float* __restrict__ lut) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
     const float src_x = rotated_dx + p.cx;
     const float src_y = rotated_dy + p.cy;
     Pix<CT, N> val;
-    if (!interpolate<CT, N, METHOD>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) warp_kernel(SrcView img, CT* __restrict__
         sy = a1 + p.m[5];
     }
     Pix<CT, N> val;
-    if (!interpolate<CT, N, METHOD>(img, sx, sy, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
+    if (!interpolate<CT, N, METHOD, ZB_BORDER_MIRROR>(img, sx, sy, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) val = zero_px<CT, N>();
     store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
 }
 
@@ -160,8 +160,15 @@ int rotate_typed(const zb_image* src, unsigned long long spitch, zb_image* dst, 
     SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
     t_last_kernel = "rotate_gather";
     return dispatch_method(method, [&](auto m) -> int {
-        rotate_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows,
-                                                                      (int)dst->cols, p, lut);
+        constexpr int M = decltype(m)::value;
+        // the default front-end combination (bilinear / nearest with .zero, python binding transforms.zig:250-251) gets a
+        // kernel with the border folded at compile time; everything else keeps it a runtime value
+        if ((M == ZB_INTERP_BILINEAR || M == ZB_INTERP_NEAREST) && border == ZB_BORDER_ZERO)
+            rotate_kernel<CT, N, M, (M == ZB_INTERP_BILINEAR || M == ZB_INTERP_NEAREST) ? ZB_BORDER_ZERO : -1><<<grid, 256, 0, s>>>(
+                v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows, (int)dst->cols, p, lut);
+        else
+            rotate_kernel<CT, N, M, -1><<<grid, 256, 0, s>>>(v, spitch, (CT*)dst->data, (size_t)dst->stride, dpitch, (int)dst->rows,
+                                                             (int)dst->cols, p, lut);
         ZB_LAUNCHED();
         return ZB_OK;
     });

@@ -108,9 +108,13 @@ def test_fused_rgba8_bit_exact(zb, rows, cols, border):
     for half in (1, 2, 4, 7, 8):
         img = rand_image(rng, (rows, cols, 4), np.uint8)
         for k in (_taps(rng, 2 * half + 1), (rng.standard_normal(2 * half + 1) * 0.4).astype(np.float32)):  # positive and signed taps
-            got = zb.Image.from_numpy(img).convolve_separable(k, k, border_enum(zb, border)).to_numpy()
-            assert L.zb_last_kernel().decode() == "fused_sep_rgba8", L.zb_last_kernel().decode()
-            assert np.array_equal(got, zo.conv_separable(img, k, k, border)), (half,)
+            want = zo.conv_separable(img, k, k, border)
+            for fmath in (1, 0):  # exact-integer pipeline on FFMA (when provably exact) and on IMAD
+                L.zb_tune(b"conv.u8_fmath", fmath)
+                got = zb.Image.from_numpy(img).convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+                assert L.zb_last_kernel().decode().startswith("fused_sep_rgba8"), L.zb_last_kernel().decode()
+                assert np.array_equal(got, want), (half, fmath, L.zb_last_kernel().decode())
+    L.zb_tune(b"conv.u8_fmath", 1)
 
 
 def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
@@ -124,7 +128,7 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     ov = out_big.view(zb.Rectangle(3, 2, 287, 187))
     kx, ky = _taps(rng, 6), _taps(rng, 15)
     v.convolve_separable(kx, ky, zb.BorderMode.MIRROR, out=ov)
-    assert L.zb_last_kernel().decode() == "fused_sep_rgba8"
+    assert L.zb_last_kernel().decode() == "fused_sep_rgba8_f"
     full = out_big.to_numpy()
     assert np.array_equal(full[2:187, 3:287], zo.conv_separable(crop, kx, ky, "mirror"))
     mask = np.ones(full.shape[:2], bool)
@@ -141,7 +145,7 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     assert np.array_equal(got, zo.conv_separable(img, huge, huge, "mirror"))
     for sigma in (0.5, 1.0, 2.25):
         got = big.gaussian_blur(sigma).to_numpy()
-        assert L.zb_last_kernel().decode() == "fused_sep_rgba8"
+        assert L.zb_last_kernel().decode() == "fused_sep_rgba8_f"
         assert np.array_equal(got, zo.gaussian_blur(img, sigma)), sigma
 
 

@@ -145,6 +145,38 @@ def test_gemm(zb, dtype, tol, ta, tb):
         gemm(np.zeros((3, 4), dtype), np.zeros((5, 2), dtype))
 
 
+@pytest.mark.parametrize("n,dim,positive", [(4096, 128, False), (8200, 256, False), (8200, 256, True), (5003, 384, False)])
+def test_gemm_xtx_tensorcore(zb, n, dim, positive):
+    """Pca.fit's covariance contraction (pca.zig:338): the tcgen05 3xTF32 kernel against the oracle's reference-order f32 GEMM
+    and against the exact f64 product.  Tolerance 1e-5 of max|C| (north_star's f32 bar); the kernel sits near 1e-6."""
+    import torch
+    from zignal_b200 import matrix
+    rng = np.random.default_rng(n + dim)
+    x = (rng.random((n, dim)) * 255.0 if positive else rng.standard_normal((n, dim))).astype(np.float32)
+    x[:, 3] *= 7.0
+    xd = torch.from_numpy(x).cuda()
+    got = matrix.gemm_device(xd, xd, True, False, 1.0, 0.0, None).cpu().numpy()
+    assert zb.lib().zb_last_kernel().decode() == "gemm_xtx_tf32x3_tcgen05"
+    exact = x.astype(np.float64).T @ x.astype(np.float64)
+    scale = np.abs(exact).max()
+    assert np.abs(got - exact).max() / scale <= 2e-6
+    assert np.array_equal(got, got.T)                      # mirrored tiles: exactly symmetric
+    want = zo.gemm(x, x, True, False)                      # the reference's own accumulation order, f32
+    assert np.abs(got - want).max() / scale <= 1e-5
+    # alpha / beta epilogue and the CUDA-core path agree with it
+    c0 = rng.standard_normal((dim, dim)).astype(np.float32)
+    got2 = matrix.gemm_device(xd, xd, True, False, 1.0 / (n - 1), 2.0, torch.from_numpy(c0).cuda()).cpu().numpy()
+    ref2 = exact / (n - 1) + 2.0 * c0
+    assert np.abs(got2 - ref2).max() / np.abs(ref2).max() <= 2e-6
+    zb.lib().zb_set_force_generic(1)
+    try:
+        gen = matrix.gemm_device(xd, xd, True, False, 1.0, 0.0, None).cpu().numpy()
+        assert zb.lib().zb_last_kernel().decode() != "gemm_xtx_tf32x3_tcgen05"
+    finally:
+        zb.lib().zb_set_force_generic(0)
+    assert np.abs(gen - got).max() / scale <= 2e-6
+
+
 def test_pca_fit_and_transform(zb):
     from zignal_b200.pca import Pca
     rng = np.random.default_rng(3)

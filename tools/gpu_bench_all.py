@@ -93,8 +93,9 @@ del src, tgt
 X = torch.randn(1048576, 256, device="cuda", dtype=torch.float32, generator=g)
 ms = time_it(lambda: matrix.gemm_device(X, X, True, False, 1.0 / (X.shape[0] - 1), 0.0, None), n=3, warm=1)
 flops = 2.0 * X.shape[0] * 256 * 256
-r = {"config": "PCA GEMM X^T X, n=1048576 x dim=256 f32 (f64 accumulate, CUDA cores)", "ms": ms, "TFLOP_per_s": flops / (ms * 1e-3) / 1e12,
-     "kernel": L.zb_last_kernel().decode(), "note": "tcgen05 path not built yet"}
+r = {"config": "PCA GEMM X^T X, n=1048576 x dim=256 f32 (tcgen05 3xTF32, fp32-accurate)", "ms": ms, "TFLOP_per_s": flops / (ms * 1e-3) / 1e12,
+     "kernel": L.zb_last_kernel().decode(), "algorithmic_bytes": 1048576 * 256 * 4, "GB_per_s": 1048576 * 256 * 4 / (ms * 1e-3) / 1e9,
+     "note": "useful fp32-accurate flops; 2.25x that is issued as TF32 MMAs (3 products on the upper-triangle tiles); shared-memory operand bandwidth bound"}
 out.append(r)
 print(json.dumps(r), flush=True)
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)

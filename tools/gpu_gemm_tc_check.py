@@ -12,7 +12,7 @@ from zignal_b200 import matrix  # noqa: E402
 
 L = zb.lib()
 g = torch.Generator(device="cuda").manual_seed(7)
-for (n, dim) in [(4096, 256), (4096, 128), (10000, 256), (65536, 256), (100003, 128)]:
+for (n, dim) in [(4096, 256), (4096, 128), (10000, 256), (65536, 256), (100003, 128), (50000, 384), (40000, 512)]:
     X = torch.randn(n, dim, device="cuda", dtype=torch.float32, generator=g)
     X[:, 3] *= 100.0
     X[:, 7] += 5.0
@@ -56,6 +56,13 @@ print(f"PCA X^T X 1048576x256: {ms:.4f} ms  {fl/(ms*1e-3)/1e12:.1f} TFLOP/s (fp3
 C = matrix.gemm_device(X, X, True, False, 1.0, 0.0, None)
 ref = X.double().T @ X.double()
 print("accuracy at n=1M:", float((C.double() - ref).abs().max() / ref.abs().max()), float(((C.double() - ref).abs() / ref.abs().clamp_min(1e-30)).max()))
+Cb = torch.matmul(X.T, X)
+print("cuBLAS fp32 accuracy at n=1M:", float((Cb.double() - ref).abs().max() / ref.abs().max()))
+Xp = torch.rand(1048576, 256, device="cuda", dtype=torch.float32, generator=g) * 255.0   # uncentred pixel-like data: every sum is coherent
+Cp = matrix.gemm_device(Xp, Xp, True, False, 1.0, 0.0, None)
+refp = Xp.double().T @ Xp.double()
+print("positive data n=1M: ours", float(((Cp.double() - refp).abs() / refp.abs()).max()), "cuBLAS fp32", float((((Xp.T @ Xp).double() - refp).abs() / refp.abs()).max()))
+del Xp, Cp, refp
 L.zb_set_force_generic(1)
 ms2 = time_it(lambda: matrix.gemm_device(X, X, True, False, 1.0, 0.0, None), n=2, warm=1)
 print(f"CUDA-core f64-accumulate path: {ms2:.3f} ms")

@@ -50,6 +50,8 @@ constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + RING_BYTES + 64 + 1024;
 struct U8Params {
     int kx[MAXK];
     int ky[MAXK];
+    float kxf[MAXK];  // the same Q8 taps as floats (FMATH variant)
+    float kyf[MAXK];
     const uint32_t* src;
     uint32_t* dst;
     unsigned long long src_pitch_px, dst_pitch_px;
@@ -106,13 +108,28 @@ __device__ __forceinline__ void mac4v(int4& acc, const int4& v, int k) {
     acc.z += v.z * k;
     acc.w += v.w * k;
 }
+// FMATH variant: when 255 * sum|kx| * sum|ky| <= 2^24 every partial sum is an integer of magnitude <= 2^24, hence exactly
+// representable in f32, and an FFMA of exact integers whose result is representable returns it exactly -- so the whole
+// Q8 pipeline can run on the (faster) FFMA path with bit-identical results.
+__device__ __forceinline__ void mac4f_px(float4& acc, uint32_t w, float k) {
+    acc.x = fmaf((float)(w & 0xffu), k, acc.x);
+    acc.y = fmaf((float)((w >> 8) & 0xffu), k, acc.y);
+    acc.z = fmaf((float)((w >> 16) & 0xffu), k, acc.z);
+    acc.w = fmaf((float)(w >> 24), k, acc.w);
+}
+__device__ __forceinline__ void mac4f(float4& acc, const float4& v, float k) {
+    acc.x = fmaf(v.x, k, acc.x);
+    acc.y = fmaf(v.y, k, acc.y);
+    acc.z = fmaf(v.z, k, acc.z);
+    acc.w = fmaf(v.w, k, acc.w);
+}
 // divClampU8(65536, acc) for |acc| < 2^31 - 32768 (convolution.zig:18-22)
 __device__ __forceinline__ uint32_t div_clamp_65536(int acc) {
     const int t = acc + 32768 + ((acc >> 31) & -65536);  // acc - 32768 when negative
     return t < 0 ? 0u : min((uint32_t)t >> 16, 255u);     // trunc toward zero, then clamp
 }
 
-template <int HALF>
+template <int HALF, bool FMATH>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ U8Params p) {
     constexpr int K = 2 * HALF + 1;
     constexpr int NLOAD = CHUNK + 2 * HALF;
@@ -177,9 +194,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
             }
             // ---------------- H(i) ----------------
             {
-                int4 acc[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = make_int4(0, 0, 0, 0);
                 // pixels [8*ht - 8, 8*ht + 16) of the strip = 24 words = 6 aligned 16-byte chunks
                 uint32_t w[24];
 #pragma unroll
@@ -187,18 +201,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
                     const int4 v = lds128_i(stage_px(stage, hr, PAD - 8 + 8 * ht + 4 * q));
                     w[4 * q + 0] = (uint32_t)v.x; w[4 * q + 1] = (uint32_t)v.y; w[4 * q + 2] = (uint32_t)v.z; w[4 * q + 3] = (uint32_t)v.w;
                 }
-#pragma unroll
-                for (int j = 0; j < NLOAD; ++j) {
-                    const uint32_t px = w[8 - HALF + j];
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const int ti = j - o;
-                        if (ti >= 0 && ti < K) mac4i(acc[o], px, p.kx[ti]);
-                    }
-                }
                 const uint32_t rrow = h_ring_col + (uint32_t)(((i % 3) * CHUNK + hr) * RING_ROW_BYTES);
+                if constexpr (FMATH) {
+                    float4 acc[8];
 #pragma unroll
-                for (int o = 0; o < 8; ++o) sts128_i(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                    for (int o = 0; o < 8; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        const uint32_t px = w[8 - HALF + j];
+                        const float4 pf = make_float4((float)(px & 0xffu), (float)((px >> 8) & 0xffu), (float)((px >> 16) & 0xffu), (float)(px >> 24));
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4f(acc[o], pf, p.kxf[ti]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sts128(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                } else {
+                    int4 acc[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[o] = make_int4(0, 0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        const uint32_t px = w[8 - HALF + j];
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4i(acc[o], px, p.kx[ti]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sts128_i(rrow + ((((uint32_t)o) ^ h_key) << 4), acc[o]);
+                }
             }
             __syncthreads();
             if (tid == 0) produce();
@@ -206,18 +241,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
             if (i >= 2) {
                 const int c = i - 2;
                 int4 acc[8];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = make_int4(0, 0, 0, 0);
                 const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
+                if constexpr (FMATH) {
+                    float4 facc[8];
 #pragma unroll
-                for (int j = 0; j < NLOAD; ++j) {
-                    uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
-                    if (sr >= RING_ROWS) sr -= RING_ROWS;
-                    const int4 v = lds128_i(v_col + sr * (uint32_t)RING_ROW_BYTES);
+                    for (int o = 0; o < 8; ++o) facc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const int ti = j - o;
-                        if (ti >= 0 && ti < K) mac4v(acc[o], v, p.ky[ti]);
+                    for (int j = 0; j < NLOAD; ++j) {
+                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                        if (sr >= RING_ROWS) sr -= RING_ROWS;
+                        const float4 v = lds128(v_col + sr * (uint32_t)RING_ROW_BYTES);
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4f(facc[o], v, p.kyf[ti]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[o] = make_int4((int)facc[o].x, (int)facc[o].y, (int)facc[o].z, (int)facc[o].w);  // exact integers
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[o] = make_int4(0, 0, 0, 0);
+#pragma unroll
+                    for (int j = 0; j < NLOAD; ++j) {
+                        uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                        if (sr >= RING_ROWS) sr -= RING_ROWS;
+                        const int4 v = lds128_i(v_col + sr * (uint32_t)RING_ROW_BYTES);
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            const int ti = j - o;
+                            if (ti >= 0 && ti < K) mac4v(acc[o], v, p.ky[ti]);
+                        }
                     }
                 }
                 const int x = x0 + vx;
@@ -240,8 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
 }
 
 template <int HALF>
-int launch_u8(const CUtensorMap& tmap, const U8Params& p, int grid, cudaStream_t s) {
-    auto k = fused_sep_rgba8_kernel<HALF>;
+int launch_u8(const CUtensorMap& tmap, const U8Params& p, int grid, bool fmath, cudaStream_t s) {
+    auto k = fmath ? fused_sep_rgba8_kernel<HALF, true> : fused_sep_rgba8_kernel<HALF, false>;
     ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     k<<<grid, NTHREADS, SMEM_BYTES, s>>>(tmap, p);
     ZB_LAUNCHED();
@@ -264,6 +318,8 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     for (int i = 0; i < nx; ++i) { const int q = (int)roundf(kx[i] * 256.0f); p.kx[i + (half - half_x)] = q; sax += llabs((long long)q); }
     for (int i = 0; i < ny; ++i) { const int q = (int)roundf(ky[i] * 256.0f); p.ky[i + (half - half_y)] = q; say += llabs((long long)q); }
     if (sax * 255 * say + 32768 >= 2147483647LL) return ZB_ERR_UNSUPPORTED;  // i32 accumulators must be provably safe
+    const bool fmath = (sax * 255 * say <= (1LL << 24)) && g_tune_u8_fmath.load() != 0;  // f32 is exact up to 2^24
+    for (int i = 0; i < MAXK; ++i) { p.kxf[i] = (float)p.kx[i]; p.kyf[i] = (float)p.ky[i]; }
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return ZB_ERR_UNSUPPORTED;
     DeviceInfo di;
@@ -302,16 +358,16 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     }
     const int n_units = p.n_strips * p.n_bands;
     const int grid = n_units < di.sm_count ? n_units : di.sm_count;
-    t_last_kernel = "fused_sep_rgba8";
+    t_last_kernel = fmath ? "fused_sep_rgba8_f" : "fused_sep_rgba8";
     switch (half) {
-        case 1: return launch_u8<1>(tmap, p, grid, s);
-        case 2: return launch_u8<2>(tmap, p, grid, s);
-        case 3: return launch_u8<3>(tmap, p, grid, s);
-        case 4: return launch_u8<4>(tmap, p, grid, s);
-        case 5: return launch_u8<5>(tmap, p, grid, s);
-        case 6: return launch_u8<6>(tmap, p, grid, s);
-        case 7: return launch_u8<7>(tmap, p, grid, s);
-        case 8: return launch_u8<8>(tmap, p, grid, s);
+        case 1: return launch_u8<1>(tmap, p, grid, fmath, s);
+        case 2: return launch_u8<2>(tmap, p, grid, fmath, s);
+        case 3: return launch_u8<3>(tmap, p, grid, fmath, s);
+        case 4: return launch_u8<4>(tmap, p, grid, fmath, s);
+        case 5: return launch_u8<5>(tmap, p, grid, fmath, s);
+        case 6: return launch_u8<6>(tmap, p, grid, fmath, s);
+        case 7: return launch_u8<7>(tmap, p, grid, fmath, s);
+        case 8: return launch_u8<8>(tmap, p, grid, fmath, s);
     }
     return ZB_ERR_UNSUPPORTED;
 }

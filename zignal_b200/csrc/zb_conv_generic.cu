@@ -115,8 +115,30 @@ __global__ void __launch_bounds__(kThreads) sep_v_kernel(const TmpT* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense kh x kw correlation (no kernel flip), convolution.zig:113-193
+// Dense kh x kw correlation (no kernel flip), convolution.zig:113-193.  One thread per PIXEL: the border
+// resolution and the tap loop are shared by the CH channels, RGBA pixels move as one 32-bit word.
 // ---------------------------------------------------------------------------------------------
+template <typename PixT, int CH>
+__device__ __forceinline__ void load_channels(const PixT* __restrict__ p, float* v) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v[k] = (float)p[k];
+}
+template <typename PixT, int CH>
+__device__ __forceinline__ void load_channels(const PixT* __restrict__ p, int* v) {
+    if constexpr (CH == 4 && sizeof(PixT) == 1) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = (int)p[k];
+    }
+}
+template <typename PixT, int CH>
+__device__ __forceinline__ void load_channels(const PixT* __restrict__ p, long long* v) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v[k] = (long long)p[k];
+}
+
 template <typename PixT, typename AccT, typename KT, int CH>
 __global__ void __launch_bounds__(kThreads) conv2d_kernel(const PixT* __restrict__ src, size_t src_row_el, PixT* __restrict__ dst,
                                                           size_t dst_row_el, int rows, int cols, const KT* __restrict__ taps_g,
@@ -125,14 +147,14 @@ __global__ void __launch_bounds__(kThreads) conv2d_kernel(const PixT* __restrict
     KT* taps = reinterpret_cast<KT*>(smem_raw);
     for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) taps[i] = taps_g[i];
     __syncthreads();
-    const int r = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = cols * CH;
-    if (e >= w) return;
-    const int c = e / CH, k = e - c * CH;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= cols || r >= rows) return;
     const int half_h = kh / 2, half_w = kw / 2;
     const bool interior = r >= half_h && r + half_h < rows && c >= half_w && c + half_w < cols;
-    AccT acc = 0;
+    AccT acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = 0;
     for (int ky = 0; ky < kh; ++ky) {
         int ry = r + ky - half_h;
         if (!interior) ry = resolve_index(ry, rows, border);
@@ -140,17 +162,31 @@ __global__ void __launch_bounds__(kThreads) conv2d_kernel(const PixT* __restrict
             int cx = c + kx - half_w;
             if (!interior) cx = resolve_index(cx, cols, border);
             const KT kv = taps[ky * kw + kx];
-            if constexpr (IsFloat<KT>::value) {
-                const float pv = (ry < 0 || cx < 0) ? 0.0f : (float)src[(size_t)ry * src_row_el + (size_t)cx * CH + k];
-                acc = mul_add_unfused(pv, kv, acc);
+            AccT pv[CH];
+            if (ry < 0 || cx < 0) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) pv[k] = 0;
             } else {
-                const AccT pv = (ry < 0 || cx < 0) ? (AccT)0 : (AccT)src[(size_t)ry * src_row_el + (size_t)cx * CH + k];
-                acc += pv * (AccT)kv;
+                load_channels<PixT, CH>(src + (size_t)ry * src_row_el + (size_t)cx * CH, pv);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                if constexpr (IsFloat<KT>::value) acc[k] = mul_add_unfused(pv[k], kv, acc[k]);
+                else acc[k] += pv[k] * (AccT)kv;
             }
         }
     }
-    if constexpr (IsFloat<KT>::value) dst[(size_t)r * dst_row_el + e] = acc;
-    else dst[(size_t)r * dst_row_el + e] = div_clamp_u8<AccT>(acc, (AccT)256);
+    PixT* out = dst + (size_t)r * dst_row_el + (size_t)c * CH;
+    if constexpr (IsFloat<KT>::value) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) out[k] = acc[k];
+    } else if constexpr (CH == 4) {
+        *reinterpret_cast<uchar4*>(out) = make_uchar4(div_clamp_u8<AccT>(acc[0], (AccT)256), div_clamp_u8<AccT>(acc[1], (AccT)256),
+                                                      div_clamp_u8<AccT>(acc[2], (AccT)256), div_clamp_u8<AccT>(acc[3], (AccT)256));
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) out[k] = div_clamp_u8<AccT>(acc[k], (AccT)256);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +255,7 @@ int conv_separable_generic(const zb_image* src, zb_image* dst, int pixfmt, const
 template <typename PixT, typename AccT, typename KT, int CH>
 static int launch_conv2d(const zb_image* src, zb_image* dst, const KT* d_k, int kh, int kw, int border, cudaStream_t s) {
     const int rows = (int)src->rows, cols = (int)src->cols;
-    dim3 grid(div_up((size_t)cols * CH, kThreads), rows);
+    dim3 grid(div_up((size_t)cols, 32), div_up((size_t)rows, 8));
     conv2d_kernel<PixT, AccT, KT, CH><<<grid, kThreads, (size_t)kh * kw * sizeof(KT), s>>>(
         (const PixT*)src->data, (size_t)src->stride * CH, (PixT*)dst->data, (size_t)dst->stride * CH, rows, cols, d_k, kh, kw, border);
     ZB_LAUNCHED();

@@ -224,7 +224,8 @@ int zb_set_exact_f32(int on);
 /* Forces the generic (two-pass through HBM) separable path; used by tests to cross-check kernels. */
 int zb_set_force_generic(int on);
 /* Kernel tuning knobs for experiments ("conv.stages" 2|3, "conv.f32x2" 0|1, "conv.band_rows" >= 64,
- * "conv.variant" -1 auto | 0 phase-synchronous | 1 warp-specialised). */
+ * "conv.variant" -1 auto | 0 phase-synchronous | 1 warp-specialised, "conv.u8_fmath" 0|1,
+ * "host.band_rows": rows per PCIe band of the pipelined host-pointer path, 0 = stage the whole image). */
 int zb_tune(const char* key, int value);
 /* Name of the kernel variant the last zb_conv_separable call selected on this thread. */
 const char* zb_last_kernel(void);

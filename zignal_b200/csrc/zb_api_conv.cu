@@ -1,5 +1,6 @@
 // zb_api_conv.cu -- C entry points for Image.convolveSeparable / convolve / gaussianBlur
 // (reference image.zig:917-994, convolution.zig:198-438) and their host-pointer twins.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -54,6 +55,113 @@ int gaussian_taps_host(float sigma, std::vector<float>& taps) {
 
 }  // namespace zb
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined host path for the fused single-pass kernels: the image crosses PCIe in row bands on one stream, each
+// band is convolved on a second stream as soon as the rows it reads (itself plus `half` rows of the next band) have
+// landed, and finished bands go back on a third stream -- PCIe is full duplex, so the call costs about one
+// direction's transfer time instead of H2D + kernel + D2H back to back.  Results are identical to the one-shot
+// path: every launch sees the whole source image, only its OUTPUT rows are restricted.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PipeStreams {
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    int device = -1;
+};
+thread_local PipeStreams t_pipe;
+
+int pipe_streams(PipeStreams** out) {
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    if (t_pipe.device != dev) {
+        // (streams of a previous device, if any, are leaked on purpose: destroying them needs that device current)
+        ZB_CUDA(cudaStreamCreateWithFlags(&t_pipe.up, cudaStreamNonBlocking));
+        ZB_CUDA(cudaStreamCreateWithFlags(&t_pipe.run, cudaStreamNonBlocking));
+        ZB_CUDA(cudaStreamCreateWithFlags(&t_pipe.down, cudaStreamNonBlocking));
+        t_pipe.device = dev;
+    }
+    *out = &t_pipe;
+    return ZB_OK;
+}
+
+struct EventList {
+    std::vector<cudaEvent_t> ev;
+    ~EventList() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    int make(cudaEvent_t* e) {
+        ZB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        ev.push_back(*e);
+        return ZB_OK;
+    }
+};
+
+}  // namespace
+
+// Returns ZB_ERR_UNSUPPORTED when the configuration has no fused kernel (the caller then stages the whole image).
+static int host_conv_separable_pipelined(const zb_image* src, zb_image* dst, int pixfmt, const float* kx, int nx, const float* ky, int ny,
+                                         int border) {
+    if (pixfmt != ZB_PIX_RGBAF32 && pixfmt != ZB_PIX_RGBA8) return ZB_ERR_UNSUPPORTED;
+    if (g_force_generic.load() || border == ZB_BORDER_WRAP) return ZB_ERR_UNSUPPORTED;   // wrap: the first band reads the last rows
+    if (nx <= 0 || ny <= 0 || !kx || !ky) return ZB_ERR_INVALID_ARGUMENT;
+    const size_t pb = pixel_bytes(pixfmt);
+    const int rows = (int)src->rows, cols = (int)src->cols;
+    const int half = ny / 2;
+    int band = g_tune_host_band_rows.load();
+    if (band <= 0) return ZB_ERR_UNSUPPORTED;
+    band = (band + 63) / 64 * 64;
+    if (rows < 2 * band || half >= band || (size_t)rows * cols * pb < ((size_t)32 << 20)) return ZB_ERR_UNSUPPORTED;  // small: one shot
+    PipeStreams* ps;
+    int rc = pipe_streams(&ps);
+    if (rc) return rc;
+    Scratch s_src, s_dst;
+    if ((rc = s_src.alloc((size_t)rows * cols * pb, ps->up))) return rc;
+    if ((rc = s_dst.alloc((size_t)rows * cols * pb, ps->up))) return rc;
+    const zb_image dsrc{s_src.p, src->rows, src->cols, src->cols};
+    zb_image ddst{s_dst.p, dst->rows, dst->cols, dst->cols};
+    EventList evs;
+    cudaEvent_t e_alloc;
+    if ((rc = evs.make(&e_alloc))) return rc;
+    ZB_CUDA(cudaEventRecord(e_alloc, ps->up));
+    ZB_CUDA(cudaStreamWaitEvent(ps->run, e_alloc, 0));
+    const int nb = (rows + band - 1) / band;
+    const bool exact = g_exact_f32.load() != 0;
+    auto run_band = [&](int j, cudaEvent_t uploaded) -> int {
+        const int y0 = j * band, y1 = std::min(rows, y0 + band);
+        ZB_CUDA(cudaStreamWaitEvent(ps->run, uploaded, 0));
+        int r = pixfmt == ZB_PIX_RGBAF32 ? conv_separable_fused_rgbaf32(&dsrc, &ddst, kx, nx, ky, ny, border, exact, ps->run, y0, y1)
+                                         : conv_separable_fused_rgba8(&dsrc, &ddst, kx, nx, ky, ny, border, ps->run, y0, y1);
+        if (r) return r;
+        cudaEvent_t done;
+        if ((r = evs.make(&done))) return r;
+        ZB_CUDA(cudaEventRecord(done, ps->run));
+        ZB_CUDA(cudaStreamWaitEvent(ps->down, done, 0));
+        ZB_CUDA(cudaMemcpy2DAsync((char*)dst->data + (size_t)y0 * dst->stride * pb, dst->stride * pb, (char*)s_dst.p + (size_t)y0 * cols * pb,
+                                  (size_t)cols * pb, (size_t)cols * pb, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ps->down));
+        return ZB_OK;
+    };
+    cudaEvent_t prev_up = nullptr;
+    for (int j = 0; j < nb; ++j) {
+        const int y0 = j * band, y1 = std::min(rows, y0 + band);
+        ZB_CUDA(cudaMemcpy2DAsync((char*)s_src.p + (size_t)y0 * cols * pb, (size_t)cols * pb, (const char*)src->data + (size_t)y0 * src->stride * pb,
+                                  src->stride * pb, (size_t)cols * pb, (size_t)(y1 - y0), cudaMemcpyHostToDevice, ps->up));
+        cudaEvent_t up;
+        if ((rc = evs.make(&up))) return rc;
+        ZB_CUDA(cudaEventRecord(up, ps->up));
+        if (j > 0) {
+            rc = run_band(j - 1, up);   // band j-1 reads up to `half` rows of band j
+            if (rc == ZB_ERR_UNSUPPORTED && j == 1) {   // outside the fused envelope: nothing has been computed yet
+                ZB_CUDA(cudaStreamSynchronize(ps->up));
+                return rc;
+            }
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+        }
+        prev_up = up;
+    }
+    if ((rc = run_band(nb - 1, prev_up))) { cudaDeviceSynchronize(); return rc; }
+    ZB_CUDA(cudaStreamSynchronize(ps->down));
+    ZB_CUDA(cudaStreamSynchronize(ps->run));
+    return ZB_OK;
+}
+
 extern "C" {
 
 int zb_gaussian_taps(float sigma, float* taps, int cap, int* n) {
@@ -99,6 +207,9 @@ int zb_host_conv_separable(const zb_image* src, zb_image* dst, int pixfmt, const
                            int border) {
     int rc = check_shapes(src, dst, pixfmt);
     if (rc) return rc;
+    if (border < ZB_BORDER_ZERO || border > ZB_BORDER_WRAP) return ZB_ERR_INVALID_ARGUMENT;
+    rc = host_conv_separable_pipelined(src, dst, pixfmt, kx, nx, ky, ny, border);
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
     HostStage st;
     if ((rc = st.begin(src, dst, pixfmt))) return rc;
     if ((rc = conv_separable_dispatch(&st.dsrc, &st.ddst, pixfmt, kx, nx, ky, ny, border, st.stream))) return rc;
@@ -117,7 +228,13 @@ int zb_host_convolve(const zb_image* src, zb_image* dst, int pixfmt, const float
 int zb_host_gaussian_blur(const zb_image* src, zb_image* dst, int pixfmt, float sigma) {
     int rc = check_shapes(src, dst, pixfmt);
     if (rc) return rc;
-    if (sigma < 0) return ZB_ERR_INVALID_SIGMA;
+    if (!(sigma >= 0)) return ZB_ERR_INVALID_SIGMA;
+    if (sigma > 0) {
+        std::vector<float> taps;
+        gaussian_taps_host(sigma, taps);
+        rc = host_conv_separable_pipelined(src, dst, pixfmt, taps.data(), (int)taps.size(), taps.data(), (int)taps.size(), ZB_BORDER_MIRROR);
+        if (rc != ZB_ERR_UNSUPPORTED) return rc;
+    }
     HostStage st;
     if ((rc = st.begin(src, dst, pixfmt))) return rc;
     if ((rc = zb_gaussian_blur(&st.dsrc, &st.ddst, pixfmt, sigma, st.stream))) return rc;

@@ -14,12 +14,13 @@ int convolve_generic(const zb_image* src, zb_image* dst, int pixfmt, const float
 
 // zb_conv_fused.cu: single-pass (read once, write once) separable convolution of interleaved RGBA f32.
 // Returns ZB_ERR_UNSUPPORTED when the configuration is outside the fused kernel's envelope; the caller
-// then uses the generic path.  *used (optional) reports whether the fused kernel was launched.
+// then uses the generic path.  [row0, row1) restricts the OUTPUT rows produced (row1 < 0: all) -- the host pipeline
+// computes a band as soon as the rows it reads have been uploaded.
 int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                                 bool exact, cudaStream_t s);
+                                 bool exact, cudaStream_t s, int row0 = 0, int row1 = -1);
 
 // zb_conv_fused_u8.cu: single-pass separable convolution of interleaved Rgba(u8) (i32 accumulators, provably overflow-free taps).
 int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                               cudaStream_t s);
+                               cudaStream_t s, int row0 = 0, int row1 = -1);
 
 }  // namespace zb

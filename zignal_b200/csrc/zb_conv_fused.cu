@@ -57,6 +57,7 @@ struct FusedParams {
     int rows, cols, border;
     int ngroups;     // floor(cols / 8): pixel groups the tensor map covers
     int n_strips, n_bands, band_rows;
+    int row0, row1;  // output rows this launch produces: [row0, row1) (the whole image unless the host pipeline slices it)
     int fix_rows;    // 1 if out-of-range rows need patching (border != zero)
     int fix_left;    // 1 if x < 0 needs patching
     int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
@@ -191,8 +192,8 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     auto produce = [&]() {
         if (pu >= n_units) return;
         const int band = pu / p.n_strips, strip = pu - band * p.n_strips;
-        const int ra = band * p.band_rows;
-        const int rb = min(ra + p.band_rows, p.rows);
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
         const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
         const uint32_t st = pcount % STAGES;
         fence_proxy_async();
@@ -224,8 +225,8 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
         const int x0 = strip * TW;
-        const int ra = band * p.band_rows;
-        const int rb = min(ra + p.band_rows, p.rows);
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
         const int n_out = (rb - ra + CHUNK - 1) / CHUNK;  // output chunks
         const int n_in = n_out + 2;                       // input chunks: chunk i covers rows [ra-8+8i, ra+8i)
         const int g0 = x0 / 8 - 1;
@@ -344,8 +345,8 @@ __device__ __forceinline__ UnitGeom unit_geom(int unit, const FusedParams& p) {
     UnitGeom u;
     const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
     u.x0 = strip * TW;
-    u.ra = band * p.band_rows;
-    u.rb = min(u.ra + p.band_rows, p.rows);
+    u.ra = p.row0 + band * p.band_rows;
+    u.rb = min(u.ra + p.band_rows, p.row1);
     u.n_out = (u.rb - u.ra + CHUNK - 1) / CHUNK;
     u.n_in = u.n_out + 2;
     u.g0 = u.x0 / 8 - 1;
@@ -501,7 +502,7 @@ int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool e
 }  // namespace
 
 int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                                 bool exact, cudaStream_t s) {
+                                 bool exact, cudaStream_t s, int row0, int row1) {
     const int half_x = nx / 2, half_y = ny / 2;
     const int half = half_x > half_y ? half_x : half_y;
     if (half < 1 || half > MAX_HALF) return ZB_ERR_UNSUPPORTED;
@@ -540,16 +541,20 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
     p.ngroups = p.cols / 8;
     p.n_strips = (p.cols + TW - 1) / TW;
     // band height: ~256 rows, then as many bands as fit in the same number of waves
+    p.row0 = row0 < 0 ? 0 : row0;
+    p.row1 = (row1 < 0 || row1 > p.rows) ? p.rows : row1;
+    if (p.row1 <= p.row0) return ZB_OK;
+    const int nrows = p.row1 - p.row0;
     const int band_target = g_tune_band_rows.load();
-    int n_bands = (p.rows + band_target - 1) / band_target;
+    int n_bands = (nrows + band_target - 1) / band_target;
     const long long waves = ((long long)n_bands * p.n_strips + di.sm_count - 1) / di.sm_count;
     int nb2 = (int)((waves * di.sm_count) / p.n_strips);
     if (nb2 > n_bands) n_bands = nb2;
-    int band_rows = (p.rows + n_bands - 1) / n_bands;
+    int band_rows = (nrows + n_bands - 1) / n_bands;
     band_rows = ((band_rows + CHUNK - 1) / CHUNK) * CHUNK;
     if (band_rows < 64) band_rows = 64;
     p.band_rows = band_rows;
-    p.n_bands = (p.rows + band_rows - 1) / band_rows;
+    p.n_bands = (nrows + band_rows - 1) / band_rows;
     p.fix_rows = border != ZB_BORDER_ZERO;
     p.fix_left = border != ZB_BORDER_ZERO;
     p.fix_right = (border != ZB_BORDER_ZERO) || (p.cols % 8 != 0);

@@ -57,6 +57,7 @@ struct U8Params {
     unsigned long long src_pitch_px, dst_pitch_px;
     int rows, cols, border;
     int n_strips, n_bands, band_rows;
+    int row0, row1;  // output rows this launch produces
     int fix;  // 1 if out-of-range stage entries need patching (border != zero)
 };
 
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
     auto produce = [&]() {
         if (pu >= n_units) return;
         const int band = pu / p.n_strips, strip = pu - band * p.n_strips;
-        const int ra = band * p.band_rows;
-        const int rb = min(ra + p.band_rows, p.rows);
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
         const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
         const uint32_t st = pcount % NSTAGE;
         fence_proxy_async();
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
         const int x0 = strip * TW;
-        const int ra = band * p.band_rows;
-        const int rb = min(ra + p.band_rows, p.rows);
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
         const int n_out = (rb - ra + CHUNK - 1) / CHUNK;
         const int n_in = n_out + 2;
         const int xs0 = x0 - PAD;
@@ -305,7 +306,7 @@ int launch_u8(const CUtensorMap& tmap, const U8Params& p, int grid, bool fmath, 
 }  // namespace
 
 int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                               cudaStream_t s) {
+                               cudaStream_t s, int row0, int row1) {
     const int half_x = nx / 2, half_y = ny / 2;
     const int half = half_x > half_y ? half_x : half_y;
     if (half < 1 || half > MAX_HALF) return ZB_ERR_UNSUPPORTED;
@@ -334,15 +335,19 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     p.cols = (int)src->cols;
     p.border = border;
     p.n_strips = (p.cols + TW - 1) / TW;
-    int n_bands = (p.rows + 255) / 256;
+    p.row0 = row0 < 0 ? 0 : row0;
+    p.row1 = (row1 < 0 || row1 > p.rows) ? p.rows : row1;
+    if (p.row1 <= p.row0) return ZB_OK;
+    const int nrows = p.row1 - p.row0;
+    int n_bands = (nrows + 255) / 256;
     const long long waves = ((long long)n_bands * p.n_strips + di.sm_count - 1) / di.sm_count;
     const int nb2 = (int)((waves * di.sm_count) / p.n_strips);
     if (nb2 > n_bands) n_bands = nb2;
-    int band_rows = (p.rows + n_bands - 1) / n_bands;
+    int band_rows = (nrows + n_bands - 1) / n_bands;
     band_rows = ((band_rows + CHUNK - 1) / CHUNK) * CHUNK;
     if (band_rows < 64) band_rows = 64;
     p.band_rows = band_rows;
-    p.n_bands = (p.rows + band_rows - 1) / band_rows;
+    p.n_bands = (nrows + band_rows - 1) / band_rows;
     p.fix = border != ZB_BORDER_ZERO;
 
     CUtensorMap tmap;

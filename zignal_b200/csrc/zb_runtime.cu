@@ -15,6 +15,7 @@ std::atomic<int> g_force_generic{0};
 std::atomic<int> g_tune_stages{2};
 std::atomic<int> g_tune_f2{0};
 std::atomic<int> g_tune_band_rows{256};
+std::atomic<int> g_tune_host_band_rows{256};
 std::atomic<int> g_tune_variant{-1};
 std::atomic<int> g_tune_u8_fmath{1};
 
@@ -107,6 +108,7 @@ int zb_tune(const char* key, int value) {
     if (!strcmp(key, "conv.f32x2")) { g_tune_f2.store(value ? 1 : 0); return ZB_OK; }
     if (!strcmp(key, "conv.variant")) { if (value < -1 || value > 1) return ZB_ERR_INVALID_ARGUMENT; g_tune_variant.store(value); return ZB_OK; }
     if (!strcmp(key, "conv.u8_fmath")) { g_tune_u8_fmath.store(value ? 1 : 0); return ZB_OK; }
+    if (!strcmp(key, "host.band_rows")) { if (value < 0) return ZB_ERR_INVALID_ARGUMENT; g_tune_host_band_rows.store(value); return ZB_OK; }
     if (!strcmp(key, "conv.band_rows")) { if (value < 64) return ZB_ERR_INVALID_ARGUMENT; g_tune_band_rows.store(value); return ZB_OK; }
     return ZB_ERR_INVALID_ARGUMENT;
 }

@@ -44,6 +44,45 @@ def test_sharpen_bit_exact(zb, shape, dtype, radius):
     assert np.array_equal(got, zo.sharpen(img, radius))
 
 
+@pytest.mark.parametrize("ch", [1, 4])
+@pytest.mark.parametrize("radius", [1, 3, 6, 15])
+def test_box_fused_strips_bands_and_ragged_views(zb, ch, radius):
+    """The fused 8-bit path (row-offset table, checkpointed column chains, shared-memory SAT ring): several strips and bands,
+    a ragged last unit (gray view whose width is not a multiple of 4), against the oracle and against the SAT-in-HBM path."""
+    import torch
+    L = zb.lib()
+    rng = np.random.default_rng(radius * 10 + ch)
+    shape = (333, 1008) if ch == 1 else (333, 300, 4)
+    base = rand_image(rng, shape, np.uint8) | 0xE0
+    view_cols = 1003 if ch == 1 else 297
+    dev = zb.Image.from_numpy(base)
+    v = dev.view(zb.Rectangle(0, 0, view_cols, shape[0]))
+    host = np.ascontiguousarray(base[:, :view_cols])
+    out = zb.Image.from_numpy(np.zeros_like(base))
+    ov = out.view(zb.Rectangle(0, 0, view_cols, shape[0]))
+    v.box_blur(radius, out=ov)
+    assert L.zb_last_kernel().decode() == "box_fused_blur"
+    assert np.array_equal(out.to_numpy()[:, :view_cols], zo.box_blur(host, radius))
+    assert not out.to_numpy()[:, view_cols:].any()
+    v.sharpen(radius, out=ov)
+    assert L.zb_last_kernel().decode() == "box_fused_sharpen"
+    assert np.array_equal(out.to_numpy()[:, :view_cols], zo.sharpen(host, radius))
+    # large image: fused vs the three-kernel SAT path (both on the GPU)
+    g = torch.Generator(device="cuda").manual_seed(radius)
+    big = torch.randint(128, 256, (3000, 2048, 4) if ch == 4 else (3000, 4096), device="cuda", dtype=torch.uint8, generator=g)
+    bi = zb.Image.from_tensor(big)
+    a = bi.box_blur(radius).tensor().clone()
+    a2 = bi.sharpen(radius).tensor().clone()
+    L.zb_set_force_generic(1)
+    try:
+        b = bi.box_blur(radius).tensor().clone()
+        assert L.zb_last_kernel().decode() == "sat_box_blur"
+        b2 = bi.sharpen(radius).tensor().clone()
+    finally:
+        L.zb_set_force_generic(0)
+    assert torch.equal(a, b) and torch.equal(a2, b2)
+
+
 def test_integral_plane_bit_exact(zb):
     import torch
     rng = np.random.default_rng(3)

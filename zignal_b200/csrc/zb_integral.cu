@@ -18,6 +18,9 @@
 
 namespace zb {
 
+// zb_box_fused.cu: 8-bit gray / Rgba without the SAT round trip through HBM (bit-identical results)
+int box_fused_u8(const zb_image* src, zb_image* dst, int channels, uint32_t radius, bool sharpen, cudaStream_t s);
+
 namespace {
 
 // ---- 1. row pass -------------------------------------------------------------------------------
@@ -137,6 +140,10 @@ int dispatch(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, cu
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
+    if ((pixfmt == ZB_PIX_U8 || pixfmt == ZB_PIX_RGBA8) && !g_force_generic.load()) {
+        rc = box_fused_u8(src, dst, pixfmt == ZB_PIX_U8 ? 1 : 4, radius, SHARPEN, s);
+        if (rc != ZB_ERR_UNSUPPORTED) return rc;
+    }
     const int rad = (int)(radius > 0x3fffffffu ? 0x3fffffffu : radius);
     t_last_kernel = SHARPEN ? "sat_sharpen" : "sat_box_blur";
     switch (pixfmt) {

@@ -19,13 +19,20 @@ template <typename CT, int N>
 struct Pix {
     CT v[N];
 };
+// Rgba(u8): one 32-bit register; `u` is what loads, stores and the packed bilinear blend touch, `v` serves the per-channel code.
+template <>
+struct Pix<uint8_t, 4> {
+    union {
+        uint8_t v[4];
+        uint32_t u;
+    };
+};
 
 template <typename CT, int N>
 __device__ __forceinline__ Pix<CT, N> load_px(const CT* __restrict__ base, size_t px) {
     Pix<CT, N> p;
     if constexpr (sizeof(CT) == 1 && N == 4) {
-        const uchar4 q = *reinterpret_cast<const uchar4*>(base + px * 4);
-        p.v[0] = q.x; p.v[1] = q.y; p.v[2] = q.z; p.v[3] = q.w;
+        p.u = *reinterpret_cast<const uint32_t*>(base + px * 4);
     } else if constexpr (sizeof(CT) == 4 && N == 4) {
         const float4 q = *reinterpret_cast<const float4*>(base + px * 4);
         p.v[0] = q.x; p.v[1] = q.y; p.v[2] = q.z; p.v[3] = q.w;
@@ -39,7 +46,7 @@ __device__ __forceinline__ Pix<CT, N> load_px(const CT* __restrict__ base, size_
 template <typename CT, int N>
 __device__ __forceinline__ void store_px(CT* __restrict__ base, size_t px, const Pix<CT, N>& p) {
     if constexpr (sizeof(CT) == 1 && N == 4) {
-        *reinterpret_cast<uchar4*>(base + px * 4) = make_uchar4(p.v[0], p.v[1], p.v[2], p.v[3]);
+        *reinterpret_cast<uint32_t*>(base + px * 4) = p.u;
     } else if constexpr (sizeof(CT) == 4 && N == 4) {
         *reinterpret_cast<float4*>(base + px * 4) = make_float4(p.v[0], p.v[1], p.v[2], p.v[3]);
     } else {
@@ -51,9 +58,29 @@ __device__ __forceinline__ void store_px(CT* __restrict__ base, size_t px, const
 template <typename CT, int N>
 __device__ __forceinline__ Pix<CT, N> zero_px() {
     Pix<CT, N> p;
+    if constexpr (sizeof(CT) == 1 && N == 4) {
+        p.u = 0u;
+    } else {
 #pragma unroll
-    for (int k = 0; k < N; ++k) p.v[k] = (CT)0;
+        for (int k = 0; k < N; ++k) p.v[k] = (CT)0;
+    }
     return p;
+}
+
+// interpolation.zig:349-367 on four channels at once.  Horizontal blend on two 16-bit lanes per register
+// (channel * 256 <= 65280 never carries into the neighbour lane), vertical blend per channel in 32 bits:
+// (top * (256 - fy) + bottom * fy + 32768) < 2^24, so ">> 16" leaves the result (<= 255, no clamp needed) in byte 2.
+__device__ __forceinline__ uint32_t bilerp_rgba8(uint32_t tl, uint32_t tr, uint32_t bl, uint32_t br, unsigned fx, unsigned fy) {
+    const unsigned gx = 256u - fx, gy = 256u - fy;
+    const uint32_t t02 = __byte_perm(tl, 0, 0x4240) * gx + __byte_perm(tr, 0, 0x4240) * fx;
+    const uint32_t t13 = __byte_perm(tl, 0, 0x4341) * gx + __byte_perm(tr, 0, 0x4341) * fx;
+    const uint32_t b02 = __byte_perm(bl, 0, 0x4240) * gx + __byte_perm(br, 0, 0x4240) * fx;
+    const uint32_t b13 = __byte_perm(bl, 0, 0x4341) * gx + __byte_perm(br, 0, 0x4341) * fx;
+    const uint32_t r0 = (t02 & 0xFFFFu) * gy + (b02 & 0xFFFFu) * fy + 32768u;
+    const uint32_t r2 = (t02 >> 16) * gy + (b02 >> 16) * fy + 32768u;
+    const uint32_t r1 = (t13 & 0xFFFFu) * gy + (b13 & 0xFFFFu) * fy + 32768u;
+    const uint32_t r3 = (t13 >> 16) * gy + (b13 >> 16) * fy + 32768u;
+    return __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
 }
 
 struct SrcView {
@@ -173,7 +200,10 @@ __device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, fl
         }
         const float lr = x - flx;  // == x - as(f32, left): floor(x) is exactly representable
         const float tb = y - fly;
-        if constexpr (sizeof(CT) == 1) {
+        if constexpr (sizeof(CT) == 1 && N == 4) {
+            const unsigned fx = (unsigned)(int)roundf(lr * 256.0f), fy = (unsigned)(int)roundf(tb * 256.0f);
+            out.u = bilerp_rgba8(tl.u, tr.u, bl.u, br.u, fx, fy);
+        } else if constexpr (sizeof(CT) == 1) {
             // :349-367.  fx, fy in [0, 256]; every intermediate is non-negative and < 2^25, so unsigned shift == @divTrunc
             const unsigned fx = (unsigned)(int)roundf(lr * 256.0f), fy = (unsigned)(int)roundf(tb * 256.0f);
 #pragma unroll

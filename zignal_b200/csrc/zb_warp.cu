@@ -4,8 +4,9 @@
 // :522-531 (warp, always .mirror), image.zig:322-327 (centre = (cols/2, rows/2) as f32),
 // geometry/transforms.zig:39-42,147-150 (affine project: (m0*x + m1*y) + b, no fusion),
 // :224-231 (projective: multiply by 1/w when w != 0).
-// One thread per destination pixel, 2-D 32x8 thread tiles so that a warp's source footprint stays in
-// a few cache lines for any rotation angle.  Compiled with -fmad=false (coordinate math is the
+// One thread per destination pixel; a CTA covers a 32x8 destination tile as 4x2 warps of 8x4 pixels, so that a
+// warp's source footprint is a ~9x9 pixel patch (8-12 sectors per gather) for any rotation angle instead of a
+// 32-pixel diagonal (one sector per lane).  Compiled with -fmad=false (coordinate math is the
 // reference's unfused f32 sequence, which the u8 outputs depend on bit for bit).
 #include <cmath>
 #include <mutex>
@@ -37,6 +38,10 @@ static int rotate_class(float angle) {
     return 0;
 }
 
+// thread -> pixel of the CTA's 32x8 tile: warp w owns the 8x4 patch at (8 * (w & 3), 4 * (w >> 2))
+__device__ __forceinline__ int patch_col(unsigned t) { return (int)(((t >> 5) & 3u) * 8u + (t & 7u)); }
+__device__ __forceinline__ int patch_row(unsigned t) { return (int)((t >> 7) * 4u + ((t >> 3) & 3u)); }
+
 struct RotParams {
     float cos_a, sin_a, cx, cy, rcx, rcy;
     int method, border;
@@ -47,8 +52,8 @@ template <typename CT, int N, int METHOD, int BORDER_T>
 __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long long src_image_pitch, CT* __restrict__ dst, size_t dst_stride,
                                                      unsigned long long dst_image_pitch, int dst_rows, int dst_cols, RotParams p,
                                                      const float* __restrict__ lut) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int c = blockIdx.x * 32 + patch_col(threadIdx.x);
+    const int r = blockIdx.y * 8 + patch_row(threadIdx.x);
     if (c >= dst_cols || r >= dst_rows) return;
     img.data = (const CT*)img.data + (size_t)blockIdx.z * src_image_pitch * N;
     dst += (size_t)blockIdx.z * dst_image_pitch * N;
@@ -102,8 +107,8 @@ struct WarpParams {
 template <typename CT, int N, int METHOD>
 __global__ void __launch_bounds__(256) warp_kernel(SrcView img, CT* __restrict__ dst, size_t dst_stride, int dst_rows, int dst_cols,
                                                    WarpParams p, const float* __restrict__ lut) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int c = blockIdx.x * 32 + patch_col(threadIdx.x);
+    const int r = blockIdx.y * 8 + patch_row(threadIdx.x);
     if (c >= dst_cols || r >= dst_rows) return;
     const float x = (float)c, y = (float)r;
     float sx, sy;

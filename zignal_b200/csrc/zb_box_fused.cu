@@ -42,7 +42,7 @@ struct BoxParams {
     int radius, mu, ou, n_strips, n_bands;
     int ring;                      // rows in the SAT ring (power of two)
     const int* offs;               // [rows][n_strips][4]   row prefix at each strip's first unit
-    const int* offs32;             // [rows][n_win][4]      row prefix at every 32nd unit (checkpoint pass)
+    const int* offs32;             // [rows][n_win][4]      row prefix at every 32nd unit, channel order 0,2,1,3 (checkpoint pass)
     int n_win;                     // ceil(row_units / 32)
     int ck_pitch;                  // floats per checkpoint row: n_win * 128
     float* ckpt;                   // [n_bands][ck_pitch]   S at row (band * BAND - radius - 2), indexed by global element column
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* _
         } else {
             c[0] = (int)__dp4a(v, 0x01010101u, 0u); c[1] = c[2] = c[3] = 0;
         }
-        if (lane == 0) out32[w] = carry;
+        if (lane == 0) out32[w] = make_int4(carry.x, carry.z, carry.y, carry.w);   // channel pairs {0,2} {1,3} contiguous
         if (s < p.n_strips && next_start < u0 + 32) {   // a strip starts inside this window (at most one: OU >= 96)
             const int pos = next_start - u0;              // exclusive prefix over lanes < pos
             int4 part = carry;
@@ -125,35 +125,38 @@ __device__ __forceinline__ int warp_exclusive(int v, int lane) {
 }
 
 // ---- 2. checkpoints: S at row (j * BAND - radius - 2) for every band j >= 1 ------------------------------------------------
-// The only sequential pass, so it carries nothing but the chain: one WARP per (32-unit window, channel) for Rgba -- lane = one
-// pixel, one chain -- and per window for gray (lane = 4 pixels, 4 chains); no block-level synchronisation.  Rows are taken
-// PF at a time: the loads of the next PF rows are in flight while the PF independent warp scans of the current ones run.
+// The only sequential pass, so it carries nothing but the chain and has no block-level synchronisation:
+//   Rgba: one WARP per (32-pixel window, channel pair {0,2} or {1,3}); lane = one pixel; the two channels ride in the 16-bit
+//         halves of one register through a single warp scan (window sums <= 32 * 255);
+//   gray: one warp per 32-unit window; lane = 4 pixels (4 chains), one scan of the lane totals.
+// Rows are taken PF at a time: the loads of the next PF rows are in flight while the PF independent scans of the current ones
+// run.  A short head makes every checkpoint row the last row of a PF-chunk.
 template <int CH>
 __global__ void __launch_bounds__(128) box_checkpoints(const BoxParams p) {
-    constexpr int PF = 8;
-    constexpr int NC = CH == 4 ? 1 : 4;   // chains per lane
+    constexpr int PF = 16;
+    constexpr int NC = CH == 4 ? 2 : 4;   // chains per lane
+    constexpr int WPW = CH == 4 ? 2 : 1;  // warps per window
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int win = CH == 4 ? gw >> 2 : gw;
-    const int k = CH == 4 ? gw & 3 : 0;
+    const int win = gw / WPW;
+    const int kp = gw % WPW;              // Rgba: channels kp and kp + 2
     if (win >= p.n_win) return;
     const int unit = win * 32 + lane;
     const bool in_row = unit < p.row_units;
     const bool full = CH == 4 || 4 * unit + 4 <= p.row_bytes;
     const uint8_t* colp = p.src + 4 * (size_t)unit;
-    const int* offp = p.offs32 + (size_t)win * 4 + k;
-    const size_t off_row = (size_t)p.n_win * 4;
+    const int2* offp = reinterpret_cast<const int2*>(p.offs32) + 2 * win + kp;   // gray: .x only (kp == 0)
     float S[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) S[i] = 0.0f;
-    const int y_end = (p.n_bands - 1) * BAND - p.radius - 2;   // last checkpoint row
+    const int y_end = (p.n_bands - 1) * BAND - p.radius - 2;   // last checkpoint row (< rows)
 
-    uint32_t u[PF], un[PF];
-    int off[PF], offn[PF];
+    uint32_t un[PF];
+    int2 offn[PF];
     auto fetch = [&](int y0) {
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
-            const int y = min(y0 + i, p.rows - 1);
+            const int y = min(y0 + i, y_end);
             const uint8_t* q = colp + (size_t)y * p.src_pitch;
             uint32_t v = 0;
             if (in_row) {
@@ -161,46 +164,66 @@ __global__ void __launch_bounds__(128) box_checkpoints(const BoxParams p) {
                 else for (int b = 0; 4 * unit + b < p.row_bytes; ++b) v |= (uint32_t)q[b] << (8 * b);
             }
             un[i] = v;
-            offn[i] = __ldg(offp + (size_t)y * off_row);
+            offn[i] = __ldg(offp + (size_t)y * (2 * p.n_win));
         }
     };
-    fetch(0);
-    for (int yb = 0; yb <= y_end; yb += PF) {
+    // rows [y0, y0 + n) with the loads already in un / offn; the next chunk's loads are issued first
+    auto chunk = [&](int y0, int n, int y_next) {
+        uint32_t u[PF];
+        int2 off[PF];
 #pragma unroll
         for (int i = 0; i < PF; ++i) { u[i] = un[i]; off[i] = offn[i]; }
-        if (yb + PF <= y_end) fetch(yb + PF);
+        if (y_next <= y_end) fetch(y_next);
         float pv[PF][NC];
 #pragma unroll
         for (int i = 0; i < PF; ++i) {   // PF independent scans
-            int loc[NC];
-            int run = 0;
             if constexpr (CH == 4) {
-                run = (int)((u[i] >> (8 * k)) & 0xFFu);
-                loc[0] = run;
+                uint32_t incl = __byte_perm(u[i], 0, kp ? 0x4341 : 0x4240);   // channel kp | channel kp+2 << 16
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                pv[i][0] = (float)(off[i].x + (int)(incl & 0xFFFFu));
+                pv[i][1] = (float)(off[i].y + (int)(incl >> 16));
             } else {
+                int loc[4];
+                int run = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     run += (int)((u[i] >> (8 * b)) & 0xFFu);
                     loc[b] = run;
                 }
-            }
-            const int base = off[i] + warp_exclusive(run, lane);
+                const int base = off[i].x + warp_exclusive(run, lane);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) pv[i][c] = (float)(base + loc[c]);
+                for (int c = 0; c < 4; ++c) pv[i][c] = (float)(base + loc[c]);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {   // the chains, row by row
-            const int y = yb + i;
-            if (y <= y_end) {
+        for (int i = 0; i < PF; ++i)     // the chains, row by row
+            if (i < n) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) S[c] = __fadd_rn(S[c], pv[i][c]);
-                const int q = y + p.radius + 2;
-                if (q % BAND == 0) {
-                    float* ck = p.ckpt + (size_t)(q / BAND) * p.ck_pitch + (size_t)unit * 4;
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) ck[CH == 4 ? k : c] = S[c];
-                }
             }
+    };
+
+    const int head = (BAND - p.radius - 1) % PF;   // rows before the PF-aligned part
+    fetch(0);
+    int y = 0;
+    if (head > 0) {
+        chunk(0, head, head);
+        y = head;
+    }
+    for (int jb = 1; jb < p.n_bands; ++jb) {
+        const int yq = jb * BAND - p.radius - 2;   // S of this row resumes band jb; (yq - y + 1) is a multiple of PF
+        for (; y <= yq; y += PF) chunk(y, PF, y + PF);
+        float* ck = p.ckpt + (size_t)jb * p.ck_pitch + (size_t)unit * 4;
+        if constexpr (CH == 4) {
+            ck[kp] = S[0];
+            ck[kp + 2] = S[1];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ck[c] = S[c];
         }
     }
 }
@@ -214,7 +237,12 @@ __device__ __forceinline__ float div_exact(float s, float area, float rcp) {
 }
 // meta.clamp(u8, f32) for the values this path produces: v = m / area or 2*orig - m / area with integer m, so v is either an
 // exact tie k + 0.5 or at least 1/(2*961) away from one -- trunc(v + 0.5) equals round-half-away for v >= 0, and v < 0 clamps to 0.
-__device__ __forceinline__ uint32_t clamp_u8_fast(float v) { return (uint32_t)min(max(__float2int_rz(__fadd_rn(v, 0.5f)), 0), 255); }
+// (float -> u8 conversion saturates: one instruction does the truncation and both clamps)
+__device__ __forceinline__ uint32_t clamp_u8_fast(float v) {
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(__fadd_rn(v, 0.5f)));
+    return r;
+}
 
 // MODE 1: box blur, MODE 2: sharpen (grid = n_strips x n_bands).
 template <int CH, int MODE>
@@ -242,6 +270,28 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
         s1 = (e1 >= 0 && e1 < p.ck_pitch) ? ck[e1] : 0.0f;
     }
 
+    // evaluation geometry of this thread's unit: loop invariant (the column window never changes)
+    float* zrow = ring + p.ring * SE;                 // 16 zero floats: the SAT left of / above the image
+    if (t < 16) zrow[t] = 0.0f;
+    const int ev_unit = strip * p.ou + (t & (SU - 1));
+    const bool ev_active = (t & (SU - 1)) < min(p.ou, p.row_units - strip * p.ou);
+    constexpr int NJ = CH == 4 ? 1 : 4;               // distinct pixel columns per unit
+    int ed[NJ], el[NJ], wcols[NJ];
+    bool has_left[NJ];
+    float area_full[NJ], rcp_full[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int c = CH == 4 ? ev_unit : min(4 * ev_unit + j, p.cols - 1);
+        const int c1 = max(c - p.radius, 0), c2 = min(c + p.radius, p.cols - 1);
+        ed[j] = (CH == 4 ? 4 * c2 : c2) - elem0;              // local element of column c2 (channel 0)
+        el[j] = (CH == 4 ? 4 * (c1 - 1) : c1 - 1) - elem0;    // local element of column c1 - 1
+        has_left[j] = c1 > 0;
+        wcols[j] = c2 - c1 + 1;
+        area_full[j] = (float)((2 * p.radius + 1) * wcols[j]);
+        rcp_full[j] = __frcp_rn(area_full[j]);
+    }
+    uint8_t* dcol = p.dst + 4 * (size_t)ev_unit;
+
     // the loads of a block are issued one block ahead of their use
     uint32_t un[4] = {0u, 0u, 0u, 0u};
     int4 offn = make_int4(0, 0, 0, 0);
@@ -262,7 +312,7 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
             const uint32_t u[4] = {un[0], un[1], un[2], un[3]};
             const int off[4] = {offn.x, offn.y, offn.z, offn.w};
             if (yb + GR <= y_last) fetch(y + GR);
-            if (y < p.rows) {
+            {   // (rows past the image end compute on stale registers; the chain phase never reads their tile row)
                 float* dstp = pt + wrow * SE;
                 if constexpr (CH == 4) {
                     int loc[4][4];   // [unit][channel] inclusive local prefix
@@ -327,31 +377,28 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
             }
         }
         __syncthreads();
-        // ---- evaluation of the output rows this block completed: yo = y - radius
-        {
-            const int out_u0 = strip * p.ou;                          // first output unit of the strip
-            const int out_un = min(p.ou, p.row_units - out_u0);      // output units in this strip
-            const int uu = t & (SU - 1);
+        // ---- evaluation of the output rows this block completed: yo = y - radius (thread: one unit, rows g, g+2, ..)
+        if (ev_active) {
             for (int g = t >> 7; g < GR; g += BF_THREADS / SU) {
                 const int yo = yb + g - p.radius;
-                if (uu >= out_un || yo < y0 || yo >= y1) continue;
+                if (yo < y0 || yo >= y1) continue;
                 const int r1 = max(yo - p.radius, 0), r2 = min(yo + p.radius, p.rows - 1);
+                const int h = r2 - r1 + 1;
                 const float* row_d = ring + (r2 & rmask) * SE;
-                const float* row_t = ring + ((r1 - 1) & rmask) * SE;
-                const int unit = out_u0 + uu;
+                const float* row_t = r1 > 0 ? ring + ((r1 - 1) & rmask) * SE : zrow;   // above the image: zeros
                 uint32_t orig = 0;
-                if constexpr (MODE == 2) orig = load_unit<CH>(p.src + (size_t)yo * p.src_pitch, unit, p.row_units, p.row_bytes);
+                if constexpr (MODE == 2) orig = load_unit<CH>(p.src + (size_t)yo * p.src_pitch, ev_unit, p.row_units, p.row_bytes);
                 uint32_t packed = 0;
                 if constexpr (CH == 4) {
-                    const int c = unit;
-                    const int c1 = max(c - p.radius, 0), c2 = min(c + p.radius, p.cols - 1);
-                    const float area = (float)((r2 - r1 + 1) * (c2 - c1 + 1));
-                    const float rcp = __frcp_rn(area);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 D = *reinterpret_cast<const float4*>(row_d + (4 * c2 - elem0));
-                    const float4 Lf = c1 > 0 ? *reinterpret_cast<const float4*>(row_d + (4 * (c1 - 1) - elem0)) : z;
-                    const float4 T = r1 > 0 ? *reinterpret_cast<const float4*>(row_t + (4 * c2 - elem0)) : z;
-                    const float4 Cn = (r1 > 0 && c1 > 0) ? *reinterpret_cast<const float4*>(row_t + (4 * (c1 - 1) - elem0)) : z;
+                    float area = area_full[0], rcp = rcp_full[0];
+                    if (h != 2 * p.radius + 1) {
+                        area = (float)(h * wcols[0]);
+                        rcp = __frcp_rn(area);
+                    }
+                    const float4 D = *reinterpret_cast<const float4*>(row_d + ed[0]);
+                    const float4 T = *reinterpret_cast<const float4*>(row_t + (r1 > 0 ? ed[0] : 0));
+                    const float4 Lf = *reinterpret_cast<const float4*>(has_left[0] ? row_d + el[0] : zrow);
+                    const float4 Cn = *reinterpret_cast<const float4*>((has_left[0] && r1 > 0) ? row_t + el[0] : zrow);
                     const float dv[4] = {D.x, D.y, D.z, D.w}, lv[4] = {Lf.x, Lf.y, Lf.z, Lf.w};
                     const float tv[4] = {T.x, T.y, T.z, T.w}, cv[4] = {Cn.x, Cn.y, Cn.z, Cn.w};
 #pragma unroll
@@ -362,29 +409,29 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
                         packed |= clamp_u8_fast(val) << (8 * j);
                     }
                 } else {
-                    const float rows_f = (float)(r2 - r1 + 1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int c = 4 * unit + j;                   // pixel column
-                        if (c >= p.cols) break;
-                        const int c1 = max(c - p.radius, 0), c2 = min(c + p.radius, p.cols - 1);
-                        const int ed = c2 - elem0, el = c1 - 1 - elem0;
-                        const float area = __fmul_rn(rows_f, (float)(c2 - c1 + 1));
-                        const float D = row_d[ed];
-                        const float left = c1 > 0 ? row_d[el] : 0.0f;
-                        const float top = r1 > 0 ? row_t[ed] : 0.0f;
-                        const float corner = (r1 > 0 && c1 > 0) ? row_t[el] : 0.0f;
+                        if (4 * ev_unit + j >= p.cols) break;
+                        float area = area_full[j], rcp = rcp_full[j];
+                        if (h != 2 * p.radius + 1) {
+                            area = (float)(h * wcols[j]);
+                            rcp = __frcp_rn(area);
+                        }
+                        const float D = row_d[ed[j]];
+                        const float top = row_t[r1 > 0 ? ed[j] : 0];
+                        const float left = has_left[j] ? row_d[el[j]] : 0.0f;
+                        const float corner = (has_left[j] && r1 > 0) ? row_t[el[j]] : 0.0f;
                         const float sum = __fadd_rn(__fsub_rn(__fsub_rn(D, left), top), corner);
-                        float val = div_exact(sum, area, __frcp_rn(area));
+                        float val = div_exact(sum, area, rcp);
                         if constexpr (MODE == 2) val = __fsub_rn(__fmul_rn(2.0f, (float)((orig >> (8 * j)) & 0xFFu)), val);
                         packed |= clamp_u8_fast(val) << (8 * j);
                     }
                 }
-                uint8_t* drow = p.dst + (size_t)yo * p.dst_pitch;
-                if (4 * unit + 4 <= p.row_bytes) {
-                    *reinterpret_cast<uint32_t*>(drow + 4 * (size_t)unit) = packed;
+                uint8_t* dpx = dcol + (size_t)yo * p.dst_pitch;
+                if (CH == 4 || 4 * ev_unit + 4 <= p.row_bytes) {
+                    *reinterpret_cast<uint32_t*>(dpx) = packed;
                 } else {
-                    for (int b = 0; 4 * unit + b < p.row_bytes; ++b) drow[4 * (size_t)unit + b] = (uint8_t)(packed >> (8 * b));
+                    for (int b = 0; 4 * ev_unit + b < p.row_bytes; ++b) dpx[b] = (uint8_t)(packed >> (8 * b));
                 }
             }
             // no barrier needed here: a thread only reaches the next chain phase (the next ring write) through the barrier after
@@ -397,9 +444,9 @@ template <int CH>
 int launch_all(const BoxParams& p, bool sharpen, int* offs, int* offs32, cudaStream_t s) {
     box_row_offsets<CH><<<div_up(p.rows, 8), 256, 0, s>>>(p, offs, offs32);
     ZB_LAUNCHED();
-    const int smem_ev = (GR + p.ring) * SE * (int)sizeof(float);
+    const int smem_ev = ((GR + p.ring) * SE + 16) * (int)sizeof(float);
     if (p.n_bands > 1) {
-        const int warps = CH == 4 ? 4 * p.n_win : p.n_win;
+        const int warps = CH == 4 ? 2 * p.n_win : p.n_win;
         box_checkpoints<CH><<<div_up(warps, 4), 128, 0, s>>>(p);
         ZB_LAUNCHED();
     }

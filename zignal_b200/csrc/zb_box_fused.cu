@@ -41,8 +41,10 @@ struct BoxParams {
     int row_bytes;                 // cols * CH
     int radius, mu, ou, n_strips, n_bands;
     int ring;                      // rows in the SAT ring (power of two)
-    const int* offs;               // [rows][n_strips][4]   row prefix at each strip's first unit
-    const int* offs32;             // [rows][n_win][4]      row prefix at every 32nd unit, channel order 0,2,1,3 (checkpoint pass)
+    // both tables hold (prefix - 2^23) as f32 -- exact, since prefixes are integers below 2^24 -- so that
+    // P = table + float(2^23 + small) needs no integer-to-float conversion in the consumers
+    const float* offs;             // [rows][n_strips][4]   row prefix at each strip's first unit
+    const float* offs32;           // [rows][n_win][4]      row prefix at every 32nd unit, channel order 0,2,1,3 (checkpoint pass)
     int n_win;                     // ceil(row_units / 32)
     int ck_pitch;                  // floats per checkpoint row: n_win * 128
     float* ckpt;                   // [n_bands][ck_pitch]   S at row (band * BAND - radius - 2), indexed by global element column
@@ -66,7 +68,7 @@ __device__ __forceinline__ int pt_index(int e) { return pt_chunk(e >> 2) * 4 + (
 
 // ---- 1. exact row prefixes: at every 32nd unit (for the checkpoint pass) and at every strip start ------------------------------
 template <int CH>
-__global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* __restrict__ offs, int* __restrict__ offs32) {
+__global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, float* __restrict__ offs, float* __restrict__ offs32) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= p.rows) return;
@@ -74,10 +76,13 @@ __global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* _
     int4 carry = make_int4(0, 0, 0, 0);
     int s = 0;                       // next strip whose start has not been passed
     int next_start = -p.mu;          // unit index of strip s's first unit
-    int4* out = reinterpret_cast<int4*>(offs) + (size_t)r * p.n_strips;
-    int4* out32 = reinterpret_cast<int4*>(offs32) + (size_t)r * p.n_win;
+    float4* out = reinterpret_cast<float4*>(offs) + (size_t)r * p.n_strips;
+    float4* out32 = reinterpret_cast<float4*>(offs32) + (size_t)r * p.n_win;
+    auto biased = [](int a, int b, int c, int d) {
+        return make_float4((float)(a - 8388608), (float)(b - 8388608), (float)(c - 8388608), (float)(d - 8388608));
+    };
     while (s < p.n_strips && next_start <= 0) {   // strips that start at or left of the row start: prefix 0
-        if (lane == 0) out[s] = carry;
+        if (lane == 0) out[s] = biased(carry.x, carry.y, carry.z, carry.w);
         ++s;
         next_start += p.ou;
     }
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* _
         } else {
             c[0] = (int)__dp4a(v, 0x01010101u, 0u); c[1] = c[2] = c[3] = 0;
         }
-        if (lane == 0) out32[w] = make_int4(carry.x, carry.z, carry.y, carry.w);   // channel pairs {0,2} {1,3} contiguous
+        if (lane == 0) out32[w] = biased(carry.x, carry.z, carry.y, carry.w);   // channel pairs {0,2} {1,3} contiguous
         if (s < p.n_strips && next_start < u0 + 32) {   // a strip starts inside this window (at most one: OU >= 96)
             const int pos = next_start - u0;              // exclusive prefix over lanes < pos
             int4 part = carry;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* _
                 part.z += __reduce_add_sync(0xffffffffu, lane < pos ? c[2] : 0);
                 part.w += __reduce_add_sync(0xffffffffu, lane < pos ? c[3] : 0);
             }
-            if (lane == 0) out[s] = part;
+            if (lane == 0) out[s] = biased(part.x, part.y, part.z, part.w);
             ++s;
             next_start += p.ou;
         }
@@ -111,6 +116,24 @@ __global__ void __launch_bounds__(256) box_row_offsets(const BoxParams p, int* _
             carry.w += __reduce_add_sync(0xffffffffu, c[3]);
         }
     }
+}
+
+// inclusive prefix over the lanes of a warp (also on two 16-bit halves at once, as long as no half overflows)
+__device__ __forceinline__ uint32_t warp_inclusive(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        const uint32_t take = lane >= d ? 1u : 0u;   // loop invariant in every caller
+        // one multiply-add per step.  (A predicated add would also be one instruction, but 16 interleaved scans would need 16
+        // live predicates and the 7 predicate registers serialise them; written in C the compiler turns this into SEL + IADD.)
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(v) : "r"(o), "r"(take));
+    }
+    return v;
+}
+// 2^23 + x as a float for the low (HI = false) or high 16 bits of a packed register: one byte permute
+template <bool HI>
+__device__ __forceinline__ float magic16(uint32_t packed) {
+    return __uint_as_float(__byte_perm(packed, 0x4B000000u, HI ? 0x7432 : 0x7410));
 }
 
 // exclusive prefix over the lanes of a warp
@@ -145,32 +168,35 @@ __global__ void __launch_bounds__(128) box_checkpoints(const BoxParams p) {
     const bool in_row = unit < p.row_units;
     const bool full = CH == 4 || 4 * unit + 4 <= p.row_bytes;
     const uint8_t* colp = p.src + 4 * (size_t)unit;
-    const int2* offp = reinterpret_cast<const int2*>(p.offs32) + 2 * win + kp;   // gray: .x only (kp == 0)
+    const float2* offp = reinterpret_cast<const float2*>(p.offs32) + 2 * win + kp;   // gray: .x only (kp == 0)
     float S[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) S[i] = 0.0f;
     const int y_end = (p.n_bands - 1) * BAND - p.radius - 2;   // last checkpoint row (< rows)
 
     uint32_t un[PF];
-    int2 offn[PF];
-    auto fetch = [&](int y0) {
+    float2 offn[PF];
+    const size_t off_pitch = 2 * (size_t)p.n_win;
+    auto fetch = [&](int y0) {   // rows y0 .. y0 + PF - 1, all <= y_end: every chunk ends on or before the last checkpoint row
+        const uint8_t* q = colp + (size_t)y0 * p.src_pitch;
+        const float2* o = offp + (size_t)y0 * off_pitch;
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
-            const int y = min(y0 + i, y_end);
-            const uint8_t* q = colp + (size_t)y * p.src_pitch;
             uint32_t v = 0;
             if (in_row) {
                 if (full) v = __ldg(reinterpret_cast<const uint32_t*>(q));
                 else for (int b = 0; 4 * unit + b < p.row_bytes; ++b) v |= (uint32_t)q[b] << (8 * b);
             }
             un[i] = v;
-            offn[i] = __ldg(offp + (size_t)y * (2 * p.n_win));
+            offn[i] = __ldg(o);
+            q += p.src_pitch;
+            o += off_pitch;
         }
     };
     // rows [y0, y0 + n) with the loads already in un / offn; the next chunk's loads are issued first
     auto chunk = [&](int y0, int n, int y_next) {
         uint32_t u[PF];
-        int2 off[PF];
+        float2 off[PF];
 #pragma unroll
         for (int i = 0; i < PF; ++i) { u[i] = un[i]; off[i] = offn[i]; }
         if (y_next <= y_end) fetch(y_next);
@@ -178,25 +204,20 @@ __global__ void __launch_bounds__(128) box_checkpoints(const BoxParams p) {
 #pragma unroll
         for (int i = 0; i < PF; ++i) {   // PF independent scans
             if constexpr (CH == 4) {
-                uint32_t incl = __byte_perm(u[i], 0, kp ? 0x4341 : 0x4240);   // channel kp | channel kp+2 << 16
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                pv[i][0] = (float)(off[i].x + (int)(incl & 0xFFFFu));
-                pv[i][1] = (float)(off[i].y + (int)(incl >> 16));
+                const uint32_t incl = warp_inclusive(__byte_perm(u[i], 0, kp ? 0x4341 : 0x4240), lane);   // channel kp | channel kp+2 << 16
+                pv[i][0] = __fadd_rn(magic16<false>(incl), off[i].x);
+                pv[i][1] = __fadd_rn(magic16<true>(incl), off[i].y);
             } else {
-                int loc[4];
-                int run = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    run += (int)((u[i] >> (8 * b)) & 0xFFu);
-                    loc[b] = run;
-                }
-                const int base = off[i].x + warp_exclusive(run, lane);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) pv[i][c] = (float)(base + loc[c]);
+                // 4 pixels of the lane: inclusive local prefix in two packed registers (p0 | p0+p1 << 16, .. + p2 | .. + p3 << 16)
+                const uint32_t b0 = u[i] & 0xFFu, b1 = (u[i] >> 8) & 0xFFu, b2 = (u[i] >> 16) & 0xFFu, b3 = u[i] >> 24;
+                const uint32_t tot = b0 + b1 + b2 + b3;
+                const uint32_t excl = warp_inclusive(tot, lane) - tot;      // < 32 * 1020
+                const uint32_t l01 = (excl + b0) | ((excl + b0 + b1) << 16);
+                const uint32_t l23 = (excl + b0 + b1 + b2) | ((excl + tot) << 16);
+                pv[i][0] = __fadd_rn(magic16<false>(l01), off[i].x);
+                pv[i][1] = __fadd_rn(magic16<true>(l01), off[i].x);
+                pv[i][2] = __fadd_rn(magic16<false>(l23), off[i].x);
+                pv[i][3] = __fadd_rn(magic16<true>(l23), off[i].x);
             }
         }
 #pragma unroll
@@ -235,12 +256,15 @@ __device__ __forceinline__ float div_exact(float s, float area, float rcp) {
     const float q1 = __fmaf_rn(__fmaf_rn(-q0, area, s), rcp, q0);
     return __fmaf_rn(__fmaf_rn(-q1, area, s), rcp, q1);
 }
-// meta.clamp(u8, f32) for the values this path produces: v = m / area or 2*orig - m / area with integer m, so v is either an
-// exact tie k + 0.5 or at least 1/(2*961) away from one -- trunc(v + 0.5) equals round-half-away for v >= 0, and v < 0 clamps to 0.
-// (float -> u8 conversion saturates: one instruction does the truncation and both clamps)
-__device__ __forceinline__ uint32_t clamp_u8_fast(float v) {
+// meta.clamp(u8, fl(m / area)) [blur] or meta.clamp(u8, fl(2*orig - fl(m / area))) [sharpen] WITHOUT the exact division.
+// m is an integer (a combination of integer-valued floats) and area <= 31*31, so the exact value v is either a tie k + 1/2
+// -- which the reference's correctly rounded divide represents exactly and then rounds away from zero -- or at least
+// 1/(2*961) = 5.2e-4 away from every tie, far more than the 3e-5 that q = m * RN(1/area) can be off for |q| <= 256 (larger |q|
+// saturate either way).  Hence trunc(q + 1/2 + 1e-4) is the reference's result for q >= 0, and every negative value clamps to 0
+// exactly as its round-half-away does.  The float -> u8 conversion saturates: one instruction truncates and clamps both sides.
+__device__ __forceinline__ uint32_t round_clamp_u8(float q) {
     uint32_t r;
-    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(__fadd_rn(v, 0.5f)));
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(__fadd_rn(q, 0.5001f)));
     return r;
 }
 
@@ -294,69 +318,64 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
 
     // the loads of a block are issued one block ahead of their use
     uint32_t un[4] = {0u, 0u, 0u, 0u};
-    int4 offn = make_int4(0, 0, 0, 0);
+    float4 offn = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch = [&](int y) {
         if (y < p.rows) {
             const uint8_t* rowp = p.src + (size_t)y * p.src_pitch;
 #pragma unroll
             for (int j = 0; j < 4; ++j) un[j] = load_unit<CH>(rowp, unit0 + 4 * lane + j, p.row_units, p.row_bytes);
-            offn = __ldg(reinterpret_cast<const int4*>(p.offs + ((size_t)y * p.n_strips + strip) * 4));
+            offn = __ldg(reinterpret_cast<const float4*>(p.offs + ((size_t)y * p.n_strips + strip) * 4));
         }
     };
     fetch(ys + wrow);
 
     for (int yb = ys; yb <= y_last; yb += GR) {
-        // ---- P phase: warp `wrow` owns row yb + wrow; lane l owns units 4l .. 4l+3 of the strip
+        // ---- P phase: warp `wrow` owns row yb + wrow; lane l owns units 4l .. 4l+3 of the strip.  All integer work rides in
+        // 16-bit halves (in-strip prefixes are <= 512 * 255 / 4 .. < 2^16); P = (2^23 + in-strip prefix) + (strip offset - 2^23).
         {
             const int y = yb + wrow;
             const uint32_t u[4] = {un[0], un[1], un[2], un[3]};
-            const int off[4] = {offn.x, offn.y, offn.z, offn.w};
+            const float4 off = offn;
             if (yb + GR <= y_last) fetch(y + GR);
-            {   // (rows past the image end compute on stale registers; the chain phase never reads their tile row)
-                float* dstp = pt + wrow * SE;
-                if constexpr (CH == 4) {
-                    int loc[4][4];   // [unit][channel] inclusive local prefix
+            // (rows past the image end compute on stale registers; the chain phase never reads their tile row)
+            float* dstp = pt + wrow * SE;
+            if constexpr (CH == 4) {
+                uint32_t l02[4], l13[4];   // inclusive local prefix: channels {0,2} and {1,3} in 16-bit halves
+                l02[0] = __byte_perm(u[0], 0, 0x4240);
+                l13[0] = __byte_perm(u[0], 0, 0x4341);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        int run = 0;
+                for (int j = 1; j < 4; ++j) {
+                    l02[j] = l02[j - 1] + __byte_perm(u[j], 0, 0x4240);
+                    l13[j] = l13[j - 1] + __byte_perm(u[j], 0, 0x4341);
+                }
+                const uint32_t e02 = warp_inclusive(l02[3], lane) - l02[3];   // exclusive over lanes: <= 124 * 255 per half
+                const uint32_t e13 = warp_inclusive(l13[3], lane) - l13[3];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            run += (int)((u[j] >> (8 * k)) & 0xFFu);
-                            loc[j][k] = run;
-                        }
-                    }
-                    int base[4];
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t a = e02 + l02[j], b = e13 + l13[j];
+                    float4 f;
+                    f.x = __fadd_rn(magic16<false>(a), off.x);
+                    f.y = __fadd_rn(magic16<false>(b), off.y);
+                    f.z = __fadd_rn(magic16<true>(a), off.z);
+                    f.w = __fadd_rn(magic16<true>(b), off.w);
+                    *reinterpret_cast<float4*>(dstp + pt_chunk(4 * lane + j) * 4) = f;
+                }
+            } else {
+                uint32_t tot[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) base[k] = off[k] + warp_exclusive(loc[3][k], lane);
+                for (int j = 0; j < 4; ++j) tot[j] = __dp4a(u[j], 0x01010101u, 0u);
+                const uint32_t lane_tot = tot[0] + tot[1] + tot[2] + tot[3];
+                uint32_t run = warp_inclusive(lane_tot, lane) - lane_tot;     // < 512 * 255 = 130560: needs 17 bits, so no packing here
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 f;
-                        f.x = (float)(base[0] + loc[j][0]);
-                        f.y = (float)(base[1] + loc[j][1]);
-                        f.z = (float)(base[2] + loc[j][2]);
-                        f.w = (float)(base[3] + loc[j][3]);
-                        *reinterpret_cast<float4*>(dstp + pt_chunk(4 * lane + j) * 4) = f;
-                    }
-                } else {
-                    int loc[16];
-                    int run = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            run += (int)((u[j] >> (8 * b)) & 0xFFu);
-                            loc[4 * j + b] = run;
-                        }
-                    const int base = off[0] + warp_exclusive(run, lane);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 f;
-                        f.x = (float)(base + loc[4 * j + 0]);
-                        f.y = (float)(base + loc[4 * j + 1]);
-                        f.z = (float)(base + loc[4 * j + 2]);
-                        f.w = (float)(base + loc[4 * j + 3]);
-                        *reinterpret_cast<float4*>(dstp + pt_chunk(4 * lane + j) * 4) = f;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t b0 = u[j] & 0xFFu, b1 = (u[j] >> 8) & 0xFFu, b2 = (u[j] >> 16) & 0xFFu;
+                    float4 f;
+                    f.x = __fadd_rn(__uint_as_float(0x4B000000u | (run + b0)), off.x);
+                    f.y = __fadd_rn(__uint_as_float(0x4B000000u | (run + b0 + b1)), off.x);
+                    f.z = __fadd_rn(__uint_as_float(0x4B000000u | (run + b0 + b1 + b2)), off.x);
+                    run += tot[j];
+                    f.w = __fadd_rn(__uint_as_float(0x4B000000u | run), off.x);
+                    *reinterpret_cast<float4*>(dstp + pt_chunk(4 * lane + j) * 4) = f;
                 }
             }
         }
@@ -404,9 +423,9 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float sum = __fadd_rn(__fsub_rn(__fsub_rn(dv[j], lv[j]), tv[j]), cv[j]);   // integral.zig:86-89
-                        float val = div_exact(sum, area, rcp);
-                        if constexpr (MODE == 2) val = __fsub_rn(__fmul_rn(2.0f, (float)((orig >> (8 * j)) & 0xFFu)), val);   // integral.zig:357
-                        packed |= clamp_u8_fast(val) << (8 * j);
+                        float val = __fmul_rn(sum, rcp);
+                        if constexpr (MODE == 2) val = __fsub_rn((float)(2u * ((orig >> (8 * j)) & 0xFFu)), val);   // integral.zig:357 (2 * orig is exact)
+                        packed |= round_clamp_u8(val) << (8 * j);
                     }
                 } else {
 #pragma unroll
@@ -422,9 +441,9 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
                         const float left = has_left[j] ? row_d[el[j]] : 0.0f;
                         const float corner = (has_left[j] && r1 > 0) ? row_t[el[j]] : 0.0f;
                         const float sum = __fadd_rn(__fsub_rn(__fsub_rn(D, left), top), corner);
-                        float val = div_exact(sum, area, rcp);
-                        if constexpr (MODE == 2) val = __fsub_rn(__fmul_rn(2.0f, (float)((orig >> (8 * j)) & 0xFFu)), val);
-                        packed |= clamp_u8_fast(val) << (8 * j);
+                        float val = __fmul_rn(sum, rcp);
+                        if constexpr (MODE == 2) val = __fsub_rn((float)(2u * ((orig >> (8 * j)) & 0xFFu)), val);
+                        packed |= round_clamp_u8(val) << (8 * j);
                     }
                 }
                 uint8_t* dpx = dcol + (size_t)yo * p.dst_pitch;
@@ -441,7 +460,7 @@ __global__ void __launch_bounds__(BF_THREADS) box_chain(const BoxParams p) {
 }
 
 template <int CH>
-int launch_all(const BoxParams& p, bool sharpen, int* offs, int* offs32, cudaStream_t s) {
+int launch_all(const BoxParams& p, bool sharpen, float* offs, float* offs32, cudaStream_t s) {
     box_row_offsets<CH><<<div_up(p.rows, 8), 256, 0, s>>>(p, offs, offs32);
     ZB_LAUNCHED();
     const int smem_ev = ((GR + p.ring) * SE + 16) * (int)sizeof(float);
@@ -497,12 +516,12 @@ int box_fused_u8(const zb_image* src, zb_image* dst, int channels, uint32_t radi
     if (rc) return rc;
     if ((rc = offs32.alloc((size_t)p.rows * p.n_win * 4 * sizeof(int), s))) return rc;
     if ((rc = ckpt.alloc((size_t)p.n_bands * p.ck_pitch * sizeof(float), s))) return rc;
-    p.offs = offs.as<int>();
-    p.offs32 = offs32.as<int>();
+    p.offs = offs.as<float>();
+    p.offs32 = offs32.as<float>();
     p.ckpt = ckpt.as<float>();
     t_last_kernel = sharpen ? "box_fused_sharpen" : "box_fused_blur";
-    return channels == 4 ? launch_all<4>(p, sharpen, offs.as<int>(), offs32.as<int>(), s)
-                         : launch_all<1>(p, sharpen, offs.as<int>(), offs32.as<int>(), s);
+    return channels == 4 ? launch_all<4>(p, sharpen, offs.as<float>(), offs32.as<float>(), s)
+                         : launch_all<1>(p, sharpen, offs.as<float>(), offs32.as<float>(), s);
 }
 
 }  // namespace zb

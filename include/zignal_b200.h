@@ -120,6 +120,13 @@ int zb_gaussian_taps(float sigma, float* taps, int cap, int* n);
  * convolution.zig:313-438.  kx/ky are HOST arrays.  In-place (src->data == dst->data) is allowed. */
 int zb_conv_separable(const zb_image* src, zb_image* dst, int pixfmt,
                       const float* kx, int nx, const float* ky, int ny, int border, zb_stream s);
+/* Sharding extension (no reference counterpart): the same operation restricted to the OUTPUT rows
+ * [row_begin, row_end) of dst.  src is still the whole image, so border handling and every value are identical to
+ * the full call.  A row-block owner convolves the rows that do not depend on its halo while the halo exchange is in
+ * flight, then the few boundary rows.  row_end == 0 means "to the last row". */
+int zb_conv_separable_rows(const zb_image* src, zb_image* dst, int pixfmt,
+                           const float* kx, int nx, const float* ky, int ny, int border,
+                           uint32_t row_begin, uint32_t row_end, zb_stream s);
 /* Image.convolve(out, allocator, kernel, border)   image.zig:917-931, convolution.zig:198-301.
  * kernel: HOST kh*kw row-major f32 (the comptime 2-D array after `as(f32, .)`). */
 int zb_convolve(const zb_image* src, zb_image* dst, int pixfmt,

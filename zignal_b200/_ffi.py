@@ -82,6 +82,7 @@ def _declare(L):
         "zb_kernel_launch_count": ([], u64),
         "zb_gaussian_taps": ([f, fp, i, P(i)], i),
         "zb_conv_separable": ([img, img, i, fp, i, fp, i, i, vp], i),
+        "zb_conv_separable_rows": ([img, img, i, fp, i, fp, i, i, C.c_uint32, C.c_uint32, vp], i),
         "zb_convolve": ([img, img, i, fp, i, i, i, vp], i),
         "zb_gaussian_blur": ([img, img, i, f, vp], i),
         "zb_box_blur": ([img, img, i, u32, vp], i),

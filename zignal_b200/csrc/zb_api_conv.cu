@@ -18,24 +18,37 @@ static int check_shapes(const zb_image* src, const zb_image* dst, int pixfmt) {
     return ZB_OK;
 }
 
+// Output rows [row0, row1) only (row1 < 0: all rows).
 int conv_separable_dispatch(const zb_image* src, zb_image* dst, int pixfmt, const float* kx, int nx, const float* ky, int ny,
-                            int border, cudaStream_t s) {
+                            int border, cudaStream_t s, int row0 = 0, int row1 = -1) {
     int rc = check_shapes(src, dst, pixfmt);
     if (rc) return rc;
     if (nx <= 0 || ny <= 0 || !kx || !ky) return ZB_ERR_INVALID_ARGUMENT;
     if (border < ZB_BORDER_ZERO || border > ZB_BORDER_WRAP) return ZB_ERR_INVALID_ARGUMENT;
     if (src->rows == 0 || src->cols == 0) return ZB_OK;
+    if (row1 < 0 || row1 > (int)src->rows) row1 = (int)src->rows;
+    if (row0 < 0 || row0 > row1) return ZB_ERR_INVALID_ARGUMENT;
+    if (row0 == row1) return ZB_OK;
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     if (pixfmt == ZB_PIX_RGBAF32 && !g_force_generic.load()) {
-        rc = conv_separable_fused_rgbaf32(src, dst, kx, nx, ky, ny, border, g_exact_f32.load() != 0, s);
+        rc = conv_separable_fused_rgbaf32(src, dst, kx, nx, ky, ny, border, g_exact_f32.load() != 0, s, row0, row1);
         if (rc != ZB_ERR_UNSUPPORTED) return rc;
     }
     if (pixfmt == ZB_PIX_RGBA8 && !g_force_generic.load()) {
-        rc = conv_separable_fused_rgba8(src, dst, kx, nx, ky, ny, border, s);
+        rc = conv_separable_fused_rgba8(src, dst, kx, nx, ky, ny, border, s, row0, row1);
         if (rc != ZB_ERR_UNSUPPORTED) return rc;
     }
-    return conv_separable_generic(src, dst, pixfmt, kx, nx, ky, ny, border, s);
+    if (row0 == 0 && row1 == (int)src->rows) return conv_separable_generic(src, dst, pixfmt, kx, nx, ky, ny, border, s);
+    // two-pass path: it has no row window, so convolve into scratch and keep the requested rows
+    const size_t pb = pixel_bytes(pixfmt);
+    Scratch tmp;
+    if ((rc = tmp.alloc((size_t)src->rows * src->cols * pb, s))) return rc;
+    zb_image full{tmp.p, src->rows, src->cols, src->cols};
+    if ((rc = conv_separable_generic(src, &full, pixfmt, kx, nx, ky, ny, border, s))) return rc;
+    ZB_CUDA(cudaMemcpy2DAsync((char*)dst->data + (size_t)row0 * dst->stride * pb, dst->stride * pb, (char*)tmp.p + (size_t)row0 * src->cols * pb,
+                              (size_t)src->cols * pb, (size_t)src->cols * pb, (size_t)(row1 - row0), cudaMemcpyDeviceToDevice, s));
+    return ZB_OK;
 }
 
 // image.zig:972-990
@@ -179,6 +192,15 @@ int zb_gaussian_taps(float sigma, float* taps, int cap, int* n) {
 int zb_conv_separable(const zb_image* src, zb_image* dst, int pixfmt, const float* kx, int nx, const float* ky, int ny, int border,
                       zb_stream s) {
     return conv_separable_dispatch(src, dst, pixfmt, kx, nx, ky, ny, border, (cudaStream_t)s);
+}
+
+int zb_conv_separable_rows(const zb_image* src, zb_image* dst, int pixfmt, const float* kx, int nx, const float* ky, int ny, int border,
+                           uint32_t row_begin, uint32_t row_end, zb_stream s) {
+    if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
+    if (row_end == 0 || row_end > src->rows) row_end = src->rows;
+    if (row_begin > row_end) return ZB_ERR_INVALID_ARGUMENT;
+    if (src->data == dst->data) return ZB_ERR_INVALID_ARGUMENT;   // a row window of an in-place convolution would read rows already overwritten
+    return conv_separable_dispatch(src, dst, pixfmt, kx, nx, ky, ny, border, (cudaStream_t)s, (int)row_begin, (int)row_end);
 }
 
 int zb_convolve(const zb_image* src, zb_image* dst, int pixfmt, const float* kernel, int kh, int kw, int border, zb_stream s) {

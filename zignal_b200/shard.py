@@ -48,6 +48,98 @@ class RowBlock:
     def interior_image(self) -> Image:
         return Image(self.t.reshape(-1), self.pixfmt, self.rows, self.cols, self.cols, self.halo * self.cols)
 
+    # -- overlapped convolution: exchange in flight while the halo-independent rows are computed -------
+    def neighbours(self, border: BorderMode):
+        """(up, down) ranks of this block, None at a global image edge (wrap closes the ring)."""
+        wrap = BorderMode(border) == BorderMode.WRAP
+        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if wrap else None)
+        down = self.rank + 1 if self.rank < self.world - 1 else (0 if wrap else None)
+        return up, down
+
+    def conv_plan(self, half: int, border: BorderMode):
+        """Row bookkeeping of the overlapped schedule.  Returns (view_lo, view_hi, steps): the op runs on the VIEW
+        rows [view_lo, view_hi) of the extended block -- a halo that lies beyond a global image edge is left out of the
+        view, so the kernel's own border handling produces the true edge (no halo fill needed) -- and `steps` is a list of
+        (row_begin, row_end, needs_halo) output windows in VIEW coordinates: first the rows that read no halo row,
+        then the (at most two) strips of `half` rows next to a neighbour."""
+        h, n = self.halo, self.rows
+        if self.world == 1 and (BorderMode(border) != BorderMode.WRAP or h == 0):
+            return h, n + h, [(0, n, False)]           # the whole image is local: one plain call on the interior
+        assert h >= half, "halo must cover the kernel half-width"
+        if self.world > 1 or BorderMode(border) == BorderMode.WRAP:
+            up, down = self.neighbours(border) if self.world > 1 else (0, 0)
+        else:
+            up, down = None, None
+        lo = 0 if up is not None else h
+        hi = n + 2 * h if down is not None else n + h
+        first, last = h - lo, h - lo + n              # interior rows in view coordinates
+        a = first + (half if up is not None else 0)
+        b = last - (half if down is not None else 0)
+        steps = []
+        if b > a:
+            steps.append((a, b, False))
+        else:                                          # block shorter than the kernel: everything waits for the halo
+            a = b = first
+        if up is not None and a > first:
+            steps.append((first, a, True))
+        if down is not None and last > max(b, first):
+            steps.append((max(b, a), last, True))
+        if not steps:
+            steps.append((first, last, up is not None or down is not None))
+        return lo, hi, steps
+
+    def post_halo_exchange(self, border: BorderMode = BorderMode.MIRROR):
+        """Post the neighbour sends / receives and return the requests (empty without neighbours)."""
+        h, n = self.halo, self.rows
+        if h == 0 or self.world == 1:
+            return []
+        assert n > h, "row block must be taller than the halo"
+        t = self.t
+        dist = _dist()
+        up, down = self.neighbours(border)
+        ops = []
+        if up is not None:
+            ops.append(dist.P2POp(dist.isend, t[h:2 * h], up))
+        if down is not None:
+            ops.append(dist.P2POp(dist.irecv, t[n + h:n + 2 * h], down))
+            ops.append(dist.P2POp(dist.isend, t[n:n + h], down))
+        if up is not None:
+            ops.append(dist.P2POp(dist.irecv, t[0:h], up))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def conv_separable(self, out: "RowBlock", kx, ky, border: BorderMode = BorderMode.MIRROR, stream=None):
+        """Image.convolveSeparable on the global image this block belongs to (interior rows of `out` receive the result).
+        One exchange (NCCL isend/irecv of `halo` rows per neighbour) overlapped with the convolution of every row that
+        does not read a halo; the 2 x half boundary rows follow once the halos have landed."""
+        from . import _ffi
+        from .image import _fptr, current_stream
+        import ctypes as C
+        kx = np.ascontiguousarray(kx, dtype=np.float32)
+        ky = np.ascontiguousarray(ky, dtype=np.float32)
+        half = max(kx.size, ky.size) // 2
+        if self.world == 1 and BorderMode(border) == BorderMode.WRAP and self.halo:
+            self.exchange_halo(border)                 # single rank, wrap: local copy into the halos
+        lo, hi, steps = self.conv_plan(half, border)
+        cols = self.cols
+        src = Image(self.t.reshape(-1), self.pixfmt, hi - lo, cols, cols, lo * cols)
+        dst = Image(out.t.reshape(-1), out.pixfmt, hi - lo, cols, cols, lo * cols)
+        a, d = src._zb(), dst._zb()
+        L = _ffi.lib()
+        st = stream if stream is not None else current_stream()
+        reqs = self.post_halo_exchange(border)
+        waited = False
+        for (r0, r1, needs_halo) in steps:
+            if needs_halo and not waited:
+                for r in reqs:
+                    r.wait()                           # the compute stream waits for the exchange; the host does not block
+                waited = True
+            _ffi.check(L.zb_conv_separable_rows(a, d, int(self.pixfmt), _fptr(kx), kx.size, _fptr(ky), ky.size, int(border),
+                                                C.c_uint32(r0), C.c_uint32(r1), st))
+        if not waited:
+            for r in reqs:
+                r.wait()
+        return out
+
     # -- the one exchange step of the convolution path ------------------------------------------------
     def exchange_halo(self, border: BorderMode = BorderMode.MIRROR):
         h, n = self.halo, self.rows

@@ -205,6 +205,10 @@ int zb_fdm_moments(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums1
 /* Install externally reduced moments (multi-GPU: after the all-reduce) as target / source statistics. */
 int zb_fdm_set_target_moments(zb_fdm* f, const uint64_t* sums11);
 int zb_fdm_update_with_moments(zb_fdm* f, const uint64_t* source_sums11, zb_stream s);
+/* zb_fdm_update queues its three kernels (moments, the 3x3 solve, the map) on the stream and returns; the solve's result
+ * (0, or ZB_ERR_NOT_CONVERGED = error.SvdFailed, fdm.zig:216) stays on the device.  This call waits for the stream and
+ * returns it. */
+int zb_fdm_status(zb_fdm* f, zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-pointer twins (H2D + op + D2H inside the call; returns when dst is valid on the host).

@@ -24,6 +24,7 @@ def _fdm(zb, src, tgt):
     s = zb.Image.from_numpy(src)
     t = zb.Image.from_numpy(tgt)
     f.match(s, t)
+    f.status()          # the 3x3 solve runs on the device; this waits and raises SvdFailed if it did not converge
     out = s.to_numpy()
     f.deinit()
     return out
@@ -118,6 +119,28 @@ def test_fdm_gray_target_branch_and_reuse(zb):
         assert np.abs(d.to_numpy().astype(int) - zo.fdm_match(s3, t3).astype(int)).max() <= 1
     f.deinit()
     assert np.abs(zb.fdm.host_match(src[..., :3].copy(), tgt[..., :3].copy()).astype(int) - zo.fdm_match(src[..., :3].copy(), tgt[..., :3].copy()).astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4])
+def test_fdm_tail_pixels_and_unaligned_row_views(zb, ch):
+    """The kernels work on 4-pixel word groups: a pixel count that is not a multiple of 4 (byte-wise tail) and a full-width row
+    view that starts on an odd byte (Rgb: 3 * 311 bytes per row) must give what the oracle gives for that view."""
+    from zignal_b200.fdm import FeatureDistributionMatching
+    rng = np.random.default_rng(40 + ch)
+    shape = (63, 311) + ((ch,) if ch > 1 else ())
+    base = rand_image(rng, shape, np.uint8)
+    tgt = (rand_image(rng, shape, np.uint8) // 3 + 90).astype(np.uint8)
+    for r0, r1 in ((0, 63), (1, 62), (3, 8)):
+        dev = zb.Image.from_numpy(base.copy())
+        view = dev.view(zb.Rectangle(0, r0, 311, r1))
+        f = FeatureDistributionMatching(dev.pixfmt)
+        f.match(view, zb.Image.from_numpy(tgt))
+        f.status()
+        got = dev.to_numpy()
+        f.deinit()
+        want = zo.fdm_match(np.ascontiguousarray(base[r0:r1]), tgt)
+        assert np.abs(got[r0:r1].astype(int) - want.astype(int)).max() <= 1, (r0, r1)
+        assert np.array_equal(got[:r0], base[:r0]) and np.array_equal(got[r1:], base[r1:])   # rows outside the view untouched
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-6), (np.float64, 1e-12)])

@@ -141,3 +141,38 @@ def test_overlapped_conv_plan(world, border):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(a and b and c for _, a, b, c in res), res
+
+
+def _cov_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zignal_b200 import shard
+        rng = np.random.default_rng(9)
+        x = (rng.standard_normal((301, 12)) * np.arange(1, 13) + 3.0).astype(np.float32)
+        lo, hi = shard.split_batch(x.shape[0], rank, world)
+        mean, cov = shard.sharded_covariance(torch.from_numpy(x[lo:hi]), gram_fn=lambda c: c.double().T @ c.double(),
+                                             center_fn=lambda a, m: a - m)
+        xc = x.astype(np.float64) - x.astype(np.float64).mean(axis=0)
+        want = xc.T @ xc / (x.shape[0] - 1)
+        ok_mean = bool(np.allclose(mean.numpy(), x.astype(np.float64).mean(axis=0), rtol=1e-6, atol=1e-6))
+        ok_cov = bool(np.abs(cov.numpy() - want).max() <= 1e-5 * np.abs(want).max())
+        q.put((rank, ok_mean, ok_cov))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_covariance_allreduce():
+    """PCA covariance with samples split over ranks: all-reduce of column sums, then of the dim x dim partial products."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cov_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for _, a, b in res), res

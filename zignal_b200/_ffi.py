@@ -105,6 +105,7 @@ def _declare(L):
         "zb_fdm_set_target": ([vp, img, vp], i),
         "zb_fdm_set_source": ([vp, img], i),
         "zb_fdm_update": ([vp, vp], i),
+        "zb_fdm_status": ([vp, vp], i),
         "zb_fdm_match": ([vp, img, img, vp], i),
         "zb_fdm_moments": ([img, i, i, P(u64), vp], i),
         "zb_fdm_set_target_moments": ([vp, P(u64)], i),

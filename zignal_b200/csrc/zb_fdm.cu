@@ -3,11 +3,14 @@
 // The reference makes two sequential full passes per image: a Welford mean/co-moment stream
 // (stats.zig:261-280, a ~10-flop dependency chain per pixel) and the per-pixel affine colour map.
 // Here the statistics pass is a parallel reduction of EXACT integer moments of the u8 pixels
-// (n, sum x_i, sum x_i x_j as u64; integer atomics, so the result is order-independent), finished on
-// the host in f64: cov_ij = (n*Sij - Si*Sj) / (n (n-1) 255^2) with the numerator exact in 128 bits.
+// (n, sum x_i, sum x_i x_j as u64; integer atomics, so the result is order-independent), finished in
+// f64: cov_ij = (n*Sij - Si*Sj) / (n (n-1) 255^2) with the numerator exact in 128 bits.
 // That differs from Welford only by Welford's own rounding noise (~1e-16 relative).  The 3x3 SVDs,
-// W = Us * diag(sqrt(lt/ls)) * Ut^T and the bias follow fdm.zig:199-254 verbatim (host, f64); the map
-// (fdm.zig:257-271) is one f64 kernel: res = r*w0 + g*w1 + b*w2 + bias, round(255*clamp(res,0,1)).
+// W = Us * diag(sqrt(lt/ls)) * Ut^T and the bias follow fdm.zig:199-254 verbatim in f64.  For `update` that
+// small solve runs ON THE DEVICE in a one-thread kernel between the two passes (same source as the host
+// version, zb_svd_core.h: + - * / sqrt only, so the bits are the same) -- no device-to-host round trip, the
+// three kernels are simply queued on the stream.  The map (fdm.zig:257-271) is one f64 kernel:
+// res = r*w0 + g*w1 + b*w2 + bias, round(255*clamp(res,0,1)).
 // The 11 moment sums are also the quantities one all-reduce combines when an image is sharded
 // across GPUs (zb_fdm_moments / zb_fdm_update_with_moments).
 #include <cmath>
@@ -16,6 +19,14 @@
 #include "zb_host_stage.h"
 #include "zb_internal.h"
 #include "zb_linalg.h"
+#include "zb_svd_core.h"
+
+struct FdmTarget {   // what `update` needs from the target (fdm.zig:92-121)
+    double mean[3];
+    double u[9];
+    double s[3];
+    int is_gray;
+};
 
 struct zb_fdm {
     int pixfmt;
@@ -25,6 +36,10 @@ struct zb_fdm {
     bool target_is_gray;
     bool has_target, has_source;
     zb_image source;
+    // device side of `update`: the 11 moment sums, the solved map parameters, a status word (0 or ZB_ERR_NOT_CONVERGED)
+    unsigned long long* d_m;
+    void* d_params;
+    int* d_status;
 };
 
 namespace zb {
@@ -36,6 +51,34 @@ __device__ __forceinline__ unsigned rgb_to_gray(unsigned r, unsigned g, unsigned
     return (unsigned)min(max(y, 0), 255);
 }
 
+// 4 consecutive pixels as CH 32-bit words (the image base is 4-byte aligned and 4 pixels are 4*CH bytes), unpacked to bytes
+template <int CH>
+__device__ __forceinline__ void load_group(const uint8_t* __restrict__ img, size_t group, uint8_t (&b)[4 * CH]) {
+    if (((uintptr_t)img & 3u) == 0) {   // (uniform) always true for whole images; a row-offset view of Rgb pixels may not be
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + group * CH;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const uint32_t v = __ldg(w + i);
+            b[4 * i] = (uint8_t)v; b[4 * i + 1] = (uint8_t)(v >> 8); b[4 * i + 2] = (uint8_t)(v >> 16); b[4 * i + 3] = (uint8_t)(v >> 24);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 * CH; ++i) b[i] = img[group * (4 * CH) + i];
+    }
+}
+template <int CH>
+__device__ __forceinline__ void store_group(uint8_t* __restrict__ img, size_t group, const uint8_t (&b)[4 * CH]) {
+    if (((uintptr_t)img & 3u) == 0) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(img) + group * CH;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            w[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 * CH; ++i) img[group * (4 * CH) + i] = b[i];
+    }
+}
+
 // sums: {n, Sr, Sg, Sb, Srr, Srg, Srb, Sgg, Sgb, Sbb, non_gray}
 template <int CH>
 __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict__ img, size_t n_px, int as_luma,
@@ -44,29 +87,80 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
 #pragma unroll
     for (int i = 0; i < 11; ++i) acc[i] = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < n_px; base += stride * 16) {
+    const size_t n_groups = n_px / 4;   // whole 4-pixel groups; the tail (< 4 pixels) is taken by one thread below
+    auto add_px = [&](unsigned (&a)[11], unsigned r, unsigned g, unsigned b) {
+        if (CH != 1 && (r != g || g != b)) a[10] += 1;
+        if (CH != 1 && as_luma) r = g = b = rgb_to_gray(r, g, b);
+        a[0] += 1;
+        a[1] += r; a[2] += g; a[3] += b;
+        a[4] += r * r; a[5] += r * g; a[6] += r * b;
+        a[7] += g * g; a[8] += g * b; a[9] += b * b;
+    };
+    if (!as_luma && ((uintptr_t)img & 3u) == 0) {
+        // packed path: the 4 pixels of a group are transposed into one word per channel (byte permutes) and every moment of the
+        // group is one dot product (dp4a): 6 PRMT + 9 DP4A for 4 pixels instead of ~40 scalar operations per pixel
+        unsigned a[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) a[i] = 0;
+        int pending = 0;
+#pragma unroll 4
+        for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < n_groups; grp += stride) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + grp * CH;
+            uint32_t R, G, B;
+            if constexpr (CH == 1) {
+                R = G = B = __ldg(w);
+            } else if constexpr (CH == 3) {
+                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+                R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);              // r0 r1 r2 . -> r0 r1 r2 r3
+                G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);              // g0 g1 g2 g3
+                B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);              // b0 b1 . . -> b0 b1 b2 b3
+            } else {
+                const uint4 q = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));   // r g b a per word (base is only 4-byte aligned)
+                const uint32_t rg01 = __byte_perm(q.x, q.y, 0x5140), rg23 = __byte_perm(q.z, q.w, 0x5140);   // r0 r1 g0 g1 | r2 r3 g2 g3
+                R = __byte_perm(rg01, rg23, 0x5410);
+                G = __byte_perm(rg01, rg23, 0x7632);
+                B = __byte_perm(__byte_perm(q.x, q.y, 0x0062), __byte_perm(q.z, q.w, 0x0062), 0x5410);
+            }
+            a[0] += 4;
+            a[1] = __dp4a(R, 0x01010101u, a[1]); a[2] = __dp4a(G, 0x01010101u, a[2]); a[3] = __dp4a(B, 0x01010101u, a[3]);
+            a[4] = __dp4a(R, R, a[4]); a[5] = __dp4a(R, G, a[5]); a[6] = __dp4a(R, B, a[6]);
+            a[7] = __dp4a(G, G, a[7]); a[8] = __dp4a(G, B, a[8]); a[9] = __dp4a(B, B, a[9]);
+            if (CH != 1) a[10] = __dp4a(__vsetne4((R ^ G) | (G ^ B), 0u), 0x01010101u, a[10]);   // pixels with r != g or g != b
+            if (++pending == 4096) {   // 16384 pixels: 16384 * 255^2 < 2^32, flush before the u32 sums can wrap
+#pragma unroll
+                for (int i = 0; i < 11; ++i) { acc[i] += a[i]; a[i] = 0; }
+                pending = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 11; ++i) acc[i] += a[i];
+    } else
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < n_groups; base += stride * 4) {
         unsigned a[11];  // 16 pixels: sums of products <= 16*255^2 fit easily in u32
 #pragma unroll
         for (int i = 0; i < 11; ++i) a[i] = 0;
-#pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-            const size_t px = base + (size_t)j * stride;
-            if (px >= n_px) break;
-            unsigned r, g, b;
-            if constexpr (CH == 1) {
-                r = g = b = img[px];
-            } else if constexpr (CH == 4) {
-                const uchar4 q = reinterpret_cast<const uchar4*>(img)[px];
-                r = q.x; g = q.y; b = q.z;
-            } else {
-                r = img[px * 3]; g = img[px * 3 + 1]; b = img[px * 3 + 2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t grp = base + (size_t)j * stride;
+            if (grp >= n_groups) break;
+            uint8_t b[4 * CH];
+            load_group<CH>(img, grp, b);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if constexpr (CH == 1) add_px(a, b[q], b[q], b[q]);
+                else add_px(a, b[q * CH], b[q * CH + 1], b[q * CH + 2]);
             }
-            if (CH != 1 && (r != g || g != b)) a[10] += 1;
-            if (CH != 1 && as_luma) r = g = b = rgb_to_gray(r, g, b);
-            a[0] += 1;
-            a[1] += r; a[2] += g; a[3] += b;
-            a[4] += r * r; a[5] += r * g; a[6] += r * b;
-            a[7] += g * g; a[8] += g * b; a[9] += b * b;
+        }
+#pragma unroll
+        for (int i = 0; i < 11; ++i) acc[i] += a[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned a[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) a[i] = 0;
+        for (size_t px = n_groups * 4; px < n_px; ++px) {
+            if constexpr (CH == 1) add_px(a, img[px], img[px], img[px]);
+            else add_px(a, img[px * CH], img[px * CH + 1], img[px * CH + 2]);
         }
 #pragma unroll
         for (int i = 0; i < 11; ++i) acc[i] += a[i];
@@ -89,37 +183,111 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
 }
 
 struct MapParams {
+    float wf[9], wa[9], bf[3], ba[3];   // f32 fast path of the colour map: weights, |weights|, 255*bias + 1/2, |that| + 1
     double w[9];
     double bias[3];
     double scale, offset;  // gray branch
     int mode;              // 0 colour (fdm.zig:257-271), 1 scalar on u8 (:185-189), 2 gray target on colour source (:191-197)
 };
 
+// round(255 * clamp(res, 0, 1)) (fdm.zig:262-270).  255 * clamp(res) and 255 * res agree wherever the clamp is idle, and outside
+// it both round to something the integer clamp maps to the same 0 / 255; round-half-away of x is trunc(x) + (x - trunc(x) >= 1/2)
+// for x >= 0 and anything <= 0 for x < 0.
+__device__ __forceinline__ uint8_t quantize01(double res) {
+    const double x = 255.0 * res;
+    const int t = __double2int_rz(x);               // saturates far outside the range
+    const int r = t + ((x - (double)t) >= 0.5 ? 1 : 0);
+    return (uint8_t)min(max(r, 0), 255);
+}
+
+// fdm.zig:257-271 for one output channel: f64, the reference's operation order.  Out of line on purpose: it runs for a few values
+// in 10^4 and must not be speculated into the fast path.
+__device__ __noinline__ uint8_t fdm_exact_channel(int r, int g, int b, int j, const MapParams* __restrict__ p) {
+    const double rr = (double)r / 255.0, gg = (double)g / 255.0, bb = (double)b / 255.0;
+    return quantize01(rr * p->w[j] + gg * p->w[3 + j] + bb * p->w[6 + j] + p->bias[j]);
+}
+
+// A thread maps 4 consecutive pixels (4*CH bytes as CH aligned words).
+//
+// FP64 is the scarce resource here (64 lanes/clk/SM): the reference's 9 multiplies, 9 adds, 3 divisions and 3 roundings per pixel
+// in f64 bound the kernel at ~5x the memory time.  So every output is first evaluated in f32 together with a rigorous bound on
+// |x32 - x64| (4 roundings of 2^-24 on the sum of absolute terms, doubled for slack); when x32 is farther than that bound from
+// every rounding boundary k + 1/2, the f64 value rounds to the same integer and the f32 result IS the reference's.  Otherwise
+// (a few pixels in 10^4) the output is recomputed with the reference's exact f64 sequence.  Gray maps are 256-entry byte tables
+// built with that same f64 sequence.
 template <int CH>
-__global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img, size_t n_px, MapParams p) {
-    const size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (px >= n_px) return;
-    if constexpr (CH == 1) {
-        const double val = (double)img[px] / 255.0;
-        const double result = fmax(0.0, fmin(val * p.scale + p.offset, 1.0));
-        img[px] = (uint8_t)round(255.0 * result);
-    } else {
-        uint8_t* q = img + px * CH;
-        if (p.mode == 2) {
-            const double val = (double)rgb_to_gray(q[0], q[1], q[2]) / 255.0;
-            const double result = fmax(0.0, fmin(val * p.scale + p.offset, 1.0));
-            const uint8_t res = (uint8_t)round(255.0 * result);
-            q[0] = res; q[1] = res; q[2] = res;
-            if (CH == 4) q[3] = 0;  // `.{ .r, .g, .b }`: alpha takes its default 0 (color.zig:405, fdm.zig:196)
+__global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img, size_t n_px, const MapParams* __restrict__ pp) {
+    __shared__ uint8_t gray_lut[256];
+    __shared__ MapParams sp;   // one copy per block instead of ~30 global loads per thread
+    if (threadIdx.x < sizeof(MapParams) / 4) reinterpret_cast<uint32_t*>(&sp)[threadIdx.x] = reinterpret_cast<const uint32_t*>(pp)[threadIdx.x];
+    __syncthreads();
+    const MapParams& p = sp;
+    const int mode = CH == 1 ? 1 : p.mode;
+    if (mode != 0) {
+        gray_lut[threadIdx.x] = quantize01(((double)threadIdx.x / 255.0) * p.scale + p.offset);
+        __syncthreads();
+    }
+    // f32 copies of the colour map, pre-scaled to the 0..255 domain: x_j = r*w0j + g*w1j + b*w2j + 255*bias_j
+    float wf[9], wa[9], bf[3], ba[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { wf[i] = p.wf[i]; wa[i] = p.wa[i]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { bf[j] = p.bf[j]; ba[j] = p.ba[j]; }
+    // maps one pixel in place; returns a 3-bit mask of the channels whose f32 value sits too close to a rounding boundary
+    auto map_px = [&](uint8_t* q) -> unsigned {
+        if constexpr (CH == 1) {
+            q[0] = gray_lut[q[0]];
+            return 0u;
         } else {
-            const double r = (double)q[0] / 255.0, g = (double)q[1] / 255.0, b = (double)q[2] / 255.0;
-            const double res0 = r * p.w[0] + g * p.w[3] + b * p.w[6] + p.bias[0];
-            const double res1 = r * p.w[1] + g * p.w[4] + b * p.w[7] + p.bias[1];
-            const double res2 = r * p.w[2] + g * p.w[5] + b * p.w[8] + p.bias[2];
-            q[0] = (uint8_t)round(255.0 * fmax(0.0, fmin(res0, 1.0)));
-            q[1] = (uint8_t)round(255.0 * fmax(0.0, fmin(res1, 1.0)));
-            q[2] = (uint8_t)round(255.0 * fmax(0.0, fmin(res2, 1.0)));
+            if (mode == 2) {
+                const uint8_t res = gray_lut[rgb_to_gray(q[0], q[1], q[2])];
+                q[0] = res; q[1] = res; q[2] = res;
+                if (CH == 4) q[3] = 0;  // `.{ .r, .g, .b }`: alpha takes its default 0 (color.zig:405, fdm.zig:196)
+                return 0u;
+            }
+            const float rf = (float)q[0], gf = (float)q[1], bfl = (float)q[2];
+            unsigned bad = 0;
+            uint8_t out[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float y = fmaf(bfl, wf[6 + j], fmaf(gf, wf[3 + j], fmaf(rf, wf[j], bf[j])));   // ~ 255*res + 1/2
+                const float m = fmaf(bfl, wa[6 + j], fmaf(gf, wa[3 + j], fmaf(rf, wa[j], ba[j])));   // sum of |terms| (+1)
+                const float fl = floorf(y);
+                const float d = y - fl;                       // distance above the boundary below
+                const float e = m * 9.6e-7f;                  // 16 * 2^-24 * m  >=  |y32 - y64| with 2x slack
+                bad |= (d > e && d < 1.0f - e) ? 0u : (1u << j);
+                out[j] = (uint8_t)fminf(fmaxf(fl, 0.0f), 255.0f);
+            }
+            if (bad) {   // rare: keep the source values, the caller recomputes those channels exactly
+                return bad | 8u;
+            }
+            q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+            return 0u;
         }
+    };
+    auto fix_px = [&](uint8_t* q) {   // exact f64 recomputation of a whole pixel (all three channels read the ORIGINAL r, g, b)
+        const int r = q[0], g = q[1], b = q[2];
+        q[0] = fdm_exact_channel(r, g, b, 0, pp);
+        q[1] = fdm_exact_channel(r, g, b, 1, pp);
+        q[2] = fdm_exact_channel(r, g, b, 2, pp);
+    };
+    const size_t n_groups = n_px / 4;
+    const size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp < n_groups) {
+        uint8_t b[4 * CH];
+        load_group<CH>(img, grp, b);
+        unsigned redo = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) redo |= (map_px(b + q * CH) ? 1u : 0u) << q;
+        if (redo) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (redo & (1u << q)) fix_px(b + q * CH);
+        }
+        store_group<CH>(img, grp, b);
+    } else if (grp == n_groups) {   // the tail (< 4 pixels), byte by byte
+        for (size_t px = n_groups * 4; px < n_px; ++px)
+            if (map_px(img + px * CH)) fix_px(img + px * CH);
     }
 }
 
@@ -151,26 +319,86 @@ int moments_device(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums1
 }
 
 // mean (stats.zig:283-286) and unbiased covariance (:301-320) of x/255 from the integer moments
-void stats_from_moments(const uint64_t* m, double mean[3], double cov[9]) {
+ZB_HD inline double i128_to_double(__int128 v) {   // two roundings at most 2^-53 relative each; no library call on the device
+    const bool neg = v < 0;
+    const unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    const double d = (double)(unsigned long long)(a >> 64) * 18446744073709551616.0 + (double)(unsigned long long)a;
+    return neg ? -d : d;
+}
+ZB_HD inline void stats_from_moments(const unsigned long long* m, double mean[3], double cov[9]) {
     const double n = (double)m[0];
     for (int i = 0; i < 3; ++i) mean[i] = m[0] ? ((double)m[1 + i] / n) / 255.0 : 0.0;
     for (int i = 0; i < 9; ++i) cov[i] = 0.0;
     if (m[0] <= 1) return;
-    static const int idx[3][3] = {{4, 5, 6}, {5, 7, 8}, {6, 8, 9}};
-    const long double denom = (long double)m[0] * (long double)(m[0] - 1) * 65025.0L;
+    const int idx[3][3] = {{4, 5, 6}, {5, 7, 8}, {6, 8, 9}};
+    const double denom = i128_to_double((__int128)m[0] * (__int128)(m[0] - 1) * 65025);
     for (int i = 0; i < 3; ++i)
         for (int j = i; j < 3; ++j) {
             const __int128 num = (__int128)m[0] * (__int128)m[idx[i][j]] - (__int128)m[1 + i] * (__int128)m[1 + j];
-            const double c = (double)((long double)num / denom);
+            const double c = i128_to_double(num) / denom;
             cov[i * 3 + j] = c;
             cov[j * 3 + i] = c;
         }
 }
 
+// scalar 3x3 product in the reference's gemm order (Matrix.zig:806-817: 27 ops < 512 -> scalar path)
+ZB_HD inline void matmul3(const double* a, const double* b, double* out) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += a[i * 3 + k] * b[k * 3 + j];
+            out[i * 3 + j] = 0.0 + 1.0 * acc;
+        }
+}
+
+// fdm.zig:174-254: the map parameters from the source moments and the target statistics
+ZB_HD inline int fdm_solve(const unsigned long long* m, const FdmTarget& t, int pixfmt, MapParams& p) {
+    double source_mean[3], scov[9];
+    stats_from_moments(m, source_mean, scov);
+    for (int i = 0; i < 9; ++i) p.w[i] = 0;
+    for (int i = 0; i < 3; ++i) p.bias[i] = 0;
+    p.scale = 1.0;
+    p.offset = 0.0;
+    if (pixfmt == ZB_PIX_U8 || t.is_gray) {  // :177-198
+        const double source_var = scov[0];
+        p.scale = source_var > 1e-10 ? sqrt(t.s[0] / source_var) : 1.0;
+        p.offset = t.mean[0] - source_mean[0] * p.scale;
+        p.mode = pixfmt == ZB_PIX_U8 ? 1 : 2;
+        return ZB_OK;
+    }
+    double us[9], ss[3], v[9], e[3];   // :199-254
+    if (svd_gr_core<double>(scov, 3, 3, ZB_SVD_SKINNY_U, false, us, 3, ss, v, e) != 0) return ZB_ERR_NOT_CONVERGED;
+    double sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 3; ++i)
+        if (ss[i] > 1e-10) sigma[i * 3 + i] = sqrt(t.s[i] / ss[i]);
+    double ut_t[9], w_temp[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) ut_t[i * 3 + j] = t.u[j * 3 + i];
+    matmul3(us, sigma, w_temp);
+    matmul3(w_temp, ut_t, p.w);
+    for (int j = 0; j < 3; ++j) {
+        double sum = 0;
+        for (int k = 0; k < 3; ++k) sum += source_mean[k] * p.w[k * 3 + j];
+        p.bias[j] = t.mean[j] - sum;
+    }
+    p.mode = 0;
+    return ZB_OK;
+}
+
+__global__ void fdm_solve_kernel(const unsigned long long* __restrict__ m, FdmTarget t, int pixfmt, MapParams* __restrict__ out,
+                                 int* __restrict__ status) {
+    MapParams p;
+    const int rc = fdm_solve(m, t, pixfmt, p);
+    for (int i = 0; i < 9; ++i) { p.wf[i] = (float)p.w[i]; p.wa[i] = fabsf(p.wf[i]); }
+    for (int j = 0; j < 3; ++j) { p.bf[j] = (float)(255.0 * p.bias[j]) + 0.5f; p.ba[j] = fabsf(p.bf[j]) + 1.0f; }
+    *out = p;
+    *status = rc;
+}
+
 // fdm.zig:92-121
 int set_target_from_moments(zb_fdm* f, const uint64_t* m) {
     double cov[9];
-    stats_from_moments(m, f->target_mean, cov);
+    stats_from_moments((const unsigned long long*)m, f->target_mean, cov);
     f->target_is_gray = (f->pixfmt == ZB_PIX_U8) || (m[10] == 0);
     memset(f->target_u, 0, sizeof(f->target_u));
     f->target_s[0] = f->target_s[1] = f->target_s[2] = 0;
@@ -184,54 +412,55 @@ int set_target_from_moments(zb_fdm* f, const uint64_t* m) {
     return ZB_OK;
 }
 
-// scalar 3x3 product in the reference's gemm order (Matrix.zig:806-817: 27 ops < 512 -> scalar path)
-void matmul3(const double* a, const double* b, double* out) {
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double acc = 0;
-            for (int k = 0; k < 3; ++k) acc += a[i * 3 + k] * b[k * 3 + j];
-            out[i * 3 + j] = 0.0 + 1.0 * acc;
-        }
+int ensure_device_state(zb_fdm* f) {
+    if (f->d_m) return ZB_OK;
+    ZB_CUDA(cudaMalloc(&f->d_m, 11 * sizeof(unsigned long long)));
+    ZB_CUDA(cudaMalloc(&f->d_params, sizeof(MapParams)));
+    ZB_CUDA(cudaMalloc(&f->d_status, sizeof(int)));
+    ZB_CUDA(cudaMemset(f->d_status, 0, sizeof(int)));
+    return ZB_OK;
 }
 
-// fdm.zig:174-272 given the source moments
-int update_from_moments(zb_fdm* f, const uint64_t* m, cudaStream_t s) {
-    double source_mean[3], scov[9];
-    stats_from_moments(m, source_mean, scov);
-    MapParams p;
-    memset(&p, 0, sizeof(p));
-    const int ch = channels_of(f->pixfmt);
-    if (f->pixfmt == ZB_PIX_U8 || f->target_is_gray) {  // :177-198
-        const double source_var = scov[0];
-        p.scale = source_var > 1e-10 ? std::sqrt(f->target_s[0] / source_var) : 1.0;
-        p.offset = f->target_mean[0] - source_mean[0] * p.scale;
-        p.mode = f->pixfmt == ZB_PIX_U8 ? 1 : 2;
-    } else {  // :199-254
-        double us[9], ss[3], v[9];
-        if (svd_golub_reinsch<double>(scov, 3, 3, ZB_SVD_SKINNY_U, false, us, 3, ss, v) != 0) return ZB_ERR_NOT_CONVERGED;
-        double sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 3; ++i)
-            if (ss[i] > 1e-10) sigma[i * 3 + i] = std::sqrt(f->target_s[i] / ss[i]);
-        double ut_t[9], w_temp[9];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) ut_t[i * 3 + j] = f->target_u[j * 3 + i];
-        matmul3(us, sigma, w_temp);
-        matmul3(w_temp, ut_t, p.w);
-        for (int j = 0; j < 3; ++j) {
-            double sum = 0;
-            for (int k = 0; k < 3; ++k) sum += source_mean[k] * p.w[k * 3 + j];
-            p.bias[j] = f->target_mean[j] - sum;
+// queue the moment pass of `img` into f->d_m (no host synchronisation)
+int moments_enqueue(zb_fdm* f, const zb_image* img, int as_luma, cudaStream_t s) {
+    if (img->stride != img->cols) return ZB_ERR_UNSUPPORTED;  // the reference walks image.data linearly (fdm.zig:82)
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if ((rc = ensure_device_state(f))) return rc;
+    const size_t n_px = (size_t)img->rows * img->cols;
+    ZB_CUDA(cudaMemsetAsync(f->d_m, 0, 11 * sizeof(unsigned long long), s));
+    if (n_px > 0) {
+        const unsigned blocks = (unsigned)std::min<size_t>((size_t)di.sm_count * 8, (n_px + 255) / 256);
+        const uint8_t* p = (const uint8_t*)img->data;
+        switch (f->pixfmt) {
+            case ZB_PIX_U8: moments_kernel<1><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
+            case ZB_PIX_RGB8: moments_kernel<3><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
+            default: moments_kernel<4><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
         }
-        p.mode = 0;
+        ZB_LAUNCHED();
     }
+    return ZB_OK;
+}
+
+// fdm.zig:174-272 with the source moments already in f->d_m: solve on the device, then map -- all queued on `s`
+int solve_and_map(zb_fdm* f, cudaStream_t s) {
+    FdmTarget t;
+    memcpy(t.mean, f->target_mean, sizeof(t.mean));
+    memcpy(t.u, f->target_u, sizeof(t.u));
+    memcpy(t.s, f->target_s, sizeof(t.s));
+    t.is_gray = f->target_is_gray ? 1 : 0;
     const size_t n_px = (size_t)f->source.rows * f->source.cols;
     if (n_px == 0) return ZB_OK;
+    MapParams* dp = (MapParams*)f->d_params;
+    fdm_solve_kernel<<<1, 1, 0, s>>>(f->d_m, t, f->pixfmt, dp, f->d_status);
+    ZB_LAUNCHED();
     uint8_t* img = (uint8_t*)f->source.data;
-    const unsigned blocks = div_up(n_px, 256);
-    switch (ch) {
-        case 1: fdm_map_kernel<1><<<blocks, 256, 0, s>>>(img, n_px, p); break;
-        case 3: fdm_map_kernel<3><<<blocks, 256, 0, s>>>(img, n_px, p); break;
-        default: fdm_map_kernel<4><<<blocks, 256, 0, s>>>(img, n_px, p); break;
+    const unsigned blocks = div_up(n_px / 4 + 1, 256);   // one thread per 4-pixel group, one more for the tail
+    switch (channels_of(f->pixfmt)) {
+        case 1: fdm_map_kernel<1><<<blocks, 256, 0, s>>>(img, n_px, dp); break;
+        case 3: fdm_map_kernel<3><<<blocks, 256, 0, s>>>(img, n_px, dp); break;
+        default: fdm_map_kernel<4><<<blocks, 256, 0, s>>>(img, n_px, dp); break;
     }
     ZB_LAUNCHED();
     t_last_kernel = "fdm_map";
@@ -254,7 +483,15 @@ int zb_fdm_create(zb_fdm** out, int pixfmt) {
     *out = f;
     return ZB_OK;
 }
-int zb_fdm_destroy(zb_fdm* f) { delete f; return ZB_OK; }
+int zb_fdm_destroy(zb_fdm* f) {
+    if (f) {
+        if (f->d_m) cudaFree(f->d_m);
+        if (f->d_params) cudaFree(f->d_params);
+        if (f->d_status) cudaFree(f->d_status);
+    }
+    delete f;
+    return ZB_OK;
+}
 
 int zb_fdm_moments(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums11, zb_stream s) {
     return moments_device(img, pixfmt, as_luma, sums11, (cudaStream_t)s);
@@ -288,18 +525,29 @@ int zb_fdm_update_with_moments(zb_fdm* f, const uint64_t* source_sums11, zb_stre
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    return update_from_moments(f, source_sums11, (cudaStream_t)s);
+    if ((rc = ensure_device_state(f))) return rc;
+    // (pageable source: the copy is staged before the call returns, so the caller's array may be reused)
+    ZB_CUDA(cudaMemcpyAsync(f->d_m, source_sums11, 11 * sizeof(unsigned long long), cudaMemcpyHostToDevice, (cudaStream_t)s));
+    return solve_and_map(f, (cudaStream_t)s);
 }
 
 int zb_fdm_update(zb_fdm* f, zb_stream s) {
     if (!f) return ZB_ERR_INVALID_ARGUMENT;
     if (!f->has_target) return ZB_ERR_NO_TARGET_SET;
     if (!f->has_source) return ZB_ERR_NO_SOURCE_SET;
-    uint64_t m[11];
     const int as_luma = (f->pixfmt != ZB_PIX_U8 && f->target_is_gray) ? 1 : 0;  // fdm.zig:155-162
-    int rc = moments_device(&f->source, f->pixfmt, as_luma, m, (cudaStream_t)s);
-    if (rc) return rc;
-    return update_from_moments(f, m, (cudaStream_t)s);
+    int rc = moments_enqueue(f, &f->source, as_luma, (cudaStream_t)s);   // statistics pass, solve and map are queued back to back:
+    if (rc) return rc;                                                    // no device-to-host round trip between them
+    return solve_and_map(f, (cudaStream_t)s);
+}
+
+int zb_fdm_status(zb_fdm* f, zb_stream s) {
+    if (!f) return ZB_ERR_INVALID_ARGUMENT;
+    if (!f->d_status) return ZB_OK;
+    int st = 0;
+    ZB_CUDA(cudaMemcpyAsync(&st, f->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    ZB_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+    return st;
 }
 
 int zb_fdm_match(zb_fdm* f, zb_image* source, const zb_image* target, zb_stream s) {  // fdm.zig:133-137

@@ -31,8 +31,12 @@ class FeatureDistributionMatching:
         s = source._zb()
         check(lib().zb_fdm_set_source(self._h, s))
 
-    def update(self):  # fdm.zig:141 (modifies the source image in place)
+    def update(self):  # fdm.zig:141 (modifies the source image in place; the three kernels are queued, nothing waits)
         check(lib().zb_fdm_update(self._h, current_stream()))
+
+    def status(self):
+        """Wait for the stream and raise SvdFailed if the device-side 3x3 solve of the last update did not converge."""
+        check(lib().zb_fdm_status(self._h, current_stream()))
 
     def match(self, source: Image, target: Image):  # fdm.zig:133
         self.set_target(target)

@@ -204,3 +204,43 @@ def split_batch(n_items: int, rank: int, world: int):
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_covariance(x_local, gram_fn=None, center_fn=None):
+    """PCA's scaled covariance X^T X / (n - 1) (reference pca.zig:135-154,331-338) with the SAMPLES split across ranks
+    (SURVEY 8(e)): one all-reduce of the column sums (dim f64 values + the count) gives the global mean, every rank centres
+    its rows and contracts them on its own GPU (the tcgen05 X^T X kernel), and one all-reduce of the dim x dim partial
+    products finishes the job.  Returns (mean, cov) as tensors on x_local's device, identical on every rank.
+
+    gram_fn(centered) -> centered^T centered and center_fn(x, mean) -> x - mean default to the CUDA library; the host-logic
+    tests pass numpy-backed stand-ins."""
+    import torch
+    dist = _dist()
+    n_local, dim = x_local.shape
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    head = torch.empty(dim + 1, dtype=torch.float64, device=x_local.device)
+    head[:dim] = x_local.sum(dim=0, dtype=torch.float64)
+    head[dim] = float(n_local)
+    if world > 1:
+        dist.all_reduce(head, op=dist.ReduceOp.SUM)
+    n = int(round(float(head[dim].item())))
+    if n < 2:
+        from ._ffi import ZignalError
+        raise ZignalError(12, "InsufficientData")
+    mean = (head[:dim] / n).to(x_local.dtype)
+    if center_fn is None:
+        from . import matrix
+
+        def center_fn(x, m):
+            out = torch.empty_like(x)
+            matrix.center_columns(x, m.contiguous(), False, out)
+            return out
+    if gram_fn is None:
+        from . import matrix
+
+        def gram_fn(c):
+            return matrix.gemm_device(c, c, True, False, 1.0, 0.0, None)
+    part = gram_fn(center_fn(x_local, mean)).to(torch.float64)
+    if world > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    return mean, (part / float(n - 1)).to(x_local.dtype)

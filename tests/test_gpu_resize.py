@@ -67,6 +67,33 @@ def test_same_shape_copy_views_and_host_twin(zb):
     assert np.array_equal(s.to_numpy(), zo.resize(img, (10, 15), "bilinear"))
 
 
+@pytest.mark.parametrize("ch", [3, 4])
+@pytest.mark.parametrize("method", ["bicubic", "catmull_rom", "mitchell"])
+def test_uniform_phase_cubic_kernel(zb, ch, method):
+    """Integer down-scale ratios give every column (row) the same tap weights: the constant-weight kernel must agree with the
+    oracle bit for bit, including odd row pitches (unaligned 32-bit windows), mirrored edge taps and strided views."""
+    rng = np.random.default_rng(ch + len(method))
+    for src_shape, dst_shape in [((96, 99), (32, 33)), ((120, 100), (60, 50)), ((64, 64), (16, 16)), ((40, 35), (8, 7)), ((12, 9), (4, 3))]:
+        img = rand_image(rng, src_shape + (ch,), np.uint8)
+        dev = zb.Image.from_numpy(img)
+        out = zb.Image.init(dst_shape[0], dst_shape[1], dev.pixfmt)
+        got = dev.resize(out, method_enum(zb, method)).to_numpy()
+        assert zb.lib().zb_last_kernel().decode() == "resize_cubic_uniform_u8", (src_shape, dst_shape)
+        assert np.array_equal(got, zo.resize(img, dst_shape, method)), (src_shape, dst_shape)
+    # a view whose rows start on odd bytes, into a view of a larger destination
+    base = rand_image(rng, (70, 67, ch), np.uint8)
+    dev = zb.Image.from_numpy(base)
+    v = dev.view(zb.Rectangle(3, 5, 63, 65))                       # 60 x 60 window
+    big = zb.Image.from_numpy(np.full((40, 41, ch), 9, np.uint8))
+    ov = big.view(zb.Rectangle(2, 1, 32, 31))                      # 30 x 30 window
+    v.resize(ov, method_enum(zb, method))
+    want = zo.resize(np.ascontiguousarray(base[5:65, 3:63]), (30, 30), method)
+    res = big.to_numpy()
+    assert np.array_equal(res[1:31, 2:32], want)
+    res[1:31, 2:32] = 9
+    assert np.all(res == 9)
+
+
 def test_config3_bicubic_4to1_rgb(zb):
     """BASELINE config 3 at reduced size for the oracle (2048^2 -> 512^2) plus the 4:1 constant-weight property at
     full size 16384^2 -> 4096^2: every output is clamp(trunc(sum(block * W) / 256)) with W = outer([-32,160,160,-32])/256."""

@@ -11,6 +11,8 @@
 // pure integer (or f32 for Lanczos) accumulate in the reference's ky-outer / kx-inner order.  Pixels
 // stay interleaved: the reference's split -> plane -> merge computes the same per-channel values.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "zb_host_stage.h"
@@ -183,6 +185,88 @@ __global__ void __launch_bounds__(256) resize_plane_kernel(const uint8_t* __rest
     }
 }
 
+// Cubic family with a UNIFORM phase: when src/dst is an integer ratio every destination column has the same fractional source
+// position (frac = 0.5 for even ratios), so the 4 x-weights are the same for all columns, likewise the 4 y-weights for all rows,
+// and the 16 products w = @divTrunc(wx * wy, 256) and their sum are per-launch constants instead of 16 multiplies + truncating
+// divides and 3 integer divisions by a runtime value per pixel.  Values are identical to the general kernel by construction.
+struct UniformCubic {
+    int w[16];        // [ky][kx]
+    int weight_sum;   // > 0
+    float rcp;        // 1 / weight_sum
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t* __restrict__ src, size_t src_row_b, size_t src_bytes,
+                                                                   uint8_t* __restrict__ dst, size_t dst_row_b, int dst_cols,
+                                                                   const TapEntry* __restrict__ xt, const TapEntry* __restrict__ yt,
+                                                                   const __grid_constant__ UniformCubic u) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= dst_cols) return;
+    const int4 ix = __ldg(reinterpret_cast<const int4*>(&xt[c]));   // idx[0..3] lead the entry
+    const int4 iy = __ldg(reinterpret_cast<const int4*>(&yt[r]));
+    const int iyv[4] = {iy.x, iy.y, iy.z, iy.w};
+    int sum[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) sum[k] = 0;
+    const bool consecutive = ix.y == ix.x + 1 && ix.z == ix.x + 2 && ix.w == ix.x + 3;   // false only where the mirror border folds
+    if (consecutive) {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const uint8_t* p = src + (size_t)iyv[ky] * src_row_b + (size_t)ix.x * CH;   // 4 * CH contiguous bytes
+            uint32_t wds[CH];                                                            // the 4*CH bytes as CH words
+            const uintptr_t a = (uintptr_t)p & 3u;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+            if (a == 0) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) wds[i] = __ldg(q + i);
+            } else if ((const uint8_t*)(q + CH + 1) <= src + src_bytes && (const uint8_t*)q >= src) {
+                uint32_t t[CH + 1];
+#pragma unroll
+                for (int i = 0; i <= CH; ++i) t[i] = __ldg(q + i);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) wds[i] = __funnelshift_r(t[i], t[i + 1], 8 * (unsigned)a);
+            } else {   // the aligned window would leave the image: bytes
+#pragma unroll
+                for (int i = 0; i < CH; ++i) wds[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int b = kx * CH + k;
+                    sum[k] += (int)((wds[b >> 2] >> (8 * (b & 3))) & 0xFFu) * u.w[ky * 4 + kx];
+                }
+        }
+    } else {
+        const int ixv[4] = {ix.x, ix.y, ix.z, ix.w};
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const uint8_t* row = src + (size_t)iyv[ky] * src_row_b;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const uint8_t* p = row + (size_t)ixv[kx] * CH;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) sum[k] += (int)p[k] * u.w[ky * 4 + kx];
+            }
+        }
+    }
+    uint8_t* out = dst + (size_t)r * dst_row_b + (size_t)c * CH;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        // @divTrunc(sum, weight_sum) clamped to 0..255: non-positive sums give 0; for positive sums (< 2^24, exact in f32) the
+        // float estimate is within one of the quotient and the remainder test fixes it
+        int q = 0;
+        if (sum[k] > 0) {
+            q = __float2int_rz((float)sum[k] * u.rcp);
+            const int rem = sum[k] - q * u.weight_sum;
+            q += rem >= u.weight_sum ? 1 : (rem < 0 ? -1 : 0);
+            q = min(q, 255);
+        }
+        out[k] = (uint8_t)q;
+    }
+}
+
 template <int CH>
 int launch_plane(const zb_image* src, zb_image* dst, int method, const TapEntry* xt, const TapEntry* yt, cudaStream_t s) {
     dim3 grid(div_up(dst->cols, 256), dst->rows);
@@ -254,6 +338,36 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
         TapEntry* dyt = dxt + xt.size();
         ZB_CUDA(cudaMemcpyAsync(dxt, xt.data(), xt.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, s));
         ZB_CUDA(cudaMemcpyAsync(dyt, yt.data(), yt.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, s));
+        if (method == ZB_INTERP_BICUBIC || method == ZB_INTERP_CATMULL_ROM || method == ZB_INTERP_MITCHELL) {
+            bool uniform = true;
+            for (size_t c = 1; c < xt.size() && uniform; ++c) uniform = memcmp(xt[c].w, xt[0].w, 4 * sizeof(int)) == 0;
+            for (size_t r = 1; r < yt.size() && uniform; ++r) uniform = memcmp(yt[r].w, yt[0].w, 4 * sizeof(int)) == 0;
+            UniformCubic u;
+            u.weight_sum = 0;
+            for (int ky = 0; ky < 4; ++ky)
+                for (int kx = 0; kx < 4; ++kx) {
+                    u.w[ky * 4 + kx] = (xt[0].w[kx] * yt[0].w[ky]) / 256;   // @divTrunc(wx * wy, SCALE), channel_ops.zig:262
+                    u.weight_sum += u.w[ky * 4 + kx];
+                }
+            long long abs_sum = 0;
+            for (int i = 0; i < 16; ++i) abs_sum += std::llabs((long long)u.w[i]);
+            if (uniform && u.weight_sum > 0 && 255 * abs_sum < (1 << 24)) {
+                u.rcp = 1.0f / (float)u.weight_sum;
+                dim3 grid(div_up(dst->cols, 256), dst->rows);
+                const int ch = pixfmt == ZB_PIX_RGB8 ? 3 : 4;
+                const size_t sb = (size_t)src->stride * ch, db = (size_t)dst->stride * ch;
+                const size_t src_bytes = (size_t)(src->rows - 1) * sb + (size_t)src->cols * ch;
+                if (ch == 3)
+                    resize_cubic_uniform_kernel<3><<<grid, 256, 0, s>>>((const uint8_t*)src->data, sb, src_bytes, (uint8_t*)dst->data, db,
+                                                                        (int)dst->cols, dxt, dyt, u);
+                else
+                    resize_cubic_uniform_kernel<4><<<grid, 256, 0, s>>>((const uint8_t*)src->data, sb, src_bytes, (uint8_t*)dst->data, db,
+                                                                        (int)dst->cols, dxt, dyt, u);
+                ZB_LAUNCHED();
+                t_last_kernel = "resize_cubic_uniform_u8";
+                return ZB_OK;
+            }
+        }
         t_last_kernel = "resize_plane_u8";
         return pixfmt == ZB_PIX_RGB8 ? launch_plane<3>(src, dst, method, dxt, dyt, s) : launch_plane<4>(src, dst, method, dxt, dyt, s);
     }

@@ -67,6 +67,14 @@ __device__ __forceinline__ Pix<CT, N> zero_px() {
     return p;
 }
 
+// @round(256 * (x - floor(x))) (interpolation.zig:349-352) without the float round: the fraction f is exact, 256 f >= 0, and
+// round-half-away(256 f) = floor(256 f + 1/2) = (floor(512 f) + 1) >> 1 with floor(512 f) = floor(512 x) - 512 floor(x);
+// 512 x is an exact product and fits an int32 for |x| < 2^21 (larger coordinates take the float path).
+__device__ __forceinline__ unsigned frac_q8(float x, float floor_x, int floor_i) {
+    if (fabsf(x) < 2097152.0f) return (unsigned)((__float2int_rd(x * 512.0f) - (floor_i << 9) + 1) >> 1);
+    return (unsigned)(int)roundf((x - floor_x) * 256.0f);
+}
+
 // interpolation.zig:349-367 on four channels at once.  Horizontal blend on two 16-bit lanes per register
 // (channel * 256 <= 65280 never carries into the neighbour lane), vertical blend per channel in 32 bits:
 // (top * (256 - fy) + bottom * fy + 32768) < 2^24, so ">> 16" leaves the result (<= 255, no clamp needed) in byte 2.
@@ -181,6 +189,10 @@ __device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, fl
         const float flx = floorf(x), fly = floorf(y);
         const I left = (I)flx, top = (I)fly;
         Pix<CT, N> tl, tr, bl, br;
+        if (BORDER_T == ZB_BORDER_ZERO && (left < -1 || left >= cols || top < -1 || top >= rows)) {
+            out = zero_px<CT, N>();   // all four neighbours are outside: .zero makes every one of them 0 (most of a rotated frame's margin)
+            return true;
+        }
         if (left >= 0 && left + 1 < cols && top >= 0 && top + 1 < rows) {  // all four neighbours inside: no border logic
             const CT* q = base + ((size_t)top * img.stride + (size_t)left) * N;
             tl = load_px<CT, N>(q, 0);
@@ -201,11 +213,11 @@ __device__ __forceinline__ bool interpolate_impl(const SrcView& img, float x, fl
         const float lr = x - flx;  // == x - as(f32, left): floor(x) is exactly representable
         const float tb = y - fly;
         if constexpr (sizeof(CT) == 1 && N == 4) {
-            const unsigned fx = (unsigned)(int)roundf(lr * 256.0f), fy = (unsigned)(int)roundf(tb * 256.0f);
+            const unsigned fx = frac_q8(x, flx, (int)left), fy = frac_q8(y, fly, (int)top);
             out.u = bilerp_rgba8(tl.u, tr.u, bl.u, br.u, fx, fy);
         } else if constexpr (sizeof(CT) == 1) {
             // :349-367.  fx, fy in [0, 256]; every intermediate is non-negative and < 2^25, so unsigned shift == @divTrunc
-            const unsigned fx = (unsigned)(int)roundf(lr * 256.0f), fy = (unsigned)(int)roundf(tb * 256.0f);
+            const unsigned fx = frac_q8(x, flx, (int)left), fy = frac_q8(y, fly, (int)top);
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 const unsigned top_val = (unsigned)tl.v[k] * (256u - fx) + (unsigned)tr.v[k] * fx;

@@ -103,6 +103,9 @@ int zb_free(void* p, zb_stream s);                         /* cudaFreeAsync */
 int zb_malloc_host(void** out, size_t bytes);              /* pinned host memory */
 int zb_free_host(void* p);
 /* Image-shaped copies (row pitch honoured on both sides); direction from the pointer kinds. */
+/* Image.setBorder(rect, zeroes(T))   image.zig:198-229: zero everything outside [l, r) x [t, b) (the rect is clipped to the
+ * image; an empty intersection zeroes the whole image).  Four strided memsets on the stream. */
+int zb_set_border_zero(zb_image* img, int pixfmt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, zb_stream s);
 int zb_upload(const zb_image* host_src, zb_image* dev_dst, int pixfmt, zb_stream s);
 int zb_download(const zb_image* dev_src, zb_image* host_dst, int pixfmt, zb_stream s);
 int zb_copy(const zb_image* dev_src, zb_image* dev_dst, int pixfmt, zb_stream s); /* Image.copy, image.zig:375-392 */
@@ -165,6 +168,13 @@ int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_i
  * m (HOST): similarity/affine {m00,m01,m10,m11,b0,b1}; projective 9 values row-major. */
 int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m,
             int method, float mitchell_b, float mitchell_c, zb_stream s);
+
+/* Image.extract(out, rect, angle, method, border)   image.zig / transforms.zig:232-283: resample the rectangle (l, t, r, b in source
+ * coordinates, rotated by `angle` CCW around its centre; cos/sin cross the ABI as data like rotateInto) into dst; an axis-aligned
+ * rect of dst's own size takes the copyRect path (:465-518).  Image.crop(rect) (:216-222) is
+ * zb_extract(rect, 0, cos 1, sin 0, NEAREST, ZERO) into a round(height) x round(width) image. */
+int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+               float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Linear algebra behind fdm / pca

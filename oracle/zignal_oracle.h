@@ -116,6 +116,10 @@ int zo_rotate_class(float angle);
  * path and the oracle consume identical values; the orthogonal fast paths key off `angle`. */
 int zo_rotate_into(const zo_image* src, zo_image* dst, int pixfmt, float angle, float cos_a, float sin_a,
                    int method, float mitchell_b, float mitchell_c, int border);
+/* transforms.zig:232-283 (extract; rect = l, t, r, b in source coordinates, angle CCW around its centre; cos/sin passed in)
+ * including the copyRect fast path :465-518.  crop (:216-222) = extract(rect, 0, nearest, zero) into round(height) x round(width). */
+int zo_extract(const zo_image* src, zo_image* dst, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+               float sin_a, int method, float mitchell_b, float mitchell_c, int border);
 /* transforms.zig:522-531 with project() of geometry/transforms.zig:39,147,224.
  * m is row-major: similarity/affine: {m00,m01,m10,m11,b0,b1}; projective: 9 values. */
 int zo_warp(const zo_image* src, zo_image* dst, int pixfmt, int xform_kind, const float* m,

@@ -1,4 +1,4 @@
-// zo_transform.cpp -- CPU oracle for Image.rotate / rotateInto / rotateBounds / warp.
+// zo_transform.cpp -- CPU oracle for Image.rotate / rotateInto / rotateBounds / warp / extract.
 // TEST INFRASTRUCTURE ONLY (see zignal_oracle.h).  Restates image/transforms.zig:112-149
 // (rotateBounds), :163-212 (rotateInto), :385-462 (rotate0/90/180/270), :522-531 (warp),
 // image.zig:200-229 (setBorder), :322-327 (getCenter), geometry/transforms.zig:39-42, :147-150,
@@ -136,9 +136,59 @@ static void warp(const zo_image* src, zo_image* dst, int kind, const float* m, i
         }
 }
 
+// transforms.zig:232-283 (extract) with :465-518 (copyRect, the axis-aligned no-resampling fast path)
+template <typename PX>
+static void extract(const zo_image* src, zo_image* dst, float rl, float rt, float rr, float rb, float angle, float cos_a, float sin_a,
+                    int method, float mb, float mc, int border) {
+    using T = typename PX::T;
+    Img<T> self(src), out(dst);
+    if (out.rows == 0 || out.cols == 0) return;
+    const float frows = (float)out.rows, fcols = (float)out.cols;
+    const float width = rl >= rr ? 0.0f : rr - rl, height = rt >= rb ? 0.0f : rb - rt;   // Rectangle(f32).width / height, Rectangle.zig:76-93
+    const float epsilon = 1e-6f;
+    if (std::fabs(angle) < epsilon && std::fabs(width - fcols) < epsilon && std::fabs(height - frows) < epsilon) {
+        const int32_t rect_top = (int32_t)std::round(rt), rect_left = (int32_t)std::round(rl);
+        for (uint32_t r = 0; r < out.rows; ++r)
+            for (uint32_t c = 0; c < out.cols; ++c) {
+                const int64_t sr = resolve_index((int64_t)r + rect_top, (int64_t)self.rows, border);
+                const int64_t sc = resolve_index((int64_t)c + rect_left, (int64_t)self.cols, border);
+                out.at(r, c) = (sr < 0 || sc < 0) ? PX::zero() : self.at((uint32_t)sr, (uint32_t)sc);
+            }
+        return;
+    }
+    const float cx = (rl + rr) * 0.5f, cy = (rt + rb) * 0.5f;
+    for (uint32_t r = 0; r < out.rows; ++r) {
+        const float ty = out.rows == 1 ? 0.5f : (float)r / (frows - 1);
+        const float y_rect = rt + ty * height;
+        for (uint32_t c = 0; c < out.cols; ++c) {
+            const float tx = out.cols == 1 ? 0.5f : (float)c / (fcols - 1);
+            const float x_rect = rl + tx * width;
+            const float dx = x_rect - cx, dy = y_rect - cy;
+            const float src_x = cx + cos_a * dx - sin_a * dy;
+            const float src_y = cy + sin_a * dx + cos_a * dy;
+            T val;
+            if (!interpolate<PX>(self, src_x, src_y, method, mb, mc, border, &val)) val = PX::zero();
+            out.at(r, c) = val;
+        }
+    }
+}
+
 }  // namespace zo
 
 extern "C" {
+
+int zo_extract(const zo_image* src, zo_image* dst, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+               float sin_a, int method, float mb, float mc, int border) {
+    using namespace zo;
+    switch (pixfmt) {
+        case ZO_PIX_U8: extract<PxU8>(src, dst, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_F32: extract<PxF32>(src, dst, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGB8: extract<PxRgb8>(src, dst, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGBA8: extract<PxRgba8>(src, dst, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+        case ZO_PIX_RGBAF32: extract<PxRgbaF32>(src, dst, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, border); return ZO_OK;
+    }
+    return ZO_ERR_UNSUPPORTED;
+}
 
 int zo_rotate_class(float angle) { return zo::rotate_class(angle); }
 

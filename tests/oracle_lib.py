@@ -82,6 +82,7 @@ def _declare(L):
     L.zo_rotate_class.argtypes = [C.c_float]
     L.zo_rotate_into.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int]
     L.zo_warp.argtypes = [img, img, C.c_int, C.c_int, fp, C.c_int, C.c_float, C.c_float]
+    L.zo_extract.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float, C.c_int]
     L.zo_svd_f64.argtypes = [dp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
     L.zo_svd_f64.restype = C.c_int64
     L.zo_svd_f32.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, fp, fp, fp]
@@ -241,6 +242,17 @@ def rotate_into(src, out, angle, method="bilinear", border="zero", cos_sin=None,
     s, d = as_image(src), as_image(out)
     _check(lib().zo_rotate_into(s, d, pixfmt_of(src), C.c_float(a32), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
                                 INTERP[method], C.c_float(b), C.c_float(c), BORDER[border]), "rotate_into")
+    return out
+
+
+def extract(src, out, rect, angle=0.0, method="bilinear", border="zero", cos_sin=None, b=1.0 / 3.0, c=1.0 / 3.0):
+    """rect = (l, t, r, b) in source coordinates (transforms.zig:232-283)."""
+    a32 = np.float32(angle)
+    if cos_sin is None:
+        cos_sin = (np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32))
+    s, d = as_image(src), as_image(out)
+    _check(lib().zo_extract(s, d, pixfmt_of(src), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]), C.c_float(a32),
+                            C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), INTERP[method], C.c_float(b), C.c_float(c), BORDER[border]), "extract")
     return out
 
 

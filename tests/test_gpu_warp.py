@@ -139,3 +139,35 @@ def test_host_rotate_and_warp(zb):
     out = np.zeros((25, 35, 4), np.uint8)
     m = [0.9, -0.2, 0.25, 1.1, 1.5, -2.0]
     assert np.array_equal(zb.host_warp(img, out, _Xf("affine", m)), zo.warp(img, np.zeros_like(out), "affine", m, "bilinear"))
+
+
+@pytest.mark.parametrize("fmt", ["u8", "rgb8", "rgba8", "f32"])
+def test_extract_and_crop(zb, fmt):
+    """Image.extract (transforms.zig:232-283): rotated / rescaled rectangles through every sampler, the copyRect fast path with
+    every border mode, and crop (= extract nearest/zero into a rounded chip) -- bit-identical to the oracle."""
+    from gpu_utils import METHODS, method_enum
+    rng = np.random.default_rng(len(fmt))
+    shape = {"u8": (40, 52), "rgb8": (40, 52, 3), "rgba8": (40, 52, 4), "f32": (40, 52)}[fmt]
+    img = rand_image(rng, shape, np.float32 if fmt == "f32" else np.uint8)
+    dev = zb.Image.from_numpy(img)
+    tail = tuple(shape[2:])
+    for rect, angle, out_shape in [((5.0, 4.0, 35.0, 28.0), 0.3, (20, 25)), ((-6.5, -3.0, 30.0, 50.0), -1.1, (17, 9)),
+                                   ((10.0, 10.0, 20.0, 20.0), 0.0, (1, 1)), ((2.2, 3.7, 48.9, 30.1), 2.0, (33, 1))]:
+        for method in METHODS:
+            for border in ("zero", "mirror"):
+                out = zb.Image.init(out_shape[0], out_shape[1], dev.pixfmt)
+                got = dev.extract(out, rect, angle, method_enum(zb, method), getattr(zb.BorderMode, border.upper())).to_numpy()
+                want = zo.extract(img, np.zeros(out_shape + tail, img.dtype), rect, angle, method, border)
+                assert np.array_equal(got, want), (rect, angle, method, border)
+    # copyRect fast path: rect of the output's own size, any border mode, partly or fully outside the image
+    for rect in [(3.0, 2.0, 23.0, 17.0), (-4.4, -7.5, 15.6, 7.5), (45.0, 30.0, 65.0, 45.0), (100.0, 100.0, 120.0, 115.0)]:
+        for border in ("zero", "replicate", "mirror", "wrap"):
+            out = zb.Image.from_numpy(np.full((15, 20) + tail, 7, img.dtype))
+            got = dev.extract(out, rect, 0.0, zb.Interpolation.BICUBIC, getattr(zb.BorderMode, border.upper())).to_numpy()
+            assert zb.lib().zb_last_kernel().decode() == "extract_copy_rect"
+            want = zo.extract(img, np.zeros((15, 20) + tail, img.dtype), rect, 0.0, "bicubic", border)
+            assert np.array_equal(got, want), (rect, border)
+    chip = dev.crop((4.4, -2.6, 30.5, 19.5))
+    assert (chip.rows, chip.cols) == (22, 26)
+    want = zo.extract(img, np.zeros((22, 26) + tail, img.dtype), (4.4, -2.6, 30.5, 19.5), 0.0, "nearest", "zero")
+    assert np.array_equal(chip.to_numpy(), want)

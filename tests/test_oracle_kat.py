@@ -506,3 +506,20 @@ def test_pca_10d_reconstruct():  # :559-588
     v = np.arange(10, dtype=np.float64)
     coeffs = comps.T @ (v - mean)
     assert np.allclose(_reconstruct(mean, comps, coeffs), v, atol=1e-10)
+
+
+def test_extract_kats():
+    """image/tests/transforms.zig:228-315: extract of a 3x3 region at 0 and 90 degrees, and the single-pixel-axis centring rule."""
+    img = (np.arange(5)[:, None] * 10 + np.arange(5)[None, :]).astype(np.uint8)
+    rect = (1.0, 1.0, 3.0, 3.0)
+    out0 = zo.extract(img, np.zeros((3, 3), np.uint8), rect, 0.0, "nearest", "mirror")
+    assert out0.tolist() == [[11, 12, 13], [21, 22, 23], [31, 32, 33]]
+    out90 = zo.extract(img, np.zeros((3, 3), np.uint8), rect, np.float32(np.pi / 2.0), "nearest", "mirror")
+    assert out90.tolist() == [[13, 23, 33], [12, 22, 32], [11, 21, 31]]
+    assert zo.extract(img, np.zeros((1, 1), np.uint8), rect, 0.0, "nearest", "mirror").tolist() == [[22]]
+    assert zo.extract(img, np.zeros((1, 3), np.uint8), rect, 0.0, "nearest", "mirror").tolist() == [[21, 22, 23]]
+    assert zo.extract(img, np.zeros((3, 1), np.uint8), rect, 0.0, "nearest", "mirror").tolist() == [[12], [22], [32]]
+    # "extract from empty image regression" (:411-424): replicate / wrap on a 0x0 source give zeros, no panic
+    empty = np.zeros((0, 0), np.uint8)
+    for border in ("replicate", "wrap"):
+        assert not zo.extract(empty, np.full((2, 2), 9, np.uint8), (0.0, 0.0, 2.0, 2.0), 0.0, "nearest", border).any()

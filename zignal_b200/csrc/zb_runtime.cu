@@ -165,6 +165,28 @@ static int copy2d(const zb_image* src, zb_image* dst, int pixfmt, cudaMemcpyKind
     ZB_CUDA(cudaMemcpy2DAsync(dst->data, dst->stride * pb, src->data, src->stride * pb, (size_t)src->cols * pb, src->rows, kind, s));
     return ZB_OK;
 }
+int zb_set_border_zero(zb_image* img, int pixfmt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, zb_stream s) {
+    if (!img) return ZB_ERR_INVALID_ARGUMENT;
+    const size_t pb = pixel_bytes(pixfmt);
+    if (pb == 0) return ZB_ERR_UNSUPPORTED;
+    if (img->rows == 0 || img->cols == 0) return ZB_OK;
+    r = r < img->cols ? r : img->cols;   // bounds.intersect(rect)
+    b = b < img->rows ? b : img->rows;
+    if (l >= r || t >= b) { l = r = 0; t = b = 0; }   // no intersection: everything is border (image.zig:202-205)
+    char* base = (char*)img->data;
+    const size_t pitch = img->stride * pb;
+    auto zero = [&](uint32_t row0, uint32_t row1, uint32_t col0, uint32_t col1) -> int {
+        if (row1 <= row0 || col1 <= col0) return ZB_OK;
+        ZB_CUDA(cudaMemset2DAsync(base + (size_t)row0 * pitch + (size_t)col0 * pb, pitch, 0, (size_t)(col1 - col0) * pb, row1 - row0, (cudaStream_t)s));
+        return ZB_OK;
+    };
+    int rc;
+    if ((rc = zero(0, t, 0, img->cols))) return rc;           // top band
+    if ((rc = zero(t, b, 0, l))) return rc;                   // left of the rect
+    if ((rc = zero(t, b, r, img->cols))) return rc;           // right of the rect
+    return zero(b, img->rows, 0, img->cols);                  // bottom band
+}
+
 int zb_upload(const zb_image* host_src, zb_image* dev_dst, int pixfmt, zb_stream s) {
     return copy2d(host_src, dev_dst, pixfmt, cudaMemcpyHostToDevice, (cudaStream_t)s);
 }

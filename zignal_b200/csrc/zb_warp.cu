@@ -239,6 +239,92 @@ int warp_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int kind, cons
     return ZB_ERR_UNSUPPORTED;
 }
 
+// ---- Image.extract (transforms.zig:232-283) and its copyRect fast path (:465-518) ---------------------------------------------
+struct ExtractParams {
+    float rl, rt, width, height, cx, cy, cos_a, sin_a, frows1, fcols1;   // frows1 = rows - 1 as f32
+    int copy_rect, rect_top, rect_left;                                   // fast path: integer shift + border
+    int border, method;
+    float mb, mc;
+};
+
+template <typename CT, int N, int METHOD>
+__global__ void __launch_bounds__(256) extract_kernel(SrcView img, CT* __restrict__ dst, size_t dst_stride, int dst_rows, int dst_cols,
+                                                      ExtractParams p, const float* __restrict__ lut) {
+    const int c = blockIdx.x * 32 + patch_col(threadIdx.x);
+    const int r = blockIdx.y * 8 + patch_row(threadIdx.x);
+    if (c >= dst_cols || r >= dst_rows) return;
+    Pix<CT, N> val;
+    if (p.copy_rect) {   // out(r, c) = self(resolve(r + top), resolve(c + left)) or zero
+        const int sr = resolve_index(r + p.rect_top, img.rows, p.border);
+        const int sc = resolve_index(c + p.rect_left, img.cols, p.border);
+        val = (sr < 0 || sc < 0) ? zero_px<CT, N>() : load_px<CT, N>((const CT*)img.data, (size_t)sr * img.stride + (size_t)sc);
+    } else {             // normalised mapping, rotation by +angle around the rect centre (unfused f32, the reference's order)
+        const float ty = dst_rows == 1 ? 0.5f : (float)r / p.frows1;
+        const float y_rect = p.rt + ty * p.height;
+        const float tx = dst_cols == 1 ? 0.5f : (float)c / p.fcols1;
+        const float x_rect = p.rl + tx * p.width;
+        const float dx = x_rect - p.cx, dy = y_rect - p.cy;
+        const float src_x = p.cx + p.cos_a * dx - p.sin_a * dy;
+        const float src_y = p.cy + p.sin_a * dx + p.cos_a * dy;
+        if (!interpolate<CT, N, METHOD, -1>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+    }
+    store_px<CT, N>(dst, (size_t)r * dst_stride + c, val);
+}
+
+template <typename CT, int N>
+int extract_typed(const zb_image* src, zb_image* dst, const ExtractParams& p, const float* lut, cudaStream_t s) {
+    SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
+    dim3 grid(div_up(dst->cols, 32), div_up(dst->rows, 8));
+    return dispatch_method(p.method, [&](auto m) -> int {
+        extract_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows, (int)dst->cols, p, lut);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    });
+}
+
+int extract_dispatch(const zb_image* src, zb_image* dst, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+                     float sin_a, int method, float mb, float mc, int border, cudaStream_t s) {
+    if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
+    if (channels_of(pixfmt) == 0) return ZB_ERR_UNSUPPORTED;
+    if (method < ZB_INTERP_NEAREST || method > ZB_INTERP_LANCZOS) return ZB_ERR_INVALID_ARGUMENT;
+    if (border < ZB_BORDER_ZERO || border > ZB_BORDER_WRAP) return ZB_ERR_INVALID_ARGUMENT;
+    if (dst->rows == 0 || dst->cols == 0) return ZB_OK;   // :233
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (src->rows == 0 || src->cols == 0) {   // every sample resolves to null -> zeroes (tests/transforms.zig:411-424)
+        ZB_CUDA(cudaMemset2DAsync(dst->data, dst->stride * pixel_bytes(pixfmt), 0, (size_t)dst->cols * pixel_bytes(pixfmt), dst->rows, s));
+        return ZB_OK;
+    }
+    ExtractParams p;
+    memset(&p, 0, sizeof(p));
+    const float frows = (float)dst->rows, fcols = (float)dst->cols;
+    p.rl = rl; p.rt = rt;
+    p.width = rl >= rr ? 0.0f : rr - rl;   // Rectangle(f32).width / height return 0 for an inverted rect (Rectangle.zig:76-93)
+    p.height = rt >= rb ? 0.0f : rb - rt;
+    const float epsilon = 1e-6f;
+    if (std::fabs(angle) < epsilon && std::fabs(p.width - fcols) < epsilon && std::fabs(p.height - frows) < epsilon) {   // :241-250
+        p.copy_rect = 1;
+        p.rect_top = (int)std::round(rt);
+        p.rect_left = (int)std::round(rl);
+    }
+    p.cx = (rl + rr) * 0.5f; p.cy = (rt + rb) * 0.5f;
+    p.cos_a = cos_a; p.sin_a = sin_a;
+    p.frows1 = frows - 1; p.fcols1 = fcols - 1;
+    p.border = border; p.method = method; p.mb = mb; p.mc = mc;
+    const float* lut = nullptr;
+    if (method == ZB_INTERP_LANCZOS && (rc = lanczos_lut_device(&lut, s))) return rc;
+    t_last_kernel = p.copy_rect ? "extract_copy_rect" : "extract_gather";
+    switch (pixfmt) {
+        case ZB_PIX_U8: return extract_typed<uint8_t, 1>(src, dst, p, lut, s);
+        case ZB_PIX_F32: return extract_typed<float, 1>(src, dst, p, lut, s);
+        case ZB_PIX_RGB8: return extract_typed<uint8_t, 3>(src, dst, p, lut, s);
+        case ZB_PIX_RGBA8: return extract_typed<uint8_t, 4>(src, dst, p, lut, s);
+        case ZB_PIX_RGBAF32: return extract_typed<float, 4>(src, dst, p, lut, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 // interpolation.zig:256-267: lut[i] = lanczosKernel(i / (1024/3), 3) in f32, computed on the host
@@ -306,6 +392,12 @@ int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_i
     if (n_images > 65535) return ZB_ERR_INVALID_ARGUMENT;
     return rotate_dispatch(src0, src_image_pitch_px, dst0, dst_image_pitch_px, n_images, pixfmt, angle, cos_a, sin_a, method, mb, mc, border,
                            (cudaStream_t)s);
+}
+
+int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+               float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int border, zb_stream s) {
+    return extract_dispatch(src, dst, pixfmt, rect_l, rect_t, rect_r, rect_b, angle, cos_a, sin_a, method, mitchell_b, mitchell_c, border,
+                            (cudaStream_t)s);
 }
 
 int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m, int method, float mb, float mc, zb_stream s) {

@@ -267,6 +267,27 @@ class Image:
         out = Image.init(rows, cols, self.pixfmt, self._t.device)
         return self.rotate_into(out, angle, method, border, cos_sin)
 
+    def extract(self, out: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
+                border: BorderMode = BorderMode.ZERO, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        """Image.extract (transforms.zig:232-283): rect = (l, t, r, b) floats in source coordinates, rotated by `angle` CCW."""
+        a32 = np.float32(angle)
+        cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_extract(a, d, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                               C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(border),
+                               current_stream()))
+        return out
+
+    def crop(self, rect) -> "Image":
+        """Image.crop (transforms.zig:216-222): round(height) x round(width) chip, out-of-bounds pixels zero."""
+        def rnd(v):  # @round on f32, half away from zero
+            v = np.float32(v)
+            return int(np.sign(v) * np.floor(np.abs(np.float64(v)) + 0.5))
+        l, t, r, b = (np.float32(v) for v in rect)
+        rows, cols = rnd(np.float32(0) if t >= b else b - t), rnd(np.float32(0) if l >= r else r - l)   # Rectangle.height / width
+        chip = Image.init(max(rows, 0), max(cols, 0), self.pixfmt, device=self._t.device)
+        return self.extract(chip, rect, 0.0, Interpolation.NEAREST, BorderMode.ZERO)
+
     def warp(self, out: "Image", transform, method: Interpolation = Interpolation.BILINEAR, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
         kind, m = transform.as_f32()
         a, d = self._zb(), out._zb()

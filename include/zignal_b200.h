@@ -169,6 +169,10 @@ int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_i
 int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, const float* m,
             int method, float mitchell_b, float mitchell_c, zb_stream s);
 
+/* Image.sobel(out, allocator)   image.zig:999-1009, edges.zig:33-73: gradient magnitude of the luma into an Image(u8)
+ * (src: U8, F32, RGB8 or RGBA8; dst is always an 8-bit gray image of the same shape). */
+int zb_sobel(const zb_image* src, zb_image* dst_u8, int pixfmt, zb_stream s);
+
 /* Image.extract(out, rect, angle, method, border)   image.zig / transforms.zig:232-283: resample the rectangle (l, t, r, b in source
  * coordinates, rotated by `angle` CCW around its centre; cos/sin cross the ABI as data like rotateInto) into dst; an axis-aligned
  * rect of dst's own size takes the copyRect path (:465-518).  Image.crop(rect) (:216-222) is

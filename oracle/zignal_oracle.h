@@ -97,6 +97,8 @@ int zo_gaussian_blur(const zo_image* src, zo_image* dst, int pixfmt, float sigma
 int zo_integral_plane(const zo_image* src, int pixfmt, float* sat /* rows*cols */);
 /* image.zig:635-648 / integral.zig:148-269; pixfmt in {U8, F32, RGB8, RGBA8, RGBAF32}. */
 int zo_box_blur(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
+/* image.zig:999-1009 / edges.zig:33-73: Sobel magnitude into an Image(u8) (src: U8, F32, RGB8 or RGBA8). */
+int zo_sobel(const zo_image* src, zo_image* dst_u8, int pixfmt);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 

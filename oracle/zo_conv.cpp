@@ -487,6 +487,47 @@ int zo_convolve(const zo_image* src, zo_image* dst, int pixfmt, const float* ker
     return zo::convolve(src, dst, pixfmt, kernel, kh, kw, border);
 }
 
+// edges.zig:33-73 Edges(T).sobel: gray f32 (as(f32, convertColor(u8, px)); float scalars pass through), two 3x3 convolutions with
+// .replicate, magnitude sqrt(gx^2 + gy^2) / 4, trunc(clamp(0, 255)) into a u8 image.  color.zig:1031-1041 for the luma.
+int zo_sobel(const zo_image* src, zo_image* dst, int pixfmt) {
+    if (src->rows != dst->rows || src->cols != dst->cols) return ZO_ERR_DIMENSION_MISMATCH;   // image.zig:1005
+    const uint32_t rows = src->rows, cols = src->cols;
+    std::vector<float> gray((size_t)rows * cols), gx((size_t)rows * cols), gy((size_t)rows * cols);
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t c = 0; c < cols; ++c) {
+            float v;
+            if (pixfmt == ZO_PIX_F32) {
+                v = ((const float*)src->data)[(size_t)r * src->stride + c];
+            } else if (pixfmt == ZO_PIX_U8) {
+                v = (float)((const uint8_t*)src->data)[(size_t)r * src->stride + c];
+            } else if (pixfmt == ZO_PIX_RGB8 || pixfmt == ZO_PIX_RGBA8) {
+                const int ch = pixfmt == ZO_PIX_RGB8 ? 3 : 4;
+                const uint8_t* px = (const uint8_t*)src->data + ((size_t)r * src->stride + c) * ch;
+                int y = (13933 * (int)px[0] + 46871 * (int)px[1] + 4732 * (int)px[2] + 32768) >> 16;
+                y = y < 0 ? 0 : (y > 255 ? 255 : y);
+                v = (float)y;
+            } else {
+                return ZO_ERR_UNSUPPORTED;
+            }
+            gray[(size_t)r * cols + c] = v;
+        }
+    zo_image g{gray.data(), rows, cols, cols}, ix{gx.data(), rows, cols, cols}, iy{gy.data(), rows, cols, cols};
+    static const float sobel_x[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};     // edges.zig:14-18
+    static const float sobel_y[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};     // :21-25
+    int rc = zo::convolve(&g, &ix, ZO_PIX_F32, sobel_x, 3, 3, ZO_BORDER_REPLICATE);
+    if (rc) return rc;
+    if ((rc = zo::convolve(&g, &iy, ZO_PIX_F32, sobel_y, 3, 3, ZO_BORDER_REPLICATE))) return rc;
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t c = 0; c < cols; ++c) {
+            const float a = gx[(size_t)r * cols + c], b = gy[(size_t)r * cols + c];
+            const float magnitude = std::sqrt(a * a + b * b);
+            const float scaled = magnitude / 4.0f;
+            const float cl = std::fmax(0.0f, std::fmin(255.0f, scaled));
+            ((uint8_t*)dst->data)[(size_t)r * dst->stride + c] = (uint8_t)std::trunc(cl);
+        }
+    return ZO_OK;
+}
+
 int zo_gaussian_blur(const zo_image* src, zo_image* dst, int pixfmt, float sigma) {
     if (src->rows != dst->rows || src->cols != dst->cols) return ZO_ERR_DIMENSION_MISMATCH;  // image.zig:962
     if (sigma == 0) { zo::copy_image(src, dst, pixfmt); return ZO_OK; }                       // :966

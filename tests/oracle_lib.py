@@ -75,6 +75,7 @@ def _declare(L):
     L.zo_integral_plane.argtypes = [img, C.c_int, fp]
     L.zo_box_blur.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sharpen.argtypes = [img, img, C.c_int, C.c_uint32]
+    L.zo_sobel.argtypes = [img, img, C.c_int]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
     L.zo_rotate_bounds.argtypes = [C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), P(C.c_uint32)]
@@ -242,6 +243,13 @@ def rotate_into(src, out, angle, method="bilinear", border="zero", cos_sin=None,
     s, d = as_image(src), as_image(out)
     _check(lib().zo_rotate_into(s, d, pixfmt_of(src), C.c_float(a32), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
                                 INTERP[method], C.c_float(b), C.c_float(c), BORDER[border]), "rotate_into")
+    return out
+
+
+def sobel(src):
+    out = np.zeros(src.shape[:2], np.uint8)
+    s, d = as_image(src), as_image(out)
+    _check(lib().zo_sobel(s, d, pixfmt_of(src)), "sobel")
     return out
 
 

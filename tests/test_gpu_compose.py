@@ -77,3 +77,16 @@ def test_letterbox(zb, src_shape, dst_shape, method):
         want = np.zeros_like(got)
         want[orow:orow + sr, ocol:ocol + sc] = zo.resize(img, (sr, sc), method)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape,dtype", [((37, 45), np.uint8), ((40, 33, 3), np.uint8), ((29, 31, 4), np.uint8), ((35, 36), np.float32), ((1, 7), np.uint8)])
+def test_sobel(zb, shape, dtype):
+    rng = np.random.default_rng(shape[0])
+    img = rand_image(rng, shape, dtype)
+    if dtype == np.float32:
+        img = (img * 255.0).astype(np.float32)     # float scalars pass through un-normalised (edges.zig:38-48)
+    got = zb.Image.from_numpy(img).sobel().to_numpy()
+    assert np.array_equal(got, zo.sobel(img))
+    step = np.tile(np.where(np.arange(5) < 2, 0, 255).astype(np.uint8), (5, 1))    # the reference's own test image
+    e = zb.Image.from_numpy(step).sobel().to_numpy()
+    assert e[2, 2] > 200 and e[2, 0] < 50

@@ -224,3 +224,46 @@ def test_pca_fit_and_transform(zb):
     p = Pca(np.float64)
     p.fit(data, 1)
     assert abs(p.eigenvalues[0] - 2.0) < 1e-9 and abs(abs(p.components[0, 0]) - 1.0) < 1e-9
+
+
+def test_config5_full_size_properties(zb):
+    """BASELINE config 5 at full size (4096x4096 Rgb u8), through size-independent properties: the integer moments equal a
+    torch int64 reduction exactly, and after fdm.match the source's channel means / covariance land on the target's (the map
+    is affine, so only the 8-bit quantisation and the [0, 255] clamp separate them)."""
+    import torch
+    from zignal_b200.fdm import FeatureDistributionMatching
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.randint(0, 256, (4096, 4096, 3), device="cuda", dtype=torch.uint8, generator=g)
+    base = torch.randint(0, 256, (4096, 4096, 3), device="cuda", dtype=torch.uint8, generator=g).to(torch.float32)
+    mix = torch.tensor([[0.5, 0.2, 0.0], [0.1, 0.4, 0.1], [0.0, 0.2, 0.45]], device="cuda")
+    tgt = (base @ mix.T * 0.6 + 50.0).clamp(0, 255).to(torch.uint8)          # a different, full-rank colour distribution
+    si, ti = zb.Image.from_tensor(src.clone()), zb.Image.from_tensor(tgt)
+    m = FeatureDistributionMatching.moments(si)
+    x = src.reshape(-1, 3).to(torch.int64)
+    assert int(m[0]) == x.shape[0] and [int(v) for v in m[1:4]] == x.sum(0).tolist()
+    assert int(m[5]) == int((x[:, 0] * x[:, 1]).sum()) and int(m[9]) == int((x[:, 2] ** 2).sum())
+    f = FeatureDistributionMatching(si.pixfmt)
+    f.match(si, ti)
+    f.status()
+    out = si.tensor().reshape(-1, 3).to(torch.float64)
+    want = tgt.reshape(-1, 3).to(torch.float64)
+    assert (out.mean(0) - want.mean(0)).abs().max().item() < 0.5
+    assert (torch.cov(out.T) - torch.cov(want.T)).abs().max().item() < 0.02 * torch.cov(want.T).abs().max().item()
+    f.deinit()
+
+
+def test_pca_gram_full_size(zb):
+    """The PCA contraction at BASELINE size (n = 1,048,576 x dim 256, tcgen05 3xTF32): against the f64 product, 5e-6 of max|C|."""
+    import torch
+    from zignal_b200 import matrix
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn(1048576, 256, device="cuda", generator=g)
+    C_ = matrix.gemm_device(X, X, True, False, 1.0 / (X.shape[0] - 1), 0.0, None)
+    assert zb.lib().zb_last_kernel().decode() == "gemm_xtx_tf32x3_tcgen05"
+    ref = torch.zeros(256, 256, dtype=torch.float64, device="cuda")
+    for i in range(0, X.shape[0], 131072):                                    # f64 reference in slices (keeps memory modest)
+        blk = X[i:i + 131072].double()
+        ref += blk.T @ blk
+    ref /= (X.shape[0] - 1)
+    assert ((C_.double() - ref).abs().max() / ref.abs().max()).item() <= 5e-6
+    assert torch.equal(C_, C_.T)

@@ -523,3 +523,12 @@ def test_extract_kats():
     empty = np.zeros((0, 0), np.uint8)
     for border in ("replicate", "wrap"):
         assert not zo.extract(empty, np.full((2, 2), 9, np.uint8), (0.0, 0.0, 2.0, 2.0), 0.0, "nearest", border).any()
+
+
+def test_sobel_kat():
+    """image/tests/filters.zig:548-569: a vertical step edge gives > 200 on the edge column and < 50 away from it."""
+    img = np.where(np.arange(5)[None, :] < 2, 0, 255).astype(np.uint8).repeat(5, axis=0).reshape(5, 5)
+    img = np.tile(np.where(np.arange(5) < 2, 0, 255).astype(np.uint8), (5, 1))
+    e = zo.sobel(img)
+    assert e[2, 2] > 200 and e[2, 0] < 50
+    assert e[2, 2] == 255 and e[2, 1] == 255 and e[2, 0] == 0 and e[2, 4] == 0     # |gx| = 4 * 255 -> 255 after /4

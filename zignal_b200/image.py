@@ -267,6 +267,14 @@ class Image:
         out = Image.init(rows, cols, self.pixfmt, self._t.device)
         return self.rotate_into(out, angle, method, border, cos_sin)
 
+    def sobel(self, out: Optional["Image"] = None) -> "Image":
+        """Image.sobel (image.zig:999-1009): gradient magnitude into an Image(u8) of the same shape."""
+        if out is None:
+            out = Image.init(self.rows, self.cols, PixFmt.U8, device=self._t.device)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
+        return out
+
     def extract(self, out: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
                 border: BorderMode = BorderMode.ZERO, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
         """Image.extract (transforms.zig:232-283): rect = (l, t, r, b) floats in source coordinates, rotated by `angle` CCW."""

@@ -78,8 +78,16 @@ def test_uniform_phase_cubic_kernel(zb, ch, method):
         dev = zb.Image.from_numpy(img)
         out = zb.Image.init(dst_shape[0], dst_shape[1], dev.pixfmt)
         got = dev.resize(out, method_enum(zb, method)).to_numpy()
-        assert zb.lib().zb_last_kernel().decode() == "resize_cubic_uniform_u8", (src_shape, dst_shape)
+        assert zb.lib().zb_last_kernel().decode() in ("resize_cubic_uniform_u8", "resize_cubic_r4_u8"), (src_shape, dst_shape)
         assert np.array_equal(got, zo.resize(img, dst_shape, method)), (src_shape, dst_shape)
+    # exact 4:1 with 16-byte friendly rows: the coalesced strip kernel (full warps, a ragged last warp, several row blocks)
+    if method == "bicubic":
+        for src_shape, dst_shape in [((64, 2048), (16, 512)), ((40, 4144), (10, 1036)), ((256, 528), (64, 132))]:
+            img = rand_image(rng, src_shape + (ch,), np.uint8)
+            dev = zb.Image.from_numpy(img)
+            got = dev.resize(zb.Image.init(dst_shape[0], dst_shape[1], dev.pixfmt), method_enum(zb, method)).to_numpy()
+            assert zb.lib().zb_last_kernel().decode() == "resize_cubic_r4_u8", (src_shape, dst_shape)
+            assert np.array_equal(got, zo.resize(img, dst_shape, method)), (src_shape, dst_shape)
     # a view whose rows start on odd bytes, into a view of a larger destination
     base = rand_image(rng, (70, 67, ch), np.uint8)
     dev = zb.Image.from_numpy(base)

@@ -193,7 +193,16 @@ struct UniformCubic {
     int w[16];        // [ky][kx]
     int weight_sum;   // > 0
     float rcp;        // 1 / weight_sum
+    int packed[4];    // row ky as four signed bytes (valid when every |w| <= 127): one dp4a does a row of taps
+    int dp4a_ok;
 };
+
+// four unsigned bytes of a times four signed bytes of b, added to c
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 template <int CH>
 __global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t* __restrict__ src, size_t src_row_b, size_t src_bytes,
@@ -230,13 +239,33 @@ __global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t
 #pragma unroll
                 for (int i = 0; i < CH; ++i) wds[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
             }
-#pragma unroll
-            for (int kx = 0; kx < 4; ++kx)
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int b = kx * CH + k;
-                    sum[k] += (int)((wds[b >> 2] >> (8 * (b & 3))) & 0xFFu) * u.w[ky * 4 + kx];
+            if (u.dp4a_ok) {
+                // transpose the window to one word per channel (bytes = the 4 taps) and take the row with one dot product:
+                // unsigned pixels x signed 8-bit weights, exact in the i32 accumulator
+                uint32_t chan[CH];
+                if constexpr (CH == 3) {   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+                    chan[0] = __byte_perm(__byte_perm(wds[0], wds[1], 0x0630), wds[2], 0x5210);
+                    chan[1] = __byte_perm(__byte_perm(wds[0], wds[1], 0x0741), wds[2], 0x6210);
+                    chan[2] = __byte_perm(__byte_perm(wds[0], wds[1], 0x0052), wds[2], 0x7410);
+                } else {                   // one pixel per word
+                    const uint32_t rg01 = __byte_perm(wds[0], wds[1], 0x5140), rg23 = __byte_perm(wds[2], wds[3], 0x5140);
+                    const uint32_t ba01 = __byte_perm(wds[0], wds[1], 0x7362), ba23 = __byte_perm(wds[2], wds[3], 0x7362);
+                    chan[0] = __byte_perm(rg01, rg23, 0x5410);
+                    chan[1] = __byte_perm(rg01, rg23, 0x7632);
+                    chan[2] = __byte_perm(ba01, ba23, 0x5410);
+                    chan[3] = __byte_perm(ba01, ba23, 0x7632);
                 }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) sum[k] = dp4a_u8_s8(chan[k], u.packed[ky], sum[k]);
+            } else {
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        const int b = kx * CH + k;
+                        sum[k] += (int)((wds[b >> 2] >> (8 * (b & 3))) & 0xFFu) * u.w[ky * 4 + kx];
+                    }
+            }
         }
     } else {
         const int ixv[4] = {ix.x, ix.y, ix.z, ix.w};
@@ -264,6 +293,98 @@ __global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t
             q = min(q, 255);
         }
         out[k] = (uint8_t)q;
+    }
+}
+
+// Exact 4:1 column geometry (idx(c) = 4c + o for every destination column): the four outputs of a lane read 16 CONSECUTIVE source
+// pixels, a warp's 128 outputs one contiguous 128*4*CH-byte run per tap row.  The warp fetches that run with fully coalesced
+// 128-bit loads (every sector of the source crosses L1 once), parks it in its private shared-memory strip, and each lane picks its
+// 4*4*CH bytes back with 128-bit loads (48-byte lane stride: conflict-free).  Taps run on dp4a as above.
+template <int CH>
+__global__ void __launch_bounds__(CH == 3 ? 256 : 128) resize_cubic_r4_kernel(const uint8_t* __restrict__ src, size_t src_row_b, uint8_t* __restrict__ dst,
+                                                              size_t dst_row_b, int dst_cols, int col_off, size_t src_valid_b, const TapEntry* __restrict__ yt,
+                                                              const __grid_constant__ UniformCubic u) {
+    constexpr int NW = CH;                 // 16-byte chunks per lane per tap row (4 outputs * 4 taps * CH bytes = 16 * CH)
+    constexpr int ROW_BYTES = 32 * NW * 16;
+    constexpr int WPB = CH == 3 ? 8 : 4;   // warps per block: 48 KB (Rgb) / 32 KB (Rgba) of strips
+    __shared__ __align__(16) uint8_t strip[WPB][4][ROW_BYTES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.y;
+    const int c_base = (blockIdx.x * WPB + warp) * 128;
+    if (c_base >= dst_cols) return;
+    const int4 iy = __ldg(reinterpret_cast<const int4*>(&yt[r]));
+    const int iyv[4] = {iy.x, iy.y, iy.z, iy.w};
+    const size_t run0 = ((size_t)4 * c_base + col_off) * CH;      // first byte of the run inside a source row (multiple of 16)
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        const uint8_t* rowp = src + (size_t)iyv[ky] * src_row_b;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const size_t off = run0 + (size_t)(lane + 32 * i) * 16;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (off + 16 <= src_valid_b) v = __ldg(reinterpret_cast<const uint4*>(rowp + off));   // (row bytes and pitch are multiples of 16)
+            *reinterpret_cast<uint4*>(&strip[warp][ky][(lane + 32 * i) * 16]) = v;
+        }
+    }
+    __syncwarp();
+    int sum[4][CH];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < CH; ++k) sum[j][k] = 0;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        uint32_t w[4 * NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&strip[warp][ky][(lane * NW + i) * 16]);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t* wd = w + j * CH;   // the 4 * CH bytes of output j's taps
+            uint32_t chan[CH];
+            if constexpr (CH == 3) {
+                chan[0] = __byte_perm(__byte_perm(wd[0], wd[1], 0x0630), wd[2], 0x5210);
+                chan[1] = __byte_perm(__byte_perm(wd[0], wd[1], 0x0741), wd[2], 0x6210);
+                chan[2] = __byte_perm(__byte_perm(wd[0], wd[1], 0x0052), wd[2], 0x7410);
+            } else {
+                const uint32_t rg01 = __byte_perm(wd[0], wd[1], 0x5140), rg23 = __byte_perm(wd[2], wd[3], 0x5140);
+                const uint32_t ba01 = __byte_perm(wd[0], wd[1], 0x7362), ba23 = __byte_perm(wd[2], wd[3], 0x7362);
+                chan[0] = __byte_perm(rg01, rg23, 0x5410);
+                chan[1] = __byte_perm(rg01, rg23, 0x7632);
+                chan[2] = __byte_perm(ba01, ba23, 0x5410);
+                chan[3] = __byte_perm(ba01, ba23, 0x7632);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) sum[j][k] = dp4a_u8_s8(chan[k], u.packed[ky], sum[j][k]);
+        }
+    }
+    uint8_t o[4 * CH];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            int q = 0;
+            const int sv = sum[j][k];
+            if (sv > 0) {   // @divTrunc(sum, weight_sum) clamped, as in the kernel above
+                q = __float2int_rz((float)sv * u.rcp);
+                const int rem = sv - q * u.weight_sum;
+                q += rem >= u.weight_sum ? 1 : (rem < 0 ? -1 : 0);
+                q = min(q, 255);
+            }
+            o[j * CH + k] = (uint8_t)q;
+        }
+    const int c0 = c_base + 4 * lane;
+    uint8_t* out = dst + (size_t)r * dst_row_b + (size_t)c0 * CH;
+    if (c0 + 4 <= dst_cols && (((uintptr_t)out) & 3u) == 0) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            reinterpret_cast<uint32_t*>(out)[i] = (uint32_t)o[4 * i] | ((uint32_t)o[4 * i + 1] << 8) | ((uint32_t)o[4 * i + 2] << 16) | ((uint32_t)o[4 * i + 3] << 24);
+    } else {
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < dst_cols)
+                for (int k = 0; k < CH; ++k) out[j * CH + k] = o[j * CH + k];
     }
 }
 
@@ -353,10 +474,34 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
             for (int i = 0; i < 16; ++i) abs_sum += std::llabs((long long)u.w[i]);
             if (uniform && u.weight_sum > 0 && 255 * abs_sum < (1 << 24)) {
                 u.rcp = 1.0f / (float)u.weight_sum;
+                u.dp4a_ok = 1;
+                for (int i = 0; i < 16; ++i) u.dp4a_ok &= (u.w[i] >= -128 && u.w[i] <= 127) ? 1 : 0;
+                for (int ky = 0; ky < 4; ++ky) {
+                    uint32_t pk = 0;
+                    for (int kx = 0; kx < 4; ++kx) pk |= ((uint32_t)(u.w[ky * 4 + kx] & 0xFF)) << (8 * kx);
+                    u.packed[ky] = (int)pk;
+                }
                 dim3 grid(div_up(dst->cols, 256), dst->rows);
                 const int ch = pixfmt == ZB_PIX_RGB8 ? 3 : 4;
                 const size_t sb = (size_t)src->stride * ch, db = (size_t)dst->stride * ch;
                 const size_t src_bytes = (size_t)(src->rows - 1) * sb + (size_t)src->cols * ch;
+                // exact 4:1 columns: idx(c) = 4c + o for every column, 16-byte friendly addresses -> the coalesced strip kernel
+                const size_t valid_b = (size_t)src->cols * ch;
+                bool r4 = u.dp4a_ok && ((uintptr_t)src->data & 15u) == 0 && sb % 16 == 0 && valid_b % 16 == 0;
+                const int o = xt[0].idx[0];
+                r4 = r4 && o >= 0 && ((size_t)o * ch) % 16 == 0;
+                for (size_t c = 0; c < xt.size() && r4; ++c)
+                    for (int k = 0; k < 4; ++k) r4 = r4 && xt[c].idx[k] == (int)(4 * c) + o + k;
+                if (r4) {
+                    dim3 g4(div_up(dst->cols, ch == 3 ? 1024 : 512), dst->rows);
+                    if (ch == 3)
+                        resize_cubic_r4_kernel<3><<<g4, 256, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->cols, o, valid_b, dyt, u);
+                    else
+                        resize_cubic_r4_kernel<4><<<g4, 128, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->cols, o, valid_b, dyt, u);
+                    ZB_LAUNCHED();
+                    t_last_kernel = "resize_cubic_r4_u8";
+                    return ZB_OK;
+                }
                 if (ch == 3)
                     resize_cubic_uniform_kernel<3><<<grid, 256, 0, s>>>((const uint8_t*)src->data, sb, src_bytes, (uint8_t*)dst->data, db,
                                                                         (int)dst->cols, dxt, dyt, u);

@@ -65,6 +65,24 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
     const float x = (float)c;                                   // transforms.zig:199-209
     const float dx = x - p.rcx;
     const float cos_dx = p.cos_a * dx, sin_dx = p.sin_a * dx;   // the two products of this column
+    if constexpr (BORDER_T == ZB_BORDER_ZERO && (METHOD == ZB_INTERP_BILINEAR || METHOD == ZB_INTERP_NEAREST)) {
+        // Most of a rotated frame's bounding box is margin.  Every step of the coordinate formula is a monotone f32 operation of the
+        // row, so the source coordinates of the rows in between lie between those of the first and the last row of this strip: if
+        // both ends are outside the image on the same side (by more than the one-pixel reach of the sampler), the whole strip is zero.
+        const int jl = min(ROT_RPT - 1, dst_rows - 1 - r0);
+        const float dy0 = (float)r0 - p.rcy, dy1 = (float)(r0 + jl) - p.rcy;
+        const float x0 = (cos_dx - p.sin_a * dy0) + p.cx, x1 = (cos_dx - p.sin_a * dy1) + p.cx;
+        const float y0 = (sin_dx + p.cos_a * dy0) + p.cy, y1 = (sin_dx + p.cos_a * dy1) + p.cy;
+        const float fc = (float)img.cols, fr = (float)img.rows;
+        if (fmaxf(x0, x1) < -1.0f || fminf(x0, x1) >= fc || fmaxf(y0, y1) < -1.0f || fminf(y0, y1) >= fr) {
+            const Pix<CT, N> z = zero_px<CT, N>();
+            for (int j = 0; j <= jl; ++j) {
+                store_px<CT, N>(out, 0, z);
+                out += dst_stride * N;
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < ROT_RPT; ++j) {
         if (r0 + j >= dst_rows) break;

@@ -86,6 +86,24 @@ def set_border_zero(img: Image, rect: Rectangle) -> None:
                                    C.c_uint32(max(0, rect.b)), current_stream()))
 
 
+def letterbox_rect(rows: int, cols: int, out_rows: int, out_cols: int):
+    """The content rectangle Image.letterbox computes (transforms.zig:69-97, f32 throughout), or None when both scale factors are
+    exactly equal (the aspect ratios match and the whole output is content)."""
+    rows_scale = np.float32(out_rows) / np.float32(rows)
+    cols_scale = np.float32(out_cols) / np.float32(cols)
+    if rows_scale == cols_scale:
+        return None
+    aspect = min(rows_scale, cols_scale)
+
+    def round_half_away(v: np.float32) -> int:                                   # @round on a non-negative f32
+        return int(np.floor(np.float64(v) + 0.5))
+    scaled_rows = round_half_away(np.float32(aspect * np.float32(rows)))        # :82-83
+    scaled_cols = round_half_away(np.float32(aspect * np.float32(cols)))
+    off_r = max(0, out_rows - scaled_rows) // 2                                  # -| is a saturating subtraction, :86-87
+    off_c = max(0, out_cols - scaled_cols) // 2
+    return Rectangle(off_c, off_r, off_c + scaled_cols, off_r + scaled_rows)
+
+
 def letterbox(image: Image, out: Image, method: Interpolation = Interpolation.BILINEAR) -> Rectangle:
     """Image.letterbox (transforms.zig:46-108): aspect-preserving resize into the centre of `out`, zero padding around it.
     Returns the rectangle of `out` that holds the image content.  One resize into a view plus four strided memsets."""
@@ -98,20 +116,10 @@ def letterbox(image: Image, out: Image, method: Interpolation = Interpolation.BI
     if image.rows == out.rows and image.cols == out.cols:                        # :63-66
         image.copy(out)
         return full
-    rows_scale = np.float32(out.rows) / np.float32(image.rows)
-    cols_scale = np.float32(out.cols) / np.float32(image.cols)
-    if rows_scale == cols_scale:                                                 # :73-76
+    rect = letterbox_rect(image.rows, image.cols, out.rows, out.cols)
+    if rect is None:                                                             # equal scale factors: plain resize, :73-76
         image.resize(out, method)
         return full
-    aspect = min(rows_scale, cols_scale)
-
-    def round_half_away(v: np.float32) -> int:                                   # @round on a non-negative f32
-        return int(np.floor(np.float64(v) + 0.5))
-    scaled_rows = round_half_away(np.float32(aspect * np.float32(image.rows)))  # :82-83
-    scaled_cols = round_half_away(np.float32(aspect * np.float32(image.cols)))
-    off_r = max(0, out.rows - scaled_rows) // 2                                  # -| is a saturating subtraction, :86-87
-    off_c = max(0, out.cols - scaled_cols) // 2
-    rect = Rectangle(off_c, off_r, off_c + scaled_cols, off_r + scaled_rows)
     view = out.view(rect)
     image.resize(view, method)                                                   # :101
     set_border_zero(out, rect)                                                   # :104

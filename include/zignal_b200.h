@@ -180,6 +180,12 @@ int zb_sobel(const zb_image* src, zb_image* dst_u8, int pixfmt, zb_stream s);
 int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
                float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
 
+/* Image.insert(source, rect, angle, method, .none)   transforms.zig:293-376, the complement of extract: `source` (same pixel type as
+ * `self`) is resampled into the rotated rectangle of `self`; pixels outside the rectangle are not touched.  Alpha blending
+ * (Blending != .none) and mixed pixel types are not on this path. */
+int zb_insert(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+              float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, zb_stream s);
+
 /* ------------------------------------------------------------------------------------------------
  * Linear algebra behind fdm / pca
  * ---------------------------------------------------------------------------------------------- */

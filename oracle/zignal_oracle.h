@@ -122,6 +122,9 @@ int zo_rotate_into(const zo_image* src, zo_image* dst, int pixfmt, float angle, 
  * including the copyRect fast path :465-518.  crop (:216-222) = extract(rect, 0, nearest, zero) into round(height) x round(width). */
 int zo_extract(const zo_image* src, zo_image* dst, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
                float sin_a, int method, float mitchell_b, float mitchell_c, int border);
+/* transforms.zig:293-376 (insert) for blend_mode == .none and a source of the destination's pixel type: `self` is modified in place. */
+int zo_insert(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+              float sin_a, int method, float mitchell_b, float mitchell_c);
 /* transforms.zig:522-531 with project() of geometry/transforms.zig:39,147,224.
  * m is row-major: similarity/affine: {m00,m01,m10,m11,b0,b1}; projective: 9 values. */
 int zo_warp(const zo_image* src, zo_image* dst, int pixfmt, int xform_kind, const float* m,

@@ -173,9 +173,72 @@ static void extract(const zo_image* src, zo_image* dst, float rl, float rt, floa
     }
 }
 
+// transforms.zig:293-376 (insert, blend_mode == .none, source and destination of the same pixel type): a gather over the
+// destination pixels of the rotated rectangle's bounding box; pixels outside the rectangle or with a null sample stay untouched.
+template <typename PX>
+static void insert(zo_image* self_img, const zo_image* source_img, float rl, float rt, float rr, float rb, float angle, float cos_a,
+                   float sin_a, int method, float mb, float mc) {
+    using T = typename PX::T;
+    Img<T> self(self_img), source(source_img);
+    if (source.rows == 0 || source.cols == 0) return;
+    const float frows = (float)source.rows, fcols = (float)source.cols;
+    const float rect_width = rl >= rr ? 0.0f : rr - rl, rect_height = rt >= rb ? 0.0f : rb - rt;
+    const float epsilon = 1e-6f;
+    if (std::fabs(angle) < epsilon && std::fabs(rect_width - fcols) < epsilon && std::fabs(rect_height - frows) < epsilon) {
+        const int32_t dst_top = (int32_t)std::round(rt), dst_left = (int32_t)std::round(rl);
+        for (uint32_t r = 0; r < source.rows; ++r) {
+            const int64_t y = (int64_t)dst_top + r;
+            for (uint32_t c = 0; c < source.cols; ++c) {
+                const int64_t x = (int64_t)dst_left + c;
+                if (y >= 0 && y < (int64_t)self.rows && x >= 0 && x < (int64_t)self.cols) self.at((uint32_t)y, (uint32_t)x) = source.at(r, c);
+            }
+        }
+        return;
+    }
+    const float cx = (rl + rr) * 0.5f, cy = (rt + rb) * 0.5f;
+    const float inv_width = 1.0f / rect_width, inv_height = 1.0f / rect_height;
+    const float half_width = rect_width * 0.5f, half_height = rect_height * 0.5f;
+    const float abs_cos = std::fabs(cos_a), abs_sin = std::fabs(sin_a);
+    const float bound_hw = half_width * abs_cos + half_height * abs_sin;
+    const float bound_hh = half_width * abs_sin + half_height * abs_cos;
+    auto to_u32 = [](float v) -> uint32_t { return v <= 0 ? 0u : (v >= 4294967040.0f ? 4294967295u : (uint32_t)v); };
+    const uint32_t min_r = (cy - bound_hh < 0) ? 0u : to_u32(std::floor(cy - bound_hh));
+    const uint32_t max_r = (uint32_t)std::min<uint64_t>(self.rows, (uint64_t)to_u32(std::ceil(cy + bound_hh)) + 1);
+    const uint32_t min_c = (cx - bound_hw < 0) ? 0u : to_u32(std::floor(cx - bound_hw));
+    const uint32_t max_c = (uint32_t)std::min<uint64_t>(self.cols, (uint64_t)to_u32(std::ceil(cx + bound_hw)) + 1);
+    for (uint32_t r = min_r; r < max_r; ++r) {
+        const float dy = (float)r - cy;
+        for (uint32_t c = min_c; c < max_c; ++c) {
+            const float dx = (float)c - cx;
+            const float rect_x = cos_a * dx + sin_a * dy;
+            const float rect_y = -sin_a * dx + cos_a * dy;
+            if (std::fabs(rect_x) > half_width || std::fabs(rect_y) > half_height) continue;
+            const float norm_x = (rect_x + half_width) * inv_width;
+            const float norm_y = (rect_y + half_height) * inv_height;
+            const float src_x = source.cols == 1 ? 0.0f : norm_x * (fcols - 1);
+            const float src_y = source.rows == 1 ? 0.0f : norm_y * (frows - 1);
+            T val;
+            if (interpolate<PX>(source, src_x, src_y, method, mb, mc, ZO_BORDER_MIRROR, &val)) self.at(r, c) = val;
+        }
+    }
+}
+
 }  // namespace zo
 
 extern "C" {
+
+int zo_insert(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a, float sin_a,
+              int method, float mb, float mc) {
+    using namespace zo;
+    switch (pixfmt) {
+        case ZO_PIX_U8: insert<PxU8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+        case ZO_PIX_F32: insert<PxF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGB8: insert<PxRgb8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGBA8: insert<PxRgba8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+        case ZO_PIX_RGBAF32: insert<PxRgbaF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+    }
+    return ZO_ERR_UNSUPPORTED;
+}
 
 int zo_extract(const zo_image* src, zo_image* dst, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
                float sin_a, int method, float mb, float mc, int border) {

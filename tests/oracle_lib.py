@@ -84,6 +84,7 @@ def _declare(L):
     L.zo_rotate_into.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int]
     L.zo_warp.argtypes = [img, img, C.c_int, C.c_int, fp, C.c_int, C.c_float, C.c_float]
     L.zo_extract.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float, C.c_int]
+    L.zo_insert.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float]
     L.zo_svd_f64.argtypes = [dp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
     L.zo_svd_f64.restype = C.c_int64
     L.zo_svd_f32.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, fp, fp, fp]
@@ -261,6 +262,18 @@ def extract(src, out, rect, angle=0.0, method="bilinear", border="zero", cos_sin
     s, d = as_image(src), as_image(out)
     _check(lib().zo_extract(s, d, pixfmt_of(src), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]), C.c_float(a32),
                             C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), INTERP[method], C.c_float(b), C.c_float(c), BORDER[border]), "extract")
+    return out
+
+
+def insert(dest, source, rect, angle=0.0, method="bilinear", cos_sin=None, b=1.0 / 3.0, c=1.0 / 3.0):
+    """dest.insert(source, rect, angle, method, .none) (transforms.zig:293-376); returns the modified copy of dest."""
+    a32 = np.float32(angle)
+    if cos_sin is None:
+        cos_sin = (np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32))
+    out = np.ascontiguousarray(dest).copy()
+    d, s = as_image(out), as_image(source)
+    _check(lib().zo_insert(d, s, pixfmt_of(out), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]), C.c_float(a32),
+                           C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), INTERP[method], C.c_float(b), C.c_float(c)), "insert")
     return out
 
 

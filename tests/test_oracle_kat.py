@@ -532,3 +532,21 @@ def test_sobel_kat():
     e = zo.sobel(img)
     assert e[2, 2] > 200 and e[2, 0] < 50
     assert e[2, 2] == 255 and e[2, 1] == 255 and e[2, 0] == 0 and e[2, 4] == 0     # |gx| = 4 * 255 -> 255 after /4
+
+
+def test_insert_extract_inverse_kat():
+    """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
+    documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""
+    src = ((np.arange(64)[:, None] + np.arange(64)[None, :]) % 256).astype(np.uint8)
+    for rect, angle, size, method in [((10.0, 10.0, 50.0, 50.0), 0.0, 40, "bilinear"), ((15.0, 15.0, 45.0, 45.0), np.pi / 4, 30, "bilinear"),
+                                      ((20.0, 20.0, 40.0, 40.0), 0.0, 40, "bicubic")]:
+        ext = zo.extract(src, np.zeros((size, size), np.uint8), rect, angle, method, "mirror")
+        canvas = zo.insert(np.zeros((64, 64), np.uint8), ext, rect, angle, method)
+        cx, cy = (rect[0] + rect[2]) * 0.5, (rect[1] + rect[3]) * 0.5
+        cs = min(rect[2] - rect[0], rect[3] - rect[1]) * 0.6
+        r0, r1, c0, c1 = int(cy - cs / 2), int(cy + cs / 2), int(cx - cs / 2), int(cx + cs / 2)
+        assert np.abs(src[r0:r1, c0:c1].astype(int) - canvas[r0:r1, c0:c1].astype(int)).mean() < 25
+    base = np.full((20, 20), 7, np.uint8)
+    out = zo.insert(base, np.full((4, 4), 200, np.uint8), (5.0, 5.0, 9.0, 9.0), 0.0, "nearest")
+    assert np.all(out[5:9, 5:9] == 200) and int((out != 7).sum()) == 16
+    assert np.array_equal(zo.insert(base, np.zeros((0, 0), np.uint8), (1.0, 1.0, 5.0, 5.0), 0.3, "bilinear"), base)

@@ -8,6 +8,7 @@
 // warp's source footprint is a ~9x9 pixel patch (8-12 sectors per gather) for any rotation angle instead of a
 // 32-pixel diagonal (one sector per lane).  Compiled with -fmad=false (coordinate math is the
 // reference's unfused f32 sequence, which the u8 outputs depend on bit for bit).
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 
@@ -358,6 +359,106 @@ int extract_dispatch(const zb_image* src, zb_image* dst, int pixfmt, float rl, f
     return ZB_ERR_UNSUPPORTED;
 }
 
+// ---- Image.insert (transforms.zig:293-376), blend_mode .none, same pixel type: the complement of extract -----------------------
+struct InsertParams {
+    float cx, cy, cos_a, sin_a, half_w, half_h, inv_w, inv_h, fcols1, frows1;
+    int copy_rect, dst_top, dst_left;      // fast path: source pixel (r, c) lands on (dst_top + r, dst_left + c)
+    int min_r, min_c, n_r, n_c;            // destination window this launch covers
+    int src_rows, src_cols, method;
+    float mb, mc;
+};
+
+template <typename CT, int N, int METHOD>
+__global__ void __launch_bounds__(256) insert_kernel(SrcView source, CT* __restrict__ self, size_t self_stride, InsertParams p,
+                                                     const float* __restrict__ lut) {
+    const int wc = blockIdx.x * 32 + patch_col(threadIdx.x);
+    const int wr = blockIdx.y * 8 + patch_row(threadIdx.x);
+    if (wc >= p.n_c || wr >= p.n_r) return;
+    const int r = p.min_r + wr, c = p.min_c + wc;   // destination pixel
+    Pix<CT, N> val;
+    if (p.copy_rect) {
+        val = load_px<CT, N>((const CT*)source.data, (size_t)(r - p.dst_top) * source.stride + (size_t)(c - p.dst_left));
+    } else {
+        const float dy = (float)r - p.cy, dx = (float)c - p.cx;
+        const float rect_x = p.cos_a * dx + p.sin_a * dy;        // inverse rotation into rectangle space
+        const float rect_y = -p.sin_a * dx + p.cos_a * dy;
+        if (fabsf(rect_x) > p.half_w || fabsf(rect_y) > p.half_h) return;
+        const float norm_x = (rect_x + p.half_w) * p.inv_w;
+        const float norm_y = (rect_y + p.half_h) * p.inv_h;
+        const float src_x = p.src_cols == 1 ? 0.0f : norm_x * p.fcols1;
+        const float src_y = p.src_rows == 1 ? 0.0f : norm_y * p.frows1;
+        if (!interpolate<CT, N, METHOD, ZB_BORDER_MIRROR>(source, src_x, src_y, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) return;
+    }
+    store_px<CT, N>(self, (size_t)r * self_stride + c, val);
+}
+
+template <typename CT, int N>
+int insert_typed(zb_image* self, const zb_image* source, const InsertParams& p, const float* lut, cudaStream_t s) {
+    SrcView v{source->data, (int)source->rows, (int)source->cols, source->stride};
+    dim3 grid(div_up(p.n_c, 32), div_up(p.n_r, 8));
+    return dispatch_method(p.method, [&](auto m) -> int {
+        insert_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, (CT*)self->data, (size_t)self->stride, p, lut);
+        ZB_LAUNCHED();
+        return ZB_OK;
+    });
+}
+
+int insert_dispatch(zb_image* self, const zb_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+                    float sin_a, int method, float mb, float mc, cudaStream_t s) {
+    if (!self || !source) return ZB_ERR_INVALID_ARGUMENT;
+    if (channels_of(pixfmt) == 0) return ZB_ERR_UNSUPPORTED;
+    if (method < ZB_INTERP_NEAREST || method > ZB_INTERP_LANCZOS) return ZB_ERR_INVALID_ARGUMENT;
+    if (source->rows == 0 || source->cols == 0) return ZB_OK;   // :294
+    if (self->rows == 0 || self->cols == 0) return ZB_OK;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    InsertParams p;
+    memset(&p, 0, sizeof(p));
+    const float frows = (float)source->rows, fcols = (float)source->cols;
+    const float rect_width = rl >= rr ? 0.0f : rr - rl, rect_height = rt >= rb ? 0.0f : rb - rt;
+    const float epsilon = 1e-6f;
+    p.src_rows = (int)source->rows; p.src_cols = (int)source->cols;
+    p.method = method; p.mb = mb; p.mc = mc;
+    long long r0, r1, c0, c1;   // destination window [r0, r1) x [c0, c1)
+    if (std::fabs(angle) < epsilon && std::fabs(rect_width - fcols) < epsilon && std::fabs(rect_height - frows) < epsilon) {   // :305-323
+        p.copy_rect = 1;
+        p.dst_top = (int)std::round(rt);
+        p.dst_left = (int)std::round(rl);
+        r0 = std::max<long long>(0, p.dst_top);
+        r1 = std::min<long long>(self->rows, (long long)p.dst_top + source->rows);
+        c0 = std::max<long long>(0, p.dst_left);
+        c1 = std::min<long long>(self->cols, (long long)p.dst_left + source->cols);
+    } else {
+        p.cx = (rl + rr) * 0.5f; p.cy = (rt + rb) * 0.5f;
+        p.cos_a = cos_a; p.sin_a = sin_a;
+        p.inv_w = 1.0f / rect_width; p.inv_h = 1.0f / rect_height;
+        p.half_w = rect_width * 0.5f; p.half_h = rect_height * 0.5f;
+        p.fcols1 = fcols - 1; p.frows1 = frows - 1;
+        const float abs_cos = std::fabs(cos_a), abs_sin = std::fabs(sin_a);
+        const float bound_hw = p.half_w * abs_cos + p.half_h * abs_sin;   // exact bounding box of the rotated rectangle, :341-349
+        const float bound_hh = p.half_w * abs_sin + p.half_h * abs_cos;
+        auto to_u32 = [](float v) -> long long { return v <= 0 ? 0ll : (v >= 4294967040.0f ? 4294967295ll : (long long)v); };
+        r0 = (p.cy - bound_hh < 0) ? 0 : to_u32(std::floor(p.cy - bound_hh));
+        r1 = std::min<long long>(self->rows, to_u32(std::ceil(p.cy + bound_hh)) + 1);
+        c0 = (p.cx - bound_hw < 0) ? 0 : to_u32(std::floor(p.cx - bound_hw));
+        c1 = std::min<long long>(self->cols, to_u32(std::ceil(p.cx + bound_hw)) + 1);
+    }
+    if (r1 <= r0 || c1 <= c0) return ZB_OK;
+    p.min_r = (int)r0; p.min_c = (int)c0; p.n_r = (int)(r1 - r0); p.n_c = (int)(c1 - c0);
+    const float* lut = nullptr;
+    if (method == ZB_INTERP_LANCZOS && (rc = lanczos_lut_device(&lut, s))) return rc;
+    t_last_kernel = p.copy_rect ? "insert_copy_rect" : "insert_gather";
+    switch (pixfmt) {
+        case ZB_PIX_U8: return insert_typed<uint8_t, 1>(self, source, p, lut, s);
+        case ZB_PIX_F32: return insert_typed<float, 1>(self, source, p, lut, s);
+        case ZB_PIX_RGB8: return insert_typed<uint8_t, 3>(self, source, p, lut, s);
+        case ZB_PIX_RGBA8: return insert_typed<uint8_t, 4>(self, source, p, lut, s);
+        case ZB_PIX_RGBAF32: return insert_typed<float, 4>(self, source, p, lut, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 // interpolation.zig:256-267: lut[i] = lanczosKernel(i / (1024/3), 3) in f32, computed on the host
@@ -424,6 +525,12 @@ int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_i
                          int pixfmt, float angle, float cos_a, float sin_a, int method, float mb, float mc, int border, zb_stream s) {
     if (n_images > 65535) return ZB_ERR_INVALID_ARGUMENT;
     return rotate_dispatch(src0, src_image_pitch_px, dst0, dst_image_pitch_px, n_images, pixfmt, angle, cos_a, sin_a, method, mb, mc, border,
+                           (cudaStream_t)s);
+}
+
+int zb_insert(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+              float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, zb_stream s) {
+    return insert_dispatch(self, source, pixfmt, rect_l, rect_t, rect_r, rect_b, angle, cos_a, sin_a, method, mitchell_b, mitchell_c,
                            (cudaStream_t)s);
 }
 

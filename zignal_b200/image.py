@@ -286,6 +286,16 @@ class Image:
                                current_stream()))
         return out
 
+    def insert(self, source: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
+               b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        """Image.insert(source, rect, angle, method, .none) (transforms.zig:293-376): modifies self in place."""
+        a32 = np.float32(angle)
+        cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
+        d, s = self._zb(), source._zb()
+        check(lib().zb_insert(d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                              C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        return self
+
     def crop(self, rect) -> "Image":
         """Image.crop (transforms.zig:216-222): round(height) x round(width) chip, out-of-bounds pixels zero."""
         def rnd(v):  # @round on f32, half away from zero

@@ -33,6 +33,12 @@ pub const c = struct {
     pub extern fn zb_rotate_bounds(rows: u32, cols: u32, angle: f32, out_rows: *u32, out_cols: *u32) c_int;
     pub extern fn zb_rotate_into_cs(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, angle: f32, cos_a: f32, sin_a: f32, method: c_int, b: f32, cc: f32, border: c_int, s: Stream) c_int;
     pub extern fn zb_warp(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, kind: c_int, m: [*]const f32, method: c_int, b: f32, cc: f32, s: Stream) c_int;
+    // widening rows (SURVEY 8f): extract / crop, insert (.none), sobel, setBorder(zeroes), and the sharding extension
+    pub extern fn zb_extract(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, border: c_int, s: Stream) c_int;
+    pub extern fn zb_insert(self: *ZbImage, source: *const ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, s: Stream) c_int;
+    pub extern fn zb_sobel(src: *const ZbImage, dst_u8: *ZbImage, pixfmt: c_int, s: Stream) c_int;
+    pub extern fn zb_set_border_zero(img: *ZbImage, pixfmt: c_int, l: u32, t: u32, r: u32, b: u32, s: Stream) c_int;
+    pub extern fn zb_conv_separable_rows(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, kx: [*]const f32, nx: c_int, ky: [*]const f32, ny: c_int, border: c_int, row_begin: u32, row_end: u32, s: Stream) c_int;
 
     // host-pointer twins: Image.data in host memory, H2D + op + D2H inside the call
     pub extern fn zb_host_gaussian_blur(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, sigma: f32) c_int;

@@ -134,10 +134,10 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     mask = np.ones(full.shape[:2], bool)
     mask[2:187, 3:287] = False
     assert np.all(full[mask] == 9)
-    # a view that breaks TMA alignment (offset 3 px) and taps that need i64 accumulators fall back to the generic path
+    # a view that breaks TMA alignment (offset 3 px) takes the shared-memory tile kernel; taps that need i64 accumulators the two-pass path
     v2 = big.view(zb.Rectangle(3, 0, 299, 100))
     got = v2.convolve_separable(kx, ky, zb.BorderMode.WRAP).to_numpy()
-    assert L.zb_last_kernel().decode() == "sep_generic_u8"
+    assert L.zb_last_kernel().decode() == "sep_tile_u8"
     assert np.array_equal(got, zo.conv_separable(np.ascontiguousarray(img[0:100, 3:299]), kx, ky, "wrap"))
     huge = (rng.standard_normal(5) * 3000).astype(np.float32)
     got = big.convolve_separable(huge, huge, zb.BorderMode.MIRROR).to_numpy()
@@ -316,6 +316,40 @@ def test_row_block_conv_single_rank(zb):
             torch.cuda.synchronize()
             want = zb.Image.from_numpy(img).convolve_separable(taps, taps, border).to_numpy()
             assert np.array_equal(ob.interior_tensor().cpu().numpy(), want), (halo, border)
+
+
+@pytest.mark.parametrize("shape", [(70, 131), (129, 257, 3), (200, 90, 3), (65, 300, 4), (33, 1000)])
+@pytest.mark.parametrize("border", BORDERS)
+def test_tile_u8_kernel_against_oracle_and_two_pass(zb, shape, border):
+    """The single-pass tile kernel for 8-bit images of any channel count / alignment: odd and even tap counts, different x / y
+    kernels, every border mode, strided views -- bit-identical to the oracle and to the two-pass path."""
+    L = zb.lib()
+    rng = np.random.default_rng(shape[0] + shape[1])
+    img = rand_image(rng, shape, np.uint8)
+    dev = zb.Image.from_numpy(img)
+    bm = border_enum(zb, border)
+    for nx, ny in [(3, 3), (15, 15), (4, 9), (1, 7), (31, 2), (5, 29)]:
+        kx, ky = _taps(rng, nx), _taps(rng, ny)
+        got = dev.convolve_separable(kx, ky, bm).to_numpy()
+        name = L.zb_last_kernel().decode()
+        assert name == "sep_tile_u8" or (name.startswith("fused_sep_rgba8") and len(shape) == 3 and shape[2] == 4), (nx, ny, name)
+        assert np.array_equal(got, zo.conv_separable(img, kx, ky, border)), (nx, ny)
+    L.zb_set_force_generic(1)
+    try:
+        kx, ky = _taps(rng, 11), _taps(rng, 7)
+        two_pass = dev.convolve_separable(kx, ky, bm).to_numpy()
+    finally:
+        L.zb_set_force_generic(0)
+    assert np.array_equal(dev.convolve_separable(kx, ky, bm).to_numpy(), two_pass)
+    # strided source and destination views
+    v = dev.view(zb.Rectangle(2, 3, shape[1] - 3, shape[0] - 1))
+    out = zb.Image.from_numpy(np.full(shape, 5, np.uint8))
+    ov = out.view(zb.Rectangle(2, 3, shape[1] - 3, shape[0] - 1))
+    v.convolve_separable(kx, ky, bm, out=ov)
+    res = out.to_numpy()
+    assert np.array_equal(res[3:shape[0] - 1, 2:shape[1] - 3], zo.conv_separable(np.ascontiguousarray(img[3:shape[0] - 1, 2:shape[1] - 3]), kx, ky, border))
+    res[3:shape[0] - 1, 2:shape[1] - 3] = 5
+    assert np.all(res == 5)
 
 
 def test_golden_fixtures(zb):

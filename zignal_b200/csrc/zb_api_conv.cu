@@ -39,7 +39,13 @@ int conv_separable_dispatch(const zb_image* src, zb_image* dst, int pixfmt, cons
         rc = conv_separable_fused_rgba8(src, dst, kx, nx, ky, ny, border, s, row0, row1);
         if (rc != ZB_ERR_UNSUPPORTED) return rc;
     }
-    if (row0 == 0 && row1 == (int)src->rows) return conv_separable_generic(src, dst, pixfmt, kx, nx, ky, ny, border, s);
+    if (row0 == 0 && row1 == (int)src->rows) {
+        if ((pixfmt == ZB_PIX_U8 || pixfmt == ZB_PIX_RGB8 || pixfmt == ZB_PIX_RGBA8) && !g_force_generic.load()) {
+            rc = conv_separable_tile_u8(src, dst, channels_of(pixfmt), kx, nx, ky, ny, border, s);
+            if (rc != ZB_ERR_UNSUPPORTED) return rc;
+        }
+        return conv_separable_generic(src, dst, pixfmt, kx, nx, ky, ny, border, s);
+    }
     // two-pass path: it has no row window, so convolve into scratch and keep the requested rows
     const size_t pb = pixel_bytes(pixfmt);
     Scratch tmp;

@@ -23,4 +23,8 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
 int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
                                cudaStream_t s, int row0 = 0, int row1 = -1);
 
+// zb_conv_tile_u8.cu: single-pass (shared-memory tile) separable convolution of any 8-bit format / alignment / border mode.
+int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, const float* kx, int nx, const float* ky, int ny, int border,
+                           cudaStream_t s);
+
 }  // namespace zb

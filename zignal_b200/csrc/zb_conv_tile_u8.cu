@@ -1,0 +1,176 @@
+// zb_conv_tile_u8.cu -- single-pass separable convolution for 8-bit images of ANY channel count (gray, Rgb, Rgba) and any
+// alignment, border mode and view stride: the fallback between the TMA kernel (zb_conv_fused_u8.cu: Rgba only, 16-byte
+// friendly) and the two-pass path (zb_conv_generic.cu: i32 temp plane through HBM, 10 bytes of traffic per byte of image).
+//
+// Reference semantics (convolution.zig:340-431, :441-647): Q8 taps round(k*256), horizontal pass into an i32 temp (not
+// rounded), vertical pass, one divClampU8(65536).  Integer sums are order-independent, so the tile decomposition changes no bit
+// as long as nothing overflows; the host proves that for i32 (otherwise the two-pass path with i64 accumulators runs).
+//
+// A row of interleaved pixels is treated as a stream of BYTES: output byte b of a row is sum_i in[b + CH*(i - half)] * kx[i],
+// i.e. the channel structure is nothing but a tap stride of CH bytes.  One CTA produces a TH-row x 256-byte tile:
+//   load : (TH + 2*half) rows x (256 + 2*half*CH) bytes into shared memory, border-resolved per pixel (resolveIndex);
+//   H    : thread t owns output byte column t: for every tile row, K taps of (byte load + integer multiply-add) with the taps
+//          as immediate constant-bank operands (the kernel is specialised on `half`), into an i32 tile in shared memory;
+//   V    : thread t owns byte column t: for every output row, K taps down the i32 tile, divClampU8, byte store.
+// HBM traffic: ~1.3 bytes read + 1 written per image byte.
+#include <cstdlib>
+
+#include "zb_conv.h"
+#include "zb_device.cuh"
+
+namespace zb {
+
+namespace {
+
+constexpr int TWB = 256;          // output bytes per tile row = threads per CTA
+constexpr int TU_MAX_HALF = 15;
+
+struct TileParams {
+    int kx[2 * TU_MAX_HALF + 1];   // taps aligned to the common half-width (zero padded)
+    int ky[2 * TU_MAX_HALF + 1];
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t src_pitch, dst_pitch;   // bytes
+    int rows, cols, row_bytes, border;
+};
+
+template <int CH, int HALF>
+__global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant__ TileParams p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int TH = HALF <= 7 ? 64 : 32;                 // output rows per tile
+    constexpr int IR = TH + 2 * HALF;                       // tile rows held in shared memory
+    constexpr int IW = (TWB + 2 * HALF * CH + 3) & ~3;      // input bytes per tile row
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* tmp = reinterpret_cast<int*>(smem);                // [IR][TWB] horizontal sums
+    uint8_t* in = smem + (size_t)IR * TWB * sizeof(int);    // [IR][IW]  border-resolved source bytes
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.x * TWB;                        // first output byte of the tile within a row
+    const int y0 = blockIdx.y * TH;                         // first output row
+
+    // ---- load: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position (b0 + tb - HALF*CH), border-resolved
+    for (int tr = 0; tr < IR; ++tr) {
+        const int ry = resolve_index(y0 + tr - HALF, p.rows, p.border);
+        const uint8_t* rowp = p.src + (size_t)(ry < 0 ? 0 : ry) * p.src_pitch;
+        for (int tb = t; tb < IW; tb += TWB) {
+            const int gb = b0 + tb - HALF * CH;
+            uint8_t v = 0;
+            if (ry >= 0) {
+                if (gb >= 0 && gb < p.row_bytes) {
+                    v = rowp[gb];
+                } else {
+                    // outside the row: which pixel / channel would this byte be, and where does the border mode send the pixel
+                    const int px = gb >= 0 ? gb / CH : -((-gb + CH - 1) / CH);     // floor division
+                    const int chn = gb - px * CH;
+                    const int rx = resolve_index(px, p.cols, p.border);
+                    if (rx >= 0) v = rowp[(size_t)rx * CH + chn];
+                }
+            }
+            in[tr * IW + tb] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal pass: tmp[tr][t] = sum_i in[tr][t + i*CH] * kx[i]
+#pragma unroll 2
+    for (int tr = 0; tr < IR; ++tr) {
+        const uint8_t* q = in + tr * IW + t;
+        int acc = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc += (int)q[i * CH] * p.kx[i];
+        tmp[tr * TWB + t] = acc;
+    }
+    __syncthreads();
+
+    // ---- vertical pass: out[y0 + r][b0 + t] = divClampU8(sum_j tmp[r + j][t] * ky[j], 65536)
+    if (b0 + t < p.row_bytes) {
+        const int nrows = min(TH, p.rows - y0);
+        uint8_t* out = p.dst + (size_t)y0 * p.dst_pitch + (size_t)(b0 + t);
+#pragma unroll 2
+        for (int r = 0; r < nrows; ++r) {
+            const int* q = tmp + r * TWB + t;
+            int acc = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc += q[j * TWB] * p.ky[j];
+            out[(size_t)r * p.dst_pitch] = div_clamp_u8<int>(acc, 65536);
+        }
+    }
+}
+
+template <int CH, int HALF>
+int launch_tile(const TileParams& p, cudaStream_t s) {
+    constexpr int TH = HALF <= 7 ? 64 : 32;
+    constexpr int IR = TH + 2 * HALF;
+    constexpr int IW = (TWB + 2 * HALF * CH + 3) & ~3;
+    constexpr int smem = IR * TWB * (int)sizeof(int) + IR * IW;
+    auto k = sep_tile_u8_kernel<CH, HALF>;
+    if (smem > 48 * 1024) ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(div_up((size_t)p.row_bytes, TWB), div_up((size_t)p.rows, TH));
+    k<<<grid, TWB, smem, s>>>(p);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+template <int CH>
+int launch_half(int half, const TileParams& p, cudaStream_t s) {
+    switch (half) {
+        case 1: return launch_tile<CH, 1>(p, s);
+        case 2: return launch_tile<CH, 2>(p, s);
+        case 3: return launch_tile<CH, 3>(p, s);
+        case 4: return launch_tile<CH, 4>(p, s);
+        case 5: return launch_tile<CH, 5>(p, s);
+        case 6: return launch_tile<CH, 6>(p, s);
+        case 7: return launch_tile<CH, 7>(p, s);
+        case 8: return launch_tile<CH, 8>(p, s);
+        case 9: return launch_tile<CH, 9>(p, s);
+        case 10: return launch_tile<CH, 10>(p, s);
+        case 11: return launch_tile<CH, 11>(p, s);
+        case 12: return launch_tile<CH, 12>(p, s);
+        case 13: return launch_tile<CH, 13>(p, s);
+        case 14: return launch_tile<CH, 14>(p, s);
+        case 15: return launch_tile<CH, 15>(p, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Returns ZB_ERR_UNSUPPORTED outside its envelope (the caller then runs the two-pass path).
+int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, const float* kx, int nx, const float* ky, int ny, int border,
+                           cudaStream_t s) {
+    if (channels != 1 && channels != 3 && channels != 4) return ZB_ERR_UNSUPPORTED;
+    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;                         // in place: the temp-plane path
+    const int half_x = nx / 2, half_y = ny / 2;
+    const int half = half_x > half_y ? half_x : half_y;
+    if (half < 1 || half > TU_MAX_HALF) return ZB_ERR_UNSUPPORTED;
+    if ((uint64_t)src->cols * channels >= (1u << 30) || src->rows >= (1u << 30)) return ZB_ERR_UNSUPPORTED;
+    TileParams p;
+    memset(&p, 0, sizeof(p));
+    long long sax = 0, say = 0;
+    for (int i = 0; i < nx; ++i) {   // Q8 taps, convolution.zig:303-309; tap i acts at offset i - n/2 (:527,542)
+        const int q = (int)roundf(kx[i] * 256.0f);
+        p.kx[i + (half - half_x)] = q;
+        sax += llabs((long long)q);
+    }
+    for (int i = 0; i < ny; ++i) {
+        const int q = (int)roundf(ky[i] * 256.0f);
+        p.ky[i + (half - half_y)] = q;
+        say += llabs((long long)q);
+    }
+    if (sax * 255 * say + 32768 >= 2147483647LL) return ZB_ERR_UNSUPPORTED;        // i32 accumulators must be provably safe
+    p.src = (const uint8_t*)src->data;
+    p.dst = (uint8_t*)dst->data;
+    p.src_pitch = (size_t)src->stride * channels;
+    p.dst_pitch = (size_t)dst->stride * channels;
+    p.rows = (int)src->rows;
+    p.cols = (int)src->cols;
+    p.row_bytes = p.cols * channels;
+    p.border = border;
+    t_last_kernel = "sep_tile_u8";
+    switch (channels) {
+        case 1: return launch_half<1>(half, p, s);
+        case 3: return launch_half<3>(half, p, s);
+        default: return launch_half<4>(half, p, s);
+    }
+}
+
+}  // namespace zb

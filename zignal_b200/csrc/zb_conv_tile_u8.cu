@@ -105,6 +105,7 @@ int launch_tile(const TileParams& p, cudaStream_t s) {
     auto k = sep_tile_u8_kernel<CH, HALF>;
     if (smem > 48 * 1024) ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(div_up((size_t)p.row_bytes, TWB), div_up((size_t)p.rows, TH));
+    if (grid.y > 65535u) return ZB_ERR_UNSUPPORTED;   // (more than 2M rows: the two-pass path)
     k<<<grid, TWB, smem, s>>>(p);
     ZB_LAUNCHED();
     return ZB_OK;

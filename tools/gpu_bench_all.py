@@ -53,12 +53,21 @@ del x, s, d
 # RGBA8 blur (the reference's most common real type)
 x = torch.randint(0, 256, (8192, 8192, 4), device="cuda", dtype=torch.uint8, generator=g)
 s, d = Image.from_tensor(x), Image.from_tensor(torch.empty_like(x))
-rec("gaussian 15x15 8192^2 RGBA u8", time_it(lambda: s.gaussian_blur(2.25, out=d)), 2 * x.numel(), 8192 * 8192, "integer-pipe bound (120 IMAD/px)")
+rec("gaussian 15x15 8192^2 RGBA u8", time_it(lambda: s.gaussian_blur(2.25, out=d)), 2 * x.numel(), 8192 * 8192, "issue bound (120 MAC/px on the FP32 pipe)")
 rec("boxBlur r=3 8192^2 RGBA u8", time_it(lambda: s.box_blur(3, out=d), n=5, warm=1), 2 * x.numel(), 8192 * 8192)
 rec("sharpen r=3 8192^2 RGBA u8", time_it(lambda: s.sharpen(3, out=d), n=5, warm=1), 2 * x.numel(), 8192 * 8192)
 k3 = np.full((3, 3), 1 / 9, np.float32)
 rec("convolve 3x3 8192^2 RGBA u8", time_it(lambda: s.convolve(k3, BorderMode.MIRROR, out=d), n=5, warm=1), 2 * x.numel(), 8192 * 8192)
 del x, s, d
+# Rgb / gray u8 blur (shared-memory tile kernel) and Sobel
+for shp, name in (((8192, 8192, 3), "RGB u8"), ((8192, 8192), "gray u8")):
+    x = torch.randint(0, 256, shp, device="cuda", dtype=torch.uint8, generator=g)
+    s, d = Image.from_tensor(x), Image.from_tensor(torch.empty_like(x))
+    rec(f"gaussian 15x15 8192^2 {name}", time_it(lambda: s.gaussian_blur(2.25, out=d), n=5, warm=1), 2 * x.numel(), 8192 * 8192)
+    if len(shp) == 2:
+        e = Image.from_tensor(torch.empty_like(x))
+        rec("sobel 8192^2 gray u8", time_it(lambda: s.sobel(out=e), n=5, warm=1), 2 * x.numel(), 8192 * 8192, "luma plane + two 3x3 f32 convolutions + magnitude")
+    del x, s, d
 # C3
 x = torch.randint(0, 256, (16384, 16384, 3), device="cuda", dtype=torch.uint8, generator=g)
 big = Image.from_tensor(x)

@@ -9,9 +9,11 @@
 // A row of interleaved pixels is treated as a stream of BYTES: output byte b of a row is sum_i in[b + CH*(i - half)] * kx[i],
 // i.e. the channel structure is nothing but a tap stride of CH bytes.  One CTA produces a TH-row x 256-byte tile:
 //   load : (TH + 2*half) rows x (256 + 2*half*CH) bytes into shared memory, border-resolved per pixel (resolveIndex);
-//   H    : thread t owns output byte column t: for every tile row, K taps of (byte load + integer multiply-add) with the taps
-//          as immediate constant-bank operands (the kernel is specialised on `half`), into an i32 tile in shared memory;
-//   V    : thread t owns byte column t: for every output row, K taps down the i32 tile, divClampU8, byte store.
+//   H    : a thread produces runs of 8 consecutive bytes of a tile row from one set of 64-bit loads; every tap is a compile-time
+//          byte extract + integer multiply-add with the tap as an immediate constant-bank operand (the kernel is specialised on
+//          `half`); results go to an i32 tile in shared memory;
+//   V    : thread t owns byte column t and walks down it with a K-deep register window (one shared load per output row),
+//          divClampU8, byte store.
 // HBM traffic: ~1.3 bytes read + 1 written per image byte.
 #include <cstdlib>
 
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant_
     constexpr int K = 2 * HALF + 1;
     constexpr int TH = HALF <= 7 ? 64 : 32;                 // output rows per tile
     constexpr int IR = TH + 2 * HALF;                       // tile rows held in shared memory
-    constexpr int IW = (TWB + 2 * HALF * CH + 3) & ~3;      // input bytes per tile row
+    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;      // input bytes per tile row (8-byte granular: 64-bit loads in the H pass)
     extern __shared__ __align__(16) unsigned char smem[];
     int* tmp = reinterpret_cast<int*>(smem);                // [IR][TWB] horizontal sums
     uint8_t* in = smem + (size_t)IR * TWB * sizeof(int);    // [IR][IW]  border-resolved source bytes
@@ -47,51 +49,115 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant_
     const int b0 = blockIdx.x * TWB;                        // first output byte of the tile within a row
     const int y0 = blockIdx.y * TH;                         // first output row
 
-    // ---- load: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position (b0 + tb - HALF*CH), border-resolved
-    for (int tr = 0; tr < IR; ++tr) {
-        const int ry = resolve_index(y0 + tr - HALF, p.rows, p.border);
-        const uint8_t* rowp = p.src + (size_t)(ry < 0 ? 0 : ry) * p.src_pitch;
-        for (int tb = t; tb < IW; tb += TWB) {
+    // ---- load: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position (b0 + tb - HALF*CH), border-resolved.
+    // LB rows are fetched per batch so that 2*LB independent global loads are in flight before the first shared-memory store
+    // (one load per iteration would expose the full memory latency IR times per tile).
+    {
+        constexpr int LB = 8;
+        constexpr int NCOL = (IW + TWB - 1) / TWB;   // byte columns per thread (2)
+        // the pixel / channel of this thread's byte columns and where the border sends them: row independent, computed once
+        int gcol[NCOL];    // resolved byte position inside a source row, or -1 (zero)
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+            const int tb = t + k * TWB;
             const int gb = b0 + tb - HALF * CH;
-            uint8_t v = 0;
-            if (ry >= 0) {
+            int g = -1;
+            if (tb < IW) {
                 if (gb >= 0 && gb < p.row_bytes) {
-                    v = rowp[gb];
+                    g = gb;
                 } else {
-                    // outside the row: which pixel / channel would this byte be, and where does the border mode send the pixel
                     const int px = gb >= 0 ? gb / CH : -((-gb + CH - 1) / CH);     // floor division
                     const int chn = gb - px * CH;
                     const int rx = resolve_index(px, p.cols, p.border);
-                    if (rx >= 0) v = rowp[(size_t)rx * CH + chn];
+                    if (rx >= 0) g = rx * CH + chn;
                 }
             }
-            in[tr * IW + tb] = v;
+            gcol[k] = g;
+        }
+        for (int tr0 = 0; tr0 < IR; tr0 += LB) {
+            uint8_t v[LB][NCOL];
+#pragma unroll
+            for (int u = 0; u < LB; ++u) {
+                const int tr = tr0 + u;
+                const int ry = tr < IR ? resolve_index(y0 + tr - HALF, p.rows, p.border) : -1;
+                const uint8_t* rowp = p.src + (size_t)(ry < 0 ? 0 : ry) * p.src_pitch;
+#pragma unroll
+                for (int k = 0; k < NCOL; ++k) v[u][k] = (ry >= 0 && gcol[k] >= 0) ? __ldg(rowp + gcol[k]) : (uint8_t)0;
+            }
+#pragma unroll
+            for (int u = 0; u < LB; ++u) {
+                const int tr = tr0 + u;
+                if (tr < IR) {
+#pragma unroll
+                    for (int k = 0; k < NCOL; ++k)
+                        if (t + k * TWB < IW) in[tr * IW + t + k * TWB] = v[u][k];
+                }
+            }
         }
     }
     __syncthreads();
 
-    // ---- horizontal pass: tmp[tr][t] = sum_i in[tr][t + i*CH] * kx[i]
-#pragma unroll 2
-    for (int tr = 0; tr < IR; ++tr) {
-        const uint8_t* q = in + tr * IW + t;
-        int acc = 0;
+    // ---- horizontal pass: tmp[tr][b] = sum_i in[tr][b + i*CH] * kx[i].  A thread produces a run of 8 consecutive bytes of one tile
+    // row from ONE set of 64-bit shared-memory loads (the 8 + 2*HALF*CH bytes the run touches); every tap byte is then a compile-time
+    // byte extract.  9x fewer shared-memory instructions than one byte load per tap, which is what bounded the first version.
+    {
+        constexpr int SPAN = 8 + 2 * HALF * CH;          // bytes a run reads
+        constexpr int NQ = (SPAN + 7) / 8;               // 64-bit words
+        for (int idx = t; idx < IR * (TWB / 8); idx += TWB) {
+            const int tr = idx / (TWB / 8), run = idx % (TWB / 8);
+            const unsigned long long* q = reinterpret_cast<const unsigned long long*>(in + tr * IW + 8 * run);
+            unsigned long long w[NQ];
 #pragma unroll
-        for (int i = 0; i < K; ++i) acc += (int)q[i * CH] * p.kx[i];
-        tmp[tr * TWB + t] = acc;
+            for (int i = 0; i < NQ; ++i) w[i] = (8 * run + 8 * i < IW) ? q[i] : 0ull;
+            int acc[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m] = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int o = m + i * CH;   // byte offset inside the span: static
+                    acc[m] += (int)((w[o >> 3] >> (8 * (o & 7))) & 0xFFull) * p.kx[i];
+                }
+            int4* dsts = reinterpret_cast<int4*>(tmp + tr * TWB + 8 * run);
+            dsts[0] = make_int4(acc[0], acc[1], acc[2], acc[3]);
+            dsts[1] = make_int4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
     __syncthreads();
 
-    // ---- vertical pass: out[y0 + r][b0 + t] = divClampU8(sum_j tmp[r + j][t] * ky[j], 65536)
+    // ---- vertical pass: out[y0 + r][b0 + t] = divClampU8(sum_j tmp[r + j][t] * ky[j], 65536); thread t walks down byte column t
     if (b0 + t < p.row_bytes) {
         const int nrows = min(TH, p.rows - y0);
         uint8_t* out = p.dst + (size_t)y0 * p.dst_pitch + (size_t)(b0 + t);
-#pragma unroll 2
-        for (int r = 0; r < nrows; ++r) {
-            const int* q = tmp + r * TWB + t;
-            int acc = 0;
+        if constexpr (K <= 15) {
+            // sliding window in registers: one new shared-memory value per output row instead of K (unrolled K-fold so that the
+            // rotating window indices are compile-time)
+            int win[K];
 #pragma unroll
-            for (int j = 0; j < K; ++j) acc += q[j * TWB] * p.ky[j];
-            out[(size_t)r * p.dst_pitch] = div_clamp_u8<int>(acc, 65536);
+            for (int j = 0; j < K - 1; ++j) win[j] = tmp[j * TWB + t];
+            for (int r0 = 0; r0 < nrows; r0 += K) {
+#pragma unroll
+                for (int rr = 0; rr < K; ++rr) {
+                    const int r = r0 + rr;
+                    if (r < nrows) {
+                        win[(rr + K - 1) % K] = tmp[(r + K - 1) * TWB + t];
+                        int acc = 0;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) acc += win[(rr + j) % K] * p.ky[j];
+                        out[(size_t)r * p.dst_pitch] = div_clamp_u8<int>(acc, 65536);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < nrows; ++r) {
+                const int* q = tmp + r * TWB + t;
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < K; ++j) acc += q[j * TWB] * p.ky[j];
+                out[(size_t)r * p.dst_pitch] = div_clamp_u8<int>(acc, 65536);
+            }
         }
     }
 }
@@ -100,7 +166,7 @@ template <int CH, int HALF>
 int launch_tile(const TileParams& p, cudaStream_t s) {
     constexpr int TH = HALF <= 7 ? 64 : 32;
     constexpr int IR = TH + 2 * HALF;
-    constexpr int IW = (TWB + 2 * HALF * CH + 3) & ~3;
+    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;
     constexpr int smem = IR * TWB * (int)sizeof(int) + IR * IW;
     auto k = sep_tile_u8_kernel<CH, HALF>;
     if (smem > 48 * 1024) ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

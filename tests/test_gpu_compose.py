@@ -86,7 +86,15 @@ def test_sobel(zb, shape, dtype):
     if dtype == np.float32:
         img = (img * 255.0).astype(np.float32)     # float scalars pass through un-normalised (edges.zig:38-48)
     got = zb.Image.from_numpy(img).sobel().to_numpy()
+    assert zb.lib().zb_last_kernel().decode() == "sobel_fused"
     assert np.array_equal(got, zo.sobel(img))
+    zb.lib().zb_set_force_generic(1)          # the three-kernel composition must agree with the one-pass kernel
+    try:
+        comp = zb.Image.from_numpy(img).sobel().to_numpy()
+        assert zb.lib().zb_last_kernel().decode() == "sobel"
+    finally:
+        zb.lib().zb_set_force_generic(0)
+    assert np.array_equal(comp, got)
     step = np.tile(np.where(np.arange(5) < 2, 0, 255).astype(np.uint8), (5, 1))    # the reference's own test image
     e = zb.Image.from_numpy(step).sobel().to_numpy()
     assert e[2, 2] > 200 and e[2, 0] < 50

@@ -39,6 +39,44 @@ __global__ void __launch_bounds__(256) sobel_magnitude_kernel(const float* __res
     dst[(size_t)r * dst_stride + c] = (uint8_t)truncf(fmaxf(0.0f, fminf(255.0f, scaled))); // :69
 }
 
+// The whole of edges.zig:33-73 in one pass over the image: 9 border-replicated luma samples, both 3x3 correlations with the dense
+// convolution's accumulation (acc = acc + px*k, separately rounded, taps in row-major order, zero taps included), magnitude.
+// Reads the source once and writes one byte per pixel; values are identical to the composition above by construction.
+template <int CH, bool IS_FLOAT>
+__global__ void __launch_bounds__(256) sobel_fused_kernel(const void* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
+                                                          size_t dst_stride, int rows, int cols) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= cols || r >= rows) return;
+    auto luma = [&](int y, int x) -> float {
+        y = min(max(y, 0), rows - 1);   // .replicate
+        x = min(max(x, 0), cols - 1);
+        if constexpr (IS_FLOAT) {
+            return ((const float*)src)[(size_t)y * src_stride + x];
+        } else if constexpr (CH == 1) {
+            return (float)((const uint8_t*)src)[(size_t)y * src_stride + x];
+        } else {
+            const uint8_t* px = (const uint8_t*)src + ((size_t)y * src_stride + x) * CH;
+            const int v = (13933 * (int)px[0] + 46871 * (int)px[1] + 4732 * (int)px[2] + 32768) >> 16;   // rgbToGray(u8)
+            return (float)min(max(v, 0), 255);
+        }
+    };
+    const float kx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};   // edges.zig:14-18
+    const float ky[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};   // :21-25
+    float gx = 0.0f, gy = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float v = luma(r + j - 1, c + i - 1);
+            gx = mul_add_unfused(v, kx[3 * j + i], gx);
+            gy = mul_add_unfused(v, ky[3 * j + i], gy);
+        }
+    const float magnitude = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+    const float scaled = __fdiv_rn(magnitude, 4.0f);
+    dst[(size_t)r * dst_stride + c] = (uint8_t)truncf(fmaxf(0.0f, fminf(255.0f, scaled)));
+}
+
 }  // namespace
 }  // namespace zb
 
@@ -54,6 +92,19 @@ extern "C" int zb_sobel(const zb_image* src, zb_image* dst, int pixfmt, zb_strea
     int rc = device_info(&di);
     if (rc) return rc;
     const int rows = (int)src->rows, cols = (int)src->cols;
+    if (!g_force_generic.load()) {   // one pass; the composition below stays as the cross-check (zb_set_force_generic)
+        dim3 g2(div_up(cols, 32), div_up(rows, 8));
+        uint8_t* dp = (uint8_t*)dst->data;
+        switch (pixfmt) {
+            case ZB_PIX_F32: sobel_fused_kernel<1, true><<<g2, 256, 0, s>>>(src->data, src->stride, dp, dst->stride, rows, cols); break;
+            case ZB_PIX_U8: sobel_fused_kernel<1, false><<<g2, 256, 0, s>>>(src->data, src->stride, dp, dst->stride, rows, cols); break;
+            case ZB_PIX_RGB8: sobel_fused_kernel<3, false><<<g2, 256, 0, s>>>(src->data, src->stride, dp, dst->stride, rows, cols); break;
+            default: sobel_fused_kernel<4, false><<<g2, 256, 0, s>>>(src->data, src->stride, dp, dst->stride, rows, cols); break;
+        }
+        ZB_LAUNCHED();
+        t_last_kernel = "sobel_fused";
+        return ZB_OK;
+    }
     const size_t plane = (size_t)rows * cols * sizeof(float);
     Scratch buf;
     if ((rc = buf.alloc(3 * plane, s))) return rc;

@@ -250,12 +250,6 @@ __global__ void __launch_bounds__(128) box_checkpoints(const BoxParams p) {
 }
 
 // ---- 3. chains from the checkpoint, SAT ring, evaluation ---------------------------------------------------------------------
-// correctly rounded s / area from a correctly rounded reciprocal: two Markstein corrections (q1 is faithful, q2 exact)
-__device__ __forceinline__ float div_exact(float s, float area, float rcp) {
-    const float q0 = __fmul_rn(s, rcp);
-    const float q1 = __fmaf_rn(__fmaf_rn(-q0, area, s), rcp, q0);
-    return __fmaf_rn(__fmaf_rn(-q1, area, s), rcp, q1);
-}
 // meta.clamp(u8, fl(m / area)) [blur] or meta.clamp(u8, fl(2*orig - fl(m / area))) [sharpen] WITHOUT the exact division.
 // m is an integer (a combination of integer-valued floats) and area <= 31*31, so the exact value v is either a tie k + 1/2
 // -- which the reference's correctly rounded divide represents exactly and then rounds away from zero -- or at least

@@ -81,7 +81,8 @@ typedef enum zb_status {
     ZB_ERR_NO_TARGET_SET = 10,     /* fdm.zig:142 */
     ZB_ERR_NO_SOURCE_SET = 11,     /* fdm.zig:143 */
     ZB_ERR_INSUFFICIENT_DATA = 12, /* pca.zig:114-115 NoVectors / InsufficientData */
-    ZB_ERR_INVALID_COMPONENTS = 13 /* pca.zig:123 */
+    ZB_ERR_INVALID_COMPONENTS = 13, /* pca.zig:123 */
+    ZB_ERR_INVALID_THRESHOLD = 14  /* error.InvalidThreshold (edges.zig:225-226) */
 } zb_status;
 
 /* ------------------------------------------------------------------------------------------------
@@ -172,6 +173,11 @@ int zb_warp(const zb_image* src, zb_image* dst, int pixfmt, int xform_kind, cons
 /* Image.sobel(out, allocator)   image.zig:999-1009, edges.zig:33-73: gradient magnitude of the luma into an Image(u8)
  * (src: U8, F32, RGB8 or RGBA8; dst is always an 8-bit gray image of the same shape). */
 int zb_sobel(const zb_image* src, zb_image* dst_u8, int pixfmt, zb_stream s);
+/* Image.canny(out, allocator, sigma, low_threshold, high_threshold)   image.zig:1041-1063, edges.zig:212-274: luma -> Gaussian
+ * (.replicate) -> Sobel -> non-maximum suppression -> double threshold + hysteresis, all on the device; dst receives 0 / 255.
+ * Non-finite parameter: ZB_ERR_INVALID_ARGUMENT (error.InvalidParameter); sigma < 0: ZB_ERR_INVALID_SIGMA; negative thresholds
+ * or low >= high: ZB_ERR_INVALID_THRESHOLD.  The hysteresis iterates to a fixed point, so this call waits for the stream. */
+int zb_canny(const zb_image* src, zb_image* dst_u8, int pixfmt, float sigma, float low_threshold, float high_threshold, zb_stream s);
 
 /* Image.extract(out, rect, angle, method, border)   image.zig / transforms.zig:232-283: resample the rectangle (l, t, r, b in source
  * coordinates, rotated by `angle` CCW around its centre; cos/sin cross the ABI as data like rotateInto) into dst; an axis-aligned

@@ -61,7 +61,8 @@ enum { ZO_SVD_NO_U = 0, ZO_SVD_SKINNY_U = 1, ZO_SVD_FULL_U = 2 };
 /* Status codes (Zig error names). */
 enum {
     ZO_OK = 0, ZO_ERR_DIMENSION_MISMATCH = 1, ZO_ERR_INVALID_SIGMA = 2, ZO_ERR_UNSUPPORTED = 3,
-    ZO_ERR_NOT_CONVERGED = 4, ZO_ERR_INVALID_ARGUMENT = 5
+    ZO_ERR_NOT_CONVERGED = 4, ZO_ERR_INVALID_ARGUMENT = 5 /* also error.InvalidParameter */,
+    ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */
 };
 
 /* Number of OpenMP threads the row-parallel loops may use (1 = the reference's behaviour). */
@@ -99,6 +100,8 @@ int zo_integral_plane(const zo_image* src, int pixfmt, float* sat /* rows*cols *
 int zo_box_blur(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 /* image.zig:999-1009 / edges.zig:33-73: Sobel magnitude into an Image(u8) (src: U8, F32, RGB8 or RGBA8). */
 int zo_sobel(const zo_image* src, zo_image* dst_u8, int pixfmt);
+/* image.zig:1041-1063 / edges.zig:212-274: Canny edges (0 / 255) into an Image(u8) (src: U8, F32, RGB8 or RGBA8). */
+int zo_canny(const zo_image* src, zo_image* dst_u8, int pixfmt, float sigma, float low_threshold, float high_threshold);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 

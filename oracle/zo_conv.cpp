@@ -528,6 +528,101 @@ int zo_sobel(const zo_image* src, zo_image* dst, int pixfmt) {
     return ZO_OK;
 }
 
+// edges.zig:212-274 Edges(T).canny: luma -> f32, Gaussian (radius ceil(3 sigma), .replicate, :663-687), Sobel gx / gy with .replicate,
+// magnitude sqrt(gx^2 + gy^2), direction-quantised non-maximum suppression (:691-763, borders stay 0), double threshold and
+// breadth-first hysteresis over the 8-neighbourhood (:499-575).  dst is a binary (0 / 255) Image(u8).
+int zo_canny(const zo_image* src, zo_image* dst, int pixfmt, float sigma, float low_threshold, float high_threshold) {
+    if (!std::isfinite(sigma) || !std::isfinite(low_threshold) || !std::isfinite(high_threshold)) return ZO_ERR_INVALID_ARGUMENT;  // :221
+    if (sigma < 0) return ZO_ERR_INVALID_SIGMA;                                                  // :224
+    if (low_threshold < 0 || high_threshold < 0) return ZO_ERR_INVALID_THRESHOLD;                // :225
+    if (low_threshold >= high_threshold) return ZO_ERR_INVALID_THRESHOLD;                        // :226
+    if (src->rows != dst->rows || src->cols != dst->cols) return ZO_ERR_DIMENSION_MISMATCH;
+    const uint32_t rows = src->rows, cols = src->cols;
+    const size_t n = (size_t)rows * cols;
+    std::vector<float> gray(n), blurred(n), gx(n), gy(n), mag(n);
+    for (uint32_t r = 0; r < rows; ++r)                                                          // :229-236 as(f32, convertColor(u8, px))
+        for (uint32_t c = 0; c < cols; ++c) {
+            float v;
+            if (pixfmt == ZO_PIX_F32) {                                                          // color.zig:114-118 float -> u8 through f64
+                double d = (double)((const float*)src->data)[(size_t)r * src->stride + c];
+                d = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : d);
+                v = (float)(uint8_t)std::round(d * 255.0);
+            } else if (pixfmt == ZO_PIX_U8) {
+                v = (float)((const uint8_t*)src->data)[(size_t)r * src->stride + c];
+            } else if (pixfmt == ZO_PIX_RGB8 || pixfmt == ZO_PIX_RGBA8) {
+                const int ch = pixfmt == ZO_PIX_RGB8 ? 3 : 4;
+                const uint8_t* px = (const uint8_t*)src->data + ((size_t)r * src->stride + c) * ch;
+                int y = (13933 * (int)px[0] + 46871 * (int)px[1] + 4732 * (int)px[2] + 32768) >> 16;   // color.zig:1031-1041
+                y = y < 0 ? 0 : (y > 255 ? 255 : y);
+                v = (float)y;
+            } else {
+                return ZO_ERR_UNSUPPORTED;
+            }
+            gray[(size_t)r * cols + c] = v;
+        }
+    zo_image g{gray.data(), rows, cols, cols}, b{blurred.data(), rows, cols, cols}, ix{gx.data(), rows, cols, cols},
+        iy{gy.data(), rows, cols, cols};
+    int rc;
+    if (sigma == 0) {                                                                            // :241-242
+        blurred = gray;
+    } else {                                                                                     // :663-687 (same taps as gaussianBlur)
+        const size_t radius = (size_t)std::ceil(3.0f * sigma);
+        std::vector<float> taps(2 * radius + 1);
+        zo::gaussian_taps(sigma, taps.data(), (int)taps.size());
+        if ((rc = zo::conv_separable(&g, &b, ZO_PIX_F32, taps.data(), (int)taps.size(), taps.data(), (int)taps.size(), ZO_BORDER_REPLICATE)))
+            return rc;
+    }
+    static const float sobel_x[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};     // edges.zig:14-18
+    static const float sobel_y[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};     // :21-25
+    if ((rc = zo::convolve(&b, &ix, ZO_PIX_F32, sobel_x, 3, 3, ZO_BORDER_REPLICATE))) return rc;   // :253
+    if ((rc = zo::convolve(&b, &iy, ZO_PIX_F32, sobel_y, 3, 3, ZO_BORDER_REPLICATE))) return rc;   // :254
+    for (size_t i = 0; i < n; ++i) mag[i] = std::sqrt(gx[i] * gx[i] + gy[i] * gy[i]);              // :259-265
+
+    std::vector<uint8_t> nms(n, 0);                                                              // :691-763
+    const float K = 0.414213562f;
+    if (rows >= 3 && cols >= 3) {
+        for (uint32_t r = 1; r + 1 < rows; ++r)
+            for (uint32_t c = 1; c + 1 < cols; ++c) {
+                const float vx = gx[(size_t)r * cols + c], vy = gy[(size_t)r * cols + c];
+                const float ax = std::fabs(vx), ay = std::fabs(vy);
+                int dr1, dc1, dr2, dc2;
+                if (ay <= K * ax) { dr1 = 0; dc1 = -1; dr2 = 0; dc2 = 1; }
+                else if (ax <= K * ay) { dr1 = -1; dc1 = 0; dr2 = 1; dc2 = 0; }
+                else if (vx * vy > 0) { dr1 = -1; dc1 = 1; dr2 = 1; dc2 = -1; }
+                else { dr1 = -1; dc1 = -1; dr2 = 1; dc2 = 1; }
+                const float m = mag[(size_t)r * cols + c];
+                const float n1 = mag[(size_t)((int)r + dr1) * cols + (size_t)((int)c + dc1)];
+                const float n2 = mag[(size_t)((int)r + dr2) * cols + (size_t)((int)c + dc2)];
+                if (m >= n1 && m >= n2) nms[(size_t)r * cols + c] = 255;
+            }
+    }
+
+    uint8_t* out = (uint8_t*)dst->data;                                                          // :499-575
+    for (uint32_t r = 0; r < rows; ++r) std::memset(out + (size_t)r * dst->stride, 0, cols);
+    std::vector<uint32_t> queue;
+    queue.reserve(n);
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t c = 0; c < cols; ++c)
+            if (nms[(size_t)r * cols + c] > 0 && mag[(size_t)r * cols + c] >= high_threshold) {
+                out[(size_t)r * dst->stride + c] = 255;
+                queue.push_back(r * cols + c);
+            }
+    for (size_t pop = 0; pop < queue.size(); ++pop) {
+        const uint32_t r = queue[pop] / cols, c = queue[pop] % cols;
+        const uint32_t r0 = r > 0 ? r - 1 : 0, r1 = std::min(r + 2, rows), c0 = c > 0 ? c - 1 : 0, c1 = std::min(c + 2, cols);
+        for (uint32_t nr = r0; nr < r1; ++nr)
+            for (uint32_t nc = c0; nc < c1; ++nc) {
+                if (nr == r && nc == c) continue;
+                if (out[(size_t)nr * dst->stride + nc] > 0) continue;
+                if (nms[(size_t)nr * cols + nc] > 0 && mag[(size_t)nr * cols + nc] >= low_threshold) {
+                    out[(size_t)nr * dst->stride + nc] = 255;
+                    queue.push_back(nr * cols + nc);
+                }
+            }
+    }
+    return ZO_OK;
+}
+
 int zo_gaussian_blur(const zo_image* src, zo_image* dst, int pixfmt, float sigma) {
     if (src->rows != dst->rows || src->cols != dst->cols) return ZO_ERR_DIMENSION_MISMATCH;  // image.zig:962
     if (sigma == 0) { zo::copy_image(src, dst, pixfmt); return ZO_OK; }                       // :966

@@ -76,6 +76,7 @@ def _declare(L):
     L.zo_box_blur.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sharpen.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sobel.argtypes = [img, img, C.c_int]
+    L.zo_canny.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
     L.zo_rotate_bounds.argtypes = [C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), P(C.c_uint32)]
@@ -139,6 +140,12 @@ def _fptr(a):
 
 def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class OracleStatus(RuntimeError):
+    def __init__(self, status, what):
+        self.status = status
+        super().__init__(f"oracle {what} failed with status {status}")
 
 
 def _check(rc, what):
@@ -251,6 +258,15 @@ def sobel(src):
     out = np.zeros(src.shape[:2], np.uint8)
     s, d = as_image(src), as_image(out)
     _check(lib().zo_sobel(s, d, pixfmt_of(src)), "sobel")
+    return out
+
+
+def canny(src, sigma, low, high):
+    out = np.zeros(src.shape[:2], np.uint8)
+    s, d = as_image(src), as_image(out)
+    rc = lib().zo_canny(s, d, pixfmt_of(src), C.c_float(sigma), C.c_float(low), C.c_float(high))
+    if rc != 0:
+        raise OracleStatus(rc, "canny")
     return out
 
 

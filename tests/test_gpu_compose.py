@@ -98,3 +98,83 @@ def test_sobel(zb, shape, dtype):
     step = np.tile(np.where(np.arange(5) < 2, 0, 255).astype(np.uint8), (5, 1))    # the reference's own test image
     e = zb.Image.from_numpy(step).sobel().to_numpy()
     assert e[2, 2] > 200 and e[2, 0] < 50
+
+
+def _structured(rng, rows, cols):
+    """Smooth blobs plus a little noise: long contours whose strength varies along them, so hysteresis has work to do."""
+    y, x = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    img = np.zeros((rows, cols))
+    for _ in range(12):
+        cy, cx, rad, amp = rng.uniform(0, rows), rng.uniform(0, cols), rng.uniform(15, min(rows, cols) / 3), rng.uniform(20, 90)
+        img += amp * (np.hypot(y - cy, x - cx) < rad)
+    img += rng.normal(0, 2.0, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape,dtype", [((37, 45), np.uint8), ((40, 33, 3), np.uint8), ((29, 31, 4), np.uint8), ((35, 36), np.float32),
+                                         ((3, 3), np.uint8), ((2, 40), np.uint8), ((1, 1), np.uint8)])
+def test_canny_matches_oracle(zb, shape, dtype):
+    """Image.canny (edges.zig:212-274), bit-exact: every stage reproduces the oracle's f32 values (generic convolution paths, separately
+    rounded magnitude), so the thresholded decisions agree pixel for pixel."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    img = rand_image(rng, shape, dtype)
+    for sigma, low, high in [(0.0, 150.0, 400.0), (1.0, 20.0, 60.0), (1.4, 10.0, 30.0), (0.5, 0.0, 1.0)]:
+        got = zb.Image.from_numpy(img).canny(sigma, low, high).to_numpy()
+        want = zo.canny(img, sigma, low, high)
+        assert zb.lib().zb_last_kernel().decode() == "canny"
+        assert np.array_equal(got, want), (sigma, low, high, int((got != want).sum()))
+        assert set(np.unique(got)) <= {0, 255}
+
+
+def test_canny_reference_cases_and_validation(zb):
+    """image/tests/filters.zig:1182-1300 through the device path."""
+    step = np.tile(np.where(np.arange(10) < 5, 0, 255).astype(np.uint8), (10, 1))
+    e = zb.Image.from_numpy(step).canny(1.0, 50, 100).to_numpy()
+    assert e.shape == step.shape and e[:, 4:7].any()
+    assert np.array_equal(e, zo.canny(step, 1.0, 50, 100))
+    rgb = np.zeros((8, 8, 3), np.uint8)
+    rgb[:, :4, 0] = 255
+    rgb[:, 4:, 1] = 255
+    e = zb.Image.from_numpy(rgb).canny(1.0, 30, 90).to_numpy()
+    assert e[:, 3:6].any() and np.array_equal(e, zo.canny(rgb, 1.0, 30, 90))
+    ramp = zb.Image.from_numpy((np.arange(5)[:, None] * 10 + np.arange(5)[None, :]).astype(np.uint8))
+    ramp.canny(0.0, 50, 100)
+    for args, name in [((-1.0, 50, 100), "InvalidSigma"), ((1.0, -1, 100), "InvalidThreshold"), ((1.0, 50, -1), "InvalidThreshold"),
+                       ((1.0, 100, 50), "InvalidThreshold"), ((np.nan, 50, 100), "InvalidArgument"), ((1.0, np.nan, 100), "InvalidArgument"),
+                       ((1.0, 50, np.nan), "InvalidArgument"), ((np.inf, 50, 100), "InvalidArgument"), ((1.0, np.inf, 100), "InvalidArgument"),
+                       ((1.0, 50, np.inf), "InvalidArgument"), ((-np.inf, 50, 100), "InvalidArgument")]:
+        with pytest.raises(zb.ZignalError) as ei:
+            ramp.canny(*args)
+        assert ei.value.name == name, args
+    with pytest.raises(zb.ZignalError) as ei:
+        ramp.canny(1.0, 10, 20, out=zb.Image.init(4, 5, zb.PixFmt.U8, device="cuda"))
+    assert ei.value.name == "DimensionMismatch"
+
+
+@pytest.mark.parametrize("sigma,low,high", [(2.0, 4.0, 12.0), (1.0, 10.0, 40.0), (0.0, 30.0, 200.0)])
+def test_canny_hysteresis_across_tiles(zb, sigma, low, high):
+    """Contours several hundred pixels long cross many 64x64 relaxation tiles; the fixed point must equal the breadth-first closure."""
+    rng = np.random.default_rng(int(high))
+    img = _structured(rng, 389, 523)
+    got = zb.Image.from_numpy(img).canny(sigma, low, high).to_numpy()
+    want = zo.canny(img, sigma, low, high)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert 0 < int(want.sum()) // 255 < want.size // 4
+
+
+def test_canny_long_weak_chain(zb):
+    """One seed at the end of a serpentine of candidates that winds through every tile: thousands of promotions along a single path,
+    the worst case for the tile relaxation.  Built directly on the magnitude by a ridge image: a bright one-pixel-wide path on black."""
+    rows, cols = 200, 330
+    img = np.zeros((rows, cols), np.uint8)
+    level = 60
+    for k, r in enumerate(range(4, rows - 4, 8)):                # horizontal runs joined alternately at the right and left ends
+        img[r, 4:cols - 4] = level
+        if r + 8 < rows - 4:
+            c = cols - 5 if k % 2 == 0 else 4
+            img[r:r + 9, c] = level
+    img[4, 4:12] = 255                                           # the only strong stretch
+    got = zb.Image.from_numpy(img).canny(0.0, 100.0, 600.0).to_numpy()
+    want = zo.canny(img, 0.0, 100.0, 600.0)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert int(want[rows - 20:, :].sum()) > 0                    # the closure really reached the far end of the serpentine

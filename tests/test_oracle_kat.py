@@ -534,6 +534,67 @@ def test_sobel_kat():
     assert e[2, 2] == 255 and e[2, 1] == 255 and e[2, 0] == 0 and e[2, 4] == 0     # |gx| = 4 * 255 -> 255 after /4
 
 
+def test_canny_kat():
+    """image/tests/filters.zig:1182-1300: a vertical step is found near its column (u8 and Rgb), sigma = 0 is valid, parameter
+    validation (InvalidSigma / InvalidThreshold / InvalidParameter).  Plus an independent breadth-first restatement of the
+    hysteresis on a hand-made chain (strong seed, weak tail, isolated weak pixel)."""
+    step = np.tile(np.where(np.arange(10) < 5, 0, 255).astype(np.uint8), (10, 1))
+    e = zo.canny(step, 1.0, 50, 100)
+    assert e.shape == step.shape and set(np.unique(e)) <= {0, 255}
+    assert e[:, 4:7].any()
+    assert not e[0].any() and not e[-1].any() and not e[:, 0].any() and not e[:, -1].any()   # NMS never marks the border (edges.zig:713)
+    rgb = np.zeros((8, 8, 3), np.uint8)
+    rgb[:, :4, 0] = 255
+    rgb[:, 4:, 1] = 255
+    assert zo.canny(rgb, 1.0, 30, 90)[:, 3:6].any()
+    ramp = (np.arange(5)[:, None] * 10 + np.arange(5)[None, :]).astype(np.uint8)
+    zo.canny(ramp, 0.0, 50, 100)
+    for args, status in [((-1.0, 50, 100), 2), ((1.0, -1, 100), 14), ((1.0, 50, -1), 14), ((1.0, 100, 50), 14), ((1.0, 50, 50), 14),
+                         ((np.nan, 50, 100), 5), ((1.0, np.nan, 100), 5), ((1.0, 50, np.nan), 5), ((np.inf, 50, 100), 5),
+                         ((1.0, np.inf, 100), 5), ((1.0, 50, np.inf), 5), ((-np.inf, 50, 100), 5)]:
+        with pytest.raises(zo.OracleStatus) as ei:
+            zo.canny(ramp, *args)
+        assert ei.value.status == status, args
+    assert not zo.canny(np.full((2, 9), 200, np.uint8), 0.0, 1, 2).any()       # < 3 rows: no interior, nothing survives
+    # sigma = 0 on an integer image: every stage is exact in f32, so a float64 numpy restatement must agree bit for bit.
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (23, 31), dtype=np.uint8)
+    p = np.pad(img.astype(np.float64), 1, mode="edge")
+    gx = (p[:-2, 2:] - p[:-2, :-2]) + 2 * (p[1:-1, 2:] - p[1:-1, :-2]) + (p[2:, 2:] - p[2:, :-2])
+    gy = (p[2:, :-2] - p[:-2, :-2]) + 2 * (p[2:, 1:-1] - p[:-2, 1:-1]) + (p[2:, 2:] - p[:-2, 2:])
+    mag = np.sqrt((gx * gx + gy * gy).astype(np.float32)).astype(np.float32)
+    K = np.float32(0.414213562)
+    ax, ay = np.abs(gx).astype(np.float32), np.abs(gy).astype(np.float32)
+    nms = np.zeros(img.shape, bool)
+    for r in range(1, img.shape[0] - 1):
+        for c in range(1, img.shape[1] - 1):
+            if ay[r, c] <= K * ax[r, c]:
+                d = (0, -1, 0, 1)
+            elif ax[r, c] <= K * ay[r, c]:
+                d = (-1, 0, 1, 0)
+            elif gx[r, c] * gy[r, c] > 0:
+                d = (-1, 1, 1, -1)
+            else:
+                d = (-1, -1, 1, 1)
+            nms[r, c] = mag[r, c] >= mag[r + d[0], c + d[1]] and mag[r, c] >= mag[r + d[2], c + d[3]]
+    low, high = 300.0, 700.0
+    out = nms & (mag >= high)
+    weak = nms & (mag >= low)
+    while True:                                  # fixed point of "weak next to an edge becomes an edge" == the BFS closure
+        grown = np.pad(out, 1)
+        nb = np.zeros_like(out)
+        for dr in range(3):
+            for dc in range(3):
+                nb |= grown[dr:dr + out.shape[0], dc:dc + out.shape[1]]
+        nxt = out | (weak & nb)
+        if np.array_equal(nxt, out):
+            break
+        out = nxt
+    got = zo.canny(img, 0.0, low, high)
+    assert np.array_equal(got, np.where(out, 255, 0).astype(np.uint8))
+    assert 0 < int(out.sum()) < out.size and int((weak & ~out).sum()) > 0       # the case exercises both hysteresis outcomes
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

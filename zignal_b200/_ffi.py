@@ -82,6 +82,7 @@ def _declare(L):
         "zb_kernel_launch_count": ([], u64),
         "zb_gaussian_taps": ([f, fp, i, P(i)], i),
         "zb_sobel": ([img, img, i, vp], i),
+        "zb_canny": ([img, img, i, f, f, f, vp], i),
         "zb_insert": ([img, img, i, f, f, f, f, f, f, f, i, f, f, vp], i),
         "zb_extract": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
         "zb_set_border_zero": ([img, i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp], i),

@@ -93,6 +93,7 @@ const char* zb_status_name(int status) {
         case ZB_ERR_NO_SOURCE_SET: return "NoSourceSet";
         case ZB_ERR_INSUFFICIENT_DATA: return "InsufficientData";
         case ZB_ERR_INVALID_COMPONENTS: return "InvalidComponents";
+        case ZB_ERR_INVALID_THRESHOLD: return "InvalidThreshold";
     }
     return "Unknown";
 }

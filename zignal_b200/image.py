@@ -275,6 +275,14 @@ class Image:
         check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
         return out
 
+    def canny(self, sigma: float, low_threshold: float, high_threshold: float, out: Optional["Image"] = None) -> "Image":
+        """Image.canny (image.zig:1041-1063, edges.zig:212-274): binary (0 / 255) edge map into an Image(u8) of the same shape."""
+        if out is None:
+            out = Image.init(self.rows, self.cols, PixFmt.U8, device=self._t.device)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_canny(a, d, int(self.pixfmt), C.c_float(sigma), C.c_float(low_threshold), C.c_float(high_threshold), current_stream()))
+        return out
+
     def extract(self, out: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
                 border: BorderMode = BorderMode.ZERO, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
         """Image.extract (transforms.zig:232-283): rect = (l, t, r, b) floats in source coordinates, rotated by `angle` CCW."""

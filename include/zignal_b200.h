@@ -82,7 +82,9 @@ typedef enum zb_status {
     ZB_ERR_NO_SOURCE_SET = 11,     /* fdm.zig:143 */
     ZB_ERR_INSUFFICIENT_DATA = 12, /* pca.zig:114-115 NoVectors / InsufficientData */
     ZB_ERR_INVALID_COMPONENTS = 13, /* pca.zig:123 */
-    ZB_ERR_INVALID_THRESHOLD = 14  /* error.InvalidThreshold (edges.zig:225-226) */
+    ZB_ERR_INVALID_THRESHOLD = 14, /* error.InvalidThreshold (edges.zig:225-226) */
+    ZB_ERR_INVALID_PERCENTILE = 15, /* error.InvalidPercentile (order_statistic_blur.zig:49) */
+    ZB_ERR_INVALID_TRIM = 16       /* error.InvalidTrim (order_statistic_blur.zig:161) */
 } zb_status;
 
 /* ------------------------------------------------------------------------------------------------
@@ -178,6 +180,18 @@ int zb_sobel(const zb_image* src, zb_image* dst_u8, int pixfmt, zb_stream s);
  * Non-finite parameter: ZB_ERR_INVALID_ARGUMENT (error.InvalidParameter); sigma < 0: ZB_ERR_INVALID_SIGMA; negative thresholds
  * or low >= high: ZB_ERR_INVALID_THRESHOLD.  The hysteresis iterates to a fixed point, so this call waits for the stream. */
 int zb_canny(const zb_image* src, zb_image* dst_u8, int pixfmt, float sigma, float low_threshold, float high_threshold, zb_stream s);
+
+/* Order-statistic filters   image.zig:650-790, image/order_statistic_blur.zig:22-197 on 8-bit images (U8, RGB8, RGBA8; every channel
+ * independently, :199-229).  One entry point for the family:
+ *   Image.percentileBlur(out, radius, percentile, border)   mode ZB_ORDER_PERCENTILE, param = percentile in [0, 1]
+ *   Image.medianBlur(out, radius)                            = percentile 0.5 with ZB_BORDER_MIRROR (:22-29)
+ *   Image.minBlur / maxBlur(out, radius, border)             = percentile 0.0 / 1.0 (:83-101)
+ *   Image.midpointBlur(out, radius, border)                  mode ZB_ORDER_MIDPOINT (param ignored)
+ *   Image.alphaTrimmedMeanBlur(out, radius, trim, border)    mode ZB_ORDER_ALPHA_TRIMMED, param = trim fraction in [0, 0.5)
+ * radius 0 copies; src may alias dst.  Errors in the reference's order: DimensionMismatch, (empty image: ok), InvalidTrim, (radius 0:
+ * copy), InvalidPercentile, Unsupported (pixel type; also radius > 31 in this build). */
+enum { ZB_ORDER_PERCENTILE = 0, ZB_ORDER_MIDPOINT = 1, ZB_ORDER_ALPHA_TRIMMED = 2 };
+int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border, zb_stream s);
 
 /* Image.extract(out, rect, angle, method, border)   image.zig / transforms.zig:232-283: resample the rectangle (l, t, r, b in source
  * coordinates, rotated by `angle` CCW around its centre; cos/sin cross the ABI as data like rotateInto) into dst; an axis-aligned

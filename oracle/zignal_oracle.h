@@ -62,7 +62,7 @@ enum { ZO_SVD_NO_U = 0, ZO_SVD_SKINNY_U = 1, ZO_SVD_FULL_U = 2 };
 enum {
     ZO_OK = 0, ZO_ERR_DIMENSION_MISMATCH = 1, ZO_ERR_INVALID_SIGMA = 2, ZO_ERR_UNSUPPORTED = 3,
     ZO_ERR_NOT_CONVERGED = 4, ZO_ERR_INVALID_ARGUMENT = 5 /* also error.InvalidParameter */,
-    ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */
+    ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */, ZO_ERR_INVALID_PERCENTILE = 15, ZO_ERR_INVALID_TRIM = 16 /* order_statistic_blur.zig:15-20 */
 };
 
 /* Number of OpenMP threads the row-parallel loops may use (1 = the reference's behaviour). */
@@ -102,6 +102,10 @@ int zo_box_blur(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius)
 int zo_sobel(const zo_image* src, zo_image* dst_u8, int pixfmt);
 /* image.zig:1041-1063 / edges.zig:212-274: Canny edges (0 / 255) into an Image(u8) (src: U8, F32, RGB8 or RGBA8). */
 int zo_canny(const zo_image* src, zo_image* dst_u8, int pixfmt, float sigma, float low_threshold, float high_threshold);
+/* image.zig:650-790 / order_statistic_blur.zig: percentileBlur (param = percentile in [0, 1]; medianBlur = 0.5 with .mirror, minBlur = 0,
+ * maxBlur = 1), midpointBlur (param ignored), alphaTrimmedMeanBlur (param = trim fraction in [0, 0.5)).  pixfmt U8, RGB8 or RGBA8. */
+enum { ZO_ORDER_PERCENTILE = 0, ZO_ORDER_MIDPOINT = 1, ZO_ORDER_ALPHA_TRIMMED = 2 };
+int zo_order_blur(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 

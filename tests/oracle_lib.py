@@ -76,6 +76,7 @@ def _declare(L):
     L.zo_box_blur.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sharpen.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sobel.argtypes = [img, img, C.c_int]
+    L.zo_order_blur.argtypes = [img, img, C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int]
     L.zo_canny.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -258,6 +259,19 @@ def sobel(src):
     out = np.zeros(src.shape[:2], np.uint8)
     s, d = as_image(src), as_image(out)
     _check(lib().zo_sobel(s, d, pixfmt_of(src)), "sobel")
+    return out
+
+
+ORDER_MODE = {"percentile": 0, "midpoint": 1, "alpha_trimmed": 2}
+
+
+def order_blur(src, radius, mode="percentile", param=0.5, border="mirror", out=None):
+    """percentileBlur / midpointBlur / alphaTrimmedMeanBlur; medianBlur = ("percentile", 0.5, "mirror")."""
+    out = np.zeros_like(src) if out is None else out
+    s, d = as_image(src), as_image(out)
+    rc = lib().zo_order_blur(s, d, pixfmt_of(src), radius, ORDER_MODE[mode], C.c_double(param), BORDER[border])
+    if rc != 0:
+        raise OracleStatus(rc, "order_blur")
     return out
 
 

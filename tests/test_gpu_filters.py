@@ -146,3 +146,80 @@ def test_config1_box_blur_512_u8(zb):
     rng = np.random.default_rng(1)
     img = rand_image(rng, (512, 512), np.uint8)
     assert np.array_equal(zb.Image.from_numpy(img).box_blur(1).to_numpy(), zo.box_blur(img, 1))
+
+
+# ---- order-statistic filters (order_statistic_blur.zig) ----
+@pytest.mark.parametrize("shape", [(37, 45), (40, 33, 3), (29, 31, 4), (1, 9), (7, 1), (3, 3)])
+def test_order_statistic_filters_match_oracle(zb, shape):
+    """Bit-exact against the oracle's sliding-histogram restatement: percentile (incl. median / min / max), midpoint and alpha-trimmed
+    mean, every border mode, windows larger than the image included."""
+    rng = np.random.default_rng(shape[0] * 13 + shape[1])
+    img = rand_image(rng, shape, np.uint8)
+    dev = zb.Image.from_numpy(img)
+    for radius in (1, 2, 5):
+        for bname, border in [("zero", zb.BorderMode.ZERO), ("replicate", zb.BorderMode.REPLICATE), ("mirror", zb.BorderMode.MIRROR),
+                              ("wrap", zb.BorderMode.WRAP)]:
+            for pct in (0.0, 0.25, 0.5, 0.9, 1.0):
+                got = dev.percentile_blur(radius, pct, border).to_numpy()
+                assert zb.lib().zb_last_kernel().decode() == "order_statistic"
+                assert np.array_equal(got, zo.order_blur(img, radius, "percentile", pct, bname)), (radius, bname, pct)
+            assert np.array_equal(dev.midpoint_blur(radius, border).to_numpy(), zo.order_blur(img, radius, "midpoint", 0.0, bname)), (radius, bname)
+            for trim in (0.0, 0.12, 0.33, 0.49):
+                got = dev.alpha_trimmed_mean_blur(radius, trim, border).to_numpy()
+                assert np.array_equal(got, zo.order_blur(img, radius, "alpha_trimmed", trim, bname)), (radius, bname, trim)
+        assert np.array_equal(dev.median_blur(radius).to_numpy(), zo.order_blur(img, radius, "percentile", 0.5, "mirror"))
+        assert np.array_equal(dev.min_blur(radius, zb.BorderMode.REPLICATE).to_numpy(), zo.order_blur(img, radius, "percentile", 0.0, "replicate"))
+        assert np.array_equal(dev.max_blur(radius, zb.BorderMode.REPLICATE).to_numpy(), zo.order_blur(img, radius, "percentile", 1.0, "replicate"))
+
+
+def test_order_statistic_reference_cases(zb):
+    """image/tests/filters.zig:817-966 through the device path, plus aliasing, radius 0 and the error order."""
+    imp = np.zeros((5, 5), np.uint8)
+    imp[2, 2] = 255
+    med = zb.Image.from_numpy(imp).median_blur(1).to_numpy()
+    assert med[2, 2] == 0 and med[2, 1] == 0 and med[1, 2] == 0
+    seq = np.arange(9, dtype=np.uint8).reshape(3, 3)
+    dseq = zb.Image.from_numpy(seq)
+    mx = dseq.percentile_blur(1, 1.0, zb.BorderMode.ZERO).to_numpy()
+    assert mx[1, 1] == 8 and mx[0, 0] == 4
+    rgb = np.tile(np.array([32, 64, 96], np.uint8), (3, 3, 1))
+    rgb[1, 1] = (255, 0, 0)
+    m = zb.Image.from_numpy(rgb).median_blur(1).to_numpy()
+    assert tuple(m[1, 1]) == (32, 64, 96) and tuple(m[0, 0]) == (32, 64, 96)
+    assert dseq.midpoint_blur(1, zb.BorderMode.REPLICATE).to_numpy()[1, 1] == 4
+    assert dseq.alpha_trimmed_mean_blur(1, 0.12, zb.BorderMode.REPLICATE).to_numpy()[1, 1] == 4
+    for trim in (0.6, 0.5, -0.1, float("nan")):
+        with pytest.raises(zb.ZignalError) as ei:
+            dseq.alpha_trimmed_mean_blur(1, trim, zb.BorderMode.REPLICATE)
+        assert ei.value.name == "InvalidTrim"
+    for pct in (-0.01, 1.01):
+        with pytest.raises(zb.ZignalError) as ei:
+            dseq.percentile_blur(1, pct)
+        assert ei.value.name == "InvalidPercentile"
+    assert np.array_equal(dseq.percentile_blur(0, 7.0).to_numpy(), seq)           # radius 0 copies before the percentile check
+    with pytest.raises(zb.ZignalError) as ei:
+        zb.Image.from_numpy(np.zeros((4, 4), np.float32)).median_blur(1)
+    assert ei.value.name == "Unsupported"
+    with pytest.raises(zb.ZignalError) as ei:
+        dseq.median_blur(1, out=zb.Image.init(3, 4, zb.PixFmt.U8, device="cuda"))
+    assert ei.value.name == "DimensionMismatch"
+    rng = np.random.default_rng(5)
+    img = rand_image(rng, (50, 70, 4), np.uint8)
+    dev = zb.Image.from_numpy(img)
+    dev.median_blur(2, out=dev)                                                   # in place (order_statistic_blur.zig:52-60)
+    assert np.array_equal(dev.to_numpy(), zo.order_blur(img, 2, "percentile", 0.5, "mirror"))
+
+
+def test_order_statistic_large(zb):
+    """A size where the grid has many tiles in both directions and the widest supported window."""
+    rng = np.random.default_rng(77)
+    img = rand_image(rng, (301, 517), np.uint8)
+    dev = zb.Image.from_numpy(img)
+    assert np.array_equal(dev.median_blur(3).to_numpy(), zo.order_blur(img, 3, "percentile", 0.5, "mirror"))
+    assert np.array_equal(dev.alpha_trimmed_mean_blur(4, 0.2, zb.BorderMode.WRAP).to_numpy(), zo.order_blur(img, 4, "alpha_trimmed", 0.2, "wrap"))
+    small = np.ascontiguousarray(img[:64, :96])
+    dsm = zb.Image.from_numpy(small)
+    assert np.array_equal(dsm.percentile_blur(31, 0.37, zb.BorderMode.MIRROR).to_numpy(), zo.order_blur(small, 31, "percentile", 0.37, "mirror"))
+    with pytest.raises(zb.ZignalError) as ei:
+        dsm.median_blur(32)
+    assert ei.value.name == "Unsupported"

@@ -595,6 +595,71 @@ def test_canny_kat():
     assert 0 < int(out.sum()) < out.size and int((weak & ~out).sum()) > 0       # the case exercises both hysteresis outcomes
 
 
+def _order_brute(img, radius, border, fn):
+    """Brute-force window gather (border-resolved indices, zero for out-of-range) -> fn(sorted window)."""
+    planes = img[..., None] if img.ndim == 2 else img
+    rows, cols, ch = planes.shape
+    ri = [zo.resolve_index(i, rows, border) for i in range(-radius, rows + radius)]
+    ci = [zo.resolve_index(i, cols, border) for i in range(-radius, cols + radius)]
+    out = np.zeros_like(planes)
+    for k in range(ch):
+        padded = np.zeros((rows + 2 * radius, cols + 2 * radius), np.uint8)
+        for y, r in enumerate(ri):
+            for x, c in enumerate(ci):
+                if r is not None and c is not None:
+                    padded[y, x] = planes[r, c, k]
+        for r in range(rows):
+            for c in range(cols):
+                out[r, c, k] = fn(np.sort(padded[r:r + 2 * radius + 1, c:c + 2 * radius + 1].ravel()).astype(np.int64))
+    return out.reshape(img.shape)
+
+
+def test_order_statistic_kats():
+    """image/tests/filters.zig:817-966 (median removes an impulse, percentile 1.0 with .zero, Rgb median, min == percentile 0,
+    max == percentile 1, midpoint, alpha-trimmed mean, InvalidTrim) and a brute-force sort-based restatement on random images."""
+    imp = np.zeros((5, 5), np.uint8)
+    imp[2, 2] = 255
+    med = zo.order_blur(imp, 1, "percentile", 0.5, "mirror")
+    assert med[2, 2] == 0 and med[2, 1] == 0 and med[1, 2] == 0
+    seq = np.arange(9, dtype=np.uint8).reshape(3, 3)
+    mx = zo.order_blur(seq, 1, "percentile", 1.0, "zero")
+    assert mx[1, 1] == 8 and mx[0, 0] == 4
+    rgb = np.tile(np.array([32, 64, 96], np.uint8), (3, 3, 1))
+    rgb[1, 1] = (255, 0, 0)
+    m = zo.order_blur(rgb, 1, "percentile", 0.5, "mirror")
+    assert tuple(m[1, 1]) == (32, 64, 96) and tuple(m[0, 0]) == (32, 64, 96)
+    assert zo.order_blur(seq, 1, "midpoint", 0.0, "replicate")[1, 1] == 4
+    assert zo.order_blur(seq, 1, "alpha_trimmed", 0.12, "replicate")[1, 1] == 4
+    for trim in (0.6, 0.5, -0.1, np.nan):
+        with pytest.raises(zo.OracleStatus) as ei:
+            zo.order_blur(seq, 1, "alpha_trimmed", trim, "replicate")
+        assert ei.value.status == 16
+    for pct in (-0.01, 1.01):
+        with pytest.raises(zo.OracleStatus) as ei:
+            zo.order_blur(seq, 1, "percentile", pct, "mirror")
+        assert ei.value.status == 15
+    assert np.array_equal(zo.order_blur(seq, 0, "percentile", 7.0, "mirror"), seq)      # radius 0 copies before the percentile check (:43-50)
+    with pytest.raises(zo.OracleStatus) as ei:
+        zo.order_blur(np.zeros((4, 4), np.float32), 1, "percentile", 0.5, "mirror")
+    assert ei.value.status == 3
+    rng = np.random.default_rng(11)
+    for shape, radius in [((9, 13), 1), ((7, 6), 2), ((5, 4, 3), 3), ((6, 8, 4), 1), ((1, 5), 2), ((3, 1), 1)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        area = (2 * radius + 1) ** 2
+        for border in ("zero", "replicate", "mirror", "wrap"):
+            for pct in (0.0, 0.1, 0.5, 0.73, 1.0):
+                rank = min(int(np.floor(pct * (area - 1) + 1e-12)), area - 1)
+                assert np.array_equal(zo.order_blur(img, radius, "percentile", pct, border),
+                                      _order_brute(img, radius, border, lambda w: w[rank])), (shape, radius, border, pct)
+            assert np.array_equal(zo.order_blur(img, radius, "midpoint", 0.0, border),
+                                  _order_brute(img, radius, border, lambda w: (w[0] + w[-1] + 1) // 2)), (shape, radius, border)
+            for trim in (0.0, 0.12, 0.3, 0.49):
+                t = min(int(np.floor(trim * area)), area // 2)
+                kept = area - 2 * t
+                assert np.array_equal(zo.order_blur(img, radius, "alpha_trimmed", trim, border),
+                                      _order_brute(img, radius, border, lambda w: min(255, (int(w[t:area - t].sum()) + kept // 2) // kept))), (shape, trim)
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

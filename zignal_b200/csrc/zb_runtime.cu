@@ -94,6 +94,8 @@ const char* zb_status_name(int status) {
         case ZB_ERR_INSUFFICIENT_DATA: return "InsufficientData";
         case ZB_ERR_INVALID_COMPONENTS: return "InvalidComponents";
         case ZB_ERR_INVALID_THRESHOLD: return "InvalidThreshold";
+        case ZB_ERR_INVALID_PERCENTILE: return "InvalidPercentile";
+        case ZB_ERR_INVALID_TRIM: return "InvalidTrim";
     }
     return "Unknown";
 }

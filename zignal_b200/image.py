@@ -275,6 +275,39 @@ class Image:
         check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
         return out
 
+    # ---- order-statistic filters (image.zig:650-790, order_statistic_blur.zig) ----
+    def _order(self, radius: int, mode: int, param: float, border: BorderMode, out: Optional["Image"]) -> "Image":
+        if out is None:
+            out = Image.init(self.rows, self.cols, self.pixfmt, device=self._t.device)
+        a, d = self._zb(), out._zb()
+        check(lib().zb_order_blur(a, d, int(self.pixfmt), int(radius), mode, C.c_double(param), int(border), current_stream()))
+        return out
+
+    def percentile_blur(self, radius: int, percentile: float, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
+        """Image.percentileBlur (image.zig:672-684)."""
+        return self._order(radius, 0, percentile, border, out)
+
+    def median_blur(self, radius: int, out: Optional["Image"] = None) -> "Image":
+        """Image.medianBlur (image.zig:650-658): percentile 0.5 with .mirror (order_statistic_blur.zig:28)."""
+        return self._order(radius, 0, 0.5, BorderMode.MIRROR, out)
+
+    def min_blur(self, radius: int, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
+        """Image.minBlur (image.zig:696-707): erosion."""
+        return self._order(radius, 0, 0.0, border, out)
+
+    def max_blur(self, radius: int, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
+        """Image.maxBlur (image.zig:719-730): dilation."""
+        return self._order(radius, 0, 1.0, border, out)
+
+    def midpoint_blur(self, radius: int, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
+        """Image.midpointBlur (image.zig:742-753)."""
+        return self._order(radius, 1, 0.0, border, out)
+
+    def alpha_trimmed_mean_blur(self, radius: int, trim_fraction: float, border: BorderMode = BorderMode.MIRROR,
+                                out: Optional["Image"] = None) -> "Image":
+        """Image.alphaTrimmedMeanBlur (image.zig:767-779)."""
+        return self._order(radius, 2, trim_fraction, border, out)
+
     def canny(self, sigma: float, low_threshold: float, high_threshold: float, out: Optional["Image"] = None) -> "Image":
         """Image.canny (image.zig:1041-1063, edges.zig:212-274): binary (0 / 255) edge map into an Image(u8) of the same shape."""
         if out is None:

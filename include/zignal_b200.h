@@ -84,7 +84,8 @@ typedef enum zb_status {
     ZB_ERR_INVALID_COMPONENTS = 13, /* pca.zig:123 */
     ZB_ERR_INVALID_THRESHOLD = 14, /* error.InvalidThreshold (edges.zig:225-226) */
     ZB_ERR_INVALID_PERCENTILE = 15, /* error.InvalidPercentile (order_statistic_blur.zig:49) */
-    ZB_ERR_INVALID_TRIM = 16       /* error.InvalidTrim (order_statistic_blur.zig:161) */
+    ZB_ERR_INVALID_TRIM = 16,      /* error.InvalidTrim (order_statistic_blur.zig:161) */
+    ZB_ERR_IMAGE_TOO_SMALL = 17    /* error.ImageTooSmall (metrics.zig:61) */
 } zb_status;
 
 /* ------------------------------------------------------------------------------------------------
@@ -192,6 +193,14 @@ int zb_canny(const zb_image* src, zb_image* dst_u8, int pixfmt, float sigma, flo
  * copy), InvalidPercentile, Unsupported (pixel type; also radius > 31 in this build). */
 enum { ZB_ORDER_PERCENTILE = 0, ZB_ORDER_MIDPOINT = 1, ZB_ORDER_ALPHA_TRIMMED = 2 };
 int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border, zb_stream s);
+
+/* Image.psnr(other) / Image.ssim(other) / Image.meanPixelError(other)   image.zig:1105-1147, image/metrics.zig:10-165: f64 quality
+ * metrics of two device images of the same pixel format (U8, F32, RGB8, RGBA8, RGBAF32); *out is a HOST double, so each call waits
+ * for the stream.  8-bit psnr / meanPixelError reproduce the reference's value exactly (integer sums); float formats and ssim
+ * associate the final f64 sum differently (relative difference ~1e-15).  ssim: images under 11x11 give ZB_ERR_IMAGE_TOO_SMALL. */
+int zb_psnr(const zb_image* a, const zb_image* b, int pixfmt, double* out, zb_stream s);
+int zb_ssim(const zb_image* a, const zb_image* b, int pixfmt, double* out, zb_stream s);
+int zb_mean_pixel_error(const zb_image* a, const zb_image* b, int pixfmt, double* out, zb_stream s);
 
 /* Image.extract(out, rect, angle, method, border)   image.zig / transforms.zig:232-283: resample the rectangle (l, t, r, b in source
  * coordinates, rotated by `angle` CCW around its centre; cos/sin cross the ABI as data like rotateInto) into dst; an axis-aligned

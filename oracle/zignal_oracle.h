@@ -62,7 +62,8 @@ enum { ZO_SVD_NO_U = 0, ZO_SVD_SKINNY_U = 1, ZO_SVD_FULL_U = 2 };
 enum {
     ZO_OK = 0, ZO_ERR_DIMENSION_MISMATCH = 1, ZO_ERR_INVALID_SIGMA = 2, ZO_ERR_UNSUPPORTED = 3,
     ZO_ERR_NOT_CONVERGED = 4, ZO_ERR_INVALID_ARGUMENT = 5 /* also error.InvalidParameter */,
-    ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */, ZO_ERR_INVALID_PERCENTILE = 15, ZO_ERR_INVALID_TRIM = 16 /* order_statistic_blur.zig:15-20 */
+    ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */, ZO_ERR_INVALID_PERCENTILE = 15, ZO_ERR_INVALID_TRIM = 16 /* order_statistic_blur.zig:15-20 */,
+    ZO_ERR_IMAGE_TOO_SMALL = 17 /* metrics.zig:61 */
 };
 
 /* Number of OpenMP threads the row-parallel loops may use (1 = the reference's behaviour). */
@@ -106,6 +107,11 @@ int zo_canny(const zo_image* src, zo_image* dst_u8, int pixfmt, float sigma, flo
  * maxBlur = 1), midpointBlur (param ignored), alphaTrimmedMeanBlur (param = trim fraction in [0, 0.5)).  pixfmt U8, RGB8 or RGBA8. */
 enum { ZO_ORDER_PERCENTILE = 0, ZO_ORDER_MIDPOINT = 1, ZO_ORDER_ALPHA_TRIMMED = 2 };
 int zo_order_blur(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border);
+/* image.zig:1105-1147 / metrics.zig: f64 image-quality metrics of two images of the same pixel format (U8, F32, RGB8, RGBA8, RGBAF32). */
+int zo_psnr(const zo_image* a, const zo_image* b, int pixfmt, double* out);
+int zo_ssim(const zo_image* a, const zo_image* b, int pixfmt, double* out);
+int zo_mean_pixel_error(const zo_image* a, const zo_image* b, int pixfmt, double* out);
+void zo_ssim_window(double* w121);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 

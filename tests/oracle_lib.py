@@ -77,6 +77,8 @@ def _declare(L):
     L.zo_sharpen.argtypes = [img, img, C.c_int, C.c_uint32]
     L.zo_sobel.argtypes = [img, img, C.c_int]
     L.zo_order_blur.argtypes = [img, img, C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int]
+    for fn in (L.zo_psnr, L.zo_ssim, L.zo_mean_pixel_error):
+        fn.argtypes = [img, img, C.c_int, C.POINTER(C.c_double)]
     L.zo_canny.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -273,6 +275,26 @@ def order_blur(src, radius, mode="percentile", param=0.5, border="mirror", out=N
     if rc != 0:
         raise OracleStatus(rc, "order_blur")
     return out
+
+
+def _metric(fn, what, a, b):
+    out = C.c_double(0.0)
+    rc = fn(as_image(a), as_image(b), pixfmt_of(a), C.byref(out))
+    if rc != 0:
+        raise OracleStatus(rc, what)
+    return out.value
+
+
+def psnr(a, b):
+    return _metric(lib().zo_psnr, "psnr", a, b)
+
+
+def ssim(a, b):
+    return _metric(lib().zo_ssim, "ssim", a, b)
+
+
+def mean_pixel_error(a, b):
+    return _metric(lib().zo_mean_pixel_error, "mean_pixel_error", a, b)
 
 
 def canny(src, sigma, low, high):

@@ -660,6 +660,58 @@ def test_order_statistic_kats():
                                       _order_brute(img, radius, border, lambda w: min(255, (int(w[t:area - t].sum()) + kept // 2) // kept))), (shape, trim)
 
 
+def test_metrics_kats():
+    """image/tests/psnr.zig:13-130 and image/metrics.zig:253-293 (meanPixelError RGB example, ssim on a checkerboard), plus a float64
+    numpy restatement of SSIM's 11x11 Gaussian-window statistics."""
+    a = np.array([[100, 150], [200, 250]], np.uint8)
+    b = np.array([[110, 140], [205, 245]], np.uint8)
+    assert zo.psnr(a, a) == np.inf
+    assert abs(zo.psnr(a, b) - 30.171) < 0.01
+    assert zo.psnr(a, b) == 20.0 * np.log10(255.0) - 10.0 * np.log10(62.5)
+    with pytest.raises(zo.OracleStatus) as ei:
+        zo.psnr(a, np.zeros((2, 3), np.uint8))
+    assert ei.value.status == 1
+    rgb1 = np.tile(np.array([100, 150, 200], np.uint8), (2, 2, 1))
+    rgb2 = np.tile(np.array([110, 140, 205], np.uint8), (2, 2, 1))
+    assert abs(zo.psnr(rgb1, rgb2) - 29.38) < 0.01
+    ra = np.array([[[255, 0, 0, 255], [0, 255, 0, 255]]], np.uint8)
+    rb = np.array([[[250, 5, 0, 255], [0, 250, 5, 255]]], np.uint8)
+    assert abs(zo.psnr(ra, rb) - 37.16) < 0.01
+    f1 = np.array([[0.5, 0.7], [0.3, 0.9]], np.float32)
+    f2 = np.array([[0.4, 0.8], [0.2, 1.0]], np.float32)
+    assert abs(zo.psnr(f1, f2) - 20.0) < 0.01
+    one = np.array([[[255, 0, 0]]], np.uint8)
+    assert abs(zo.mean_pixel_error(one, np.zeros_like(one)) - 1.0 / 3.0) < 1e-9
+    assert zo.mean_pixel_error(np.zeros((0, 0), np.uint8), np.zeros((0, 0), np.uint8)) == 0.0
+    chk = np.zeros((12, 12, 3), np.uint8)
+    rr, cc = np.mgrid[0:12, 0:12]
+    chk[(rr + cc) % 2 == 0] = (255, 0, 0)
+    chk[(rr + cc) % 2 == 1] = (0, 255, 0)
+    assert zo.ssim(chk, np.zeros_like(chk)) < 0.99
+    assert zo.ssim(chk, chk) == 1.0
+    with pytest.raises(zo.OracleStatus) as ei:
+        zo.ssim(np.zeros((10, 30), np.uint8), np.zeros((10, 30), np.uint8))
+    assert ei.value.status == 17
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 256, (19, 23), dtype=np.uint8)
+    y = np.clip(x.astype(int) + rng.integers(-30, 31, x.shape), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[-5:6, -5:6].astype(np.float64)
+    w = np.exp(-(xx * xx + yy * yy) / (2.0 * 1.5 * 1.5))
+    w /= w.sum()
+    c1, c2 = (0.01 * 255.0) ** 2, (0.03 * 255.0) ** 2
+    vals = []
+    for r in range(5, x.shape[0] - 5):
+        for c in range(5, x.shape[1] - 5):
+            px, py = x[r - 5:r + 6, c - 5:c + 6].astype(np.float64), y[r - 5:r + 6, c - 5:c + 6].astype(np.float64)
+            mx, my = (w * px).sum(), (w * py).sum()
+            sx, sy, sxy = max(0.0, (w * px * px).sum() - mx * mx), max(0.0, (w * py * py).sum() - my * my), (w * px * py).sum() - mx * my
+            vals.append((2 * mx * my + c1) * (2 * sxy + c2) / ((mx * mx + my * my + c1) * (sx + sy + c2)))
+    assert abs(zo.ssim(x, y) - np.mean(vals)) < 1e-12
+    xf = rng.random((14, 15, 4), dtype=np.float32)
+    yf = np.clip(xf + rng.normal(0, 0.05, xf.shape).astype(np.float32), 0, 1).astype(np.float32)
+    assert 0.0 < zo.ssim(xf, yf) < 1.0 and abs(zo.mean_pixel_error(xf, yf) - np.abs(xf.astype(np.float64) - yf).mean()) < 1e-12
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

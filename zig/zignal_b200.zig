@@ -38,6 +38,9 @@ pub const c = struct {
     pub extern fn zb_insert(self: *ZbImage, source: *const ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, s: Stream) c_int;
     pub extern fn zb_sobel(src: *const ZbImage, dst_u8: *ZbImage, pixfmt: c_int, s: Stream) c_int;
     pub extern fn zb_order_blur(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, radius: u32, mode: c_int, param: f64, border: c_int, s: Stream) c_int;
+    pub extern fn zb_psnr(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
+    pub extern fn zb_ssim(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
+    pub extern fn zb_mean_pixel_error(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_canny(src: *const ZbImage, dst_u8: *ZbImage, pixfmt: c_int, sigma: f32, low_threshold: f32, high_threshold: f32, s: Stream) c_int;
     pub extern fn zb_set_border_zero(img: *ZbImage, pixfmt: c_int, l: u32, t: u32, r: u32, b: u32, s: Stream) c_int;
     pub extern fn zb_conv_separable_rows(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, kx: [*]const f32, nx: c_int, ky: [*]const f32, ny: c_int, border: c_int, row_begin: u32, row_end: u32, s: Stream) c_int;
@@ -53,7 +56,7 @@ pub const c = struct {
 };
 
 /// Zig error set the status codes map onto (names as in the reference: image.zig:637,970,531-536; fdm.zig:114,142).
-pub const Error = error{ DimensionMismatch, InvalidSigma, Unsupported, NotConverged, InvalidArgument, OutOfMemory, DeviceFailure, InvalidScaleFactor, InvalidDimensions, NoTargetSet, NoSourceSet, InsufficientData, InvalidComponents, InvalidThreshold, InvalidPercentile, InvalidTrim };
+pub const Error = error{ DimensionMismatch, InvalidSigma, Unsupported, NotConverged, InvalidArgument, OutOfMemory, DeviceFailure, InvalidScaleFactor, InvalidDimensions, NoTargetSet, NoSourceSet, InsufficientData, InvalidComponents, InvalidThreshold, InvalidPercentile, InvalidTrim, ImageTooSmall };
 
 pub fn check(status: c_int) Error!void {
     return switch (status) {
@@ -73,6 +76,7 @@ pub fn check(status: c_int) Error!void {
         14 => error.InvalidThreshold,
         15 => error.InvalidPercentile,
         16 => error.InvalidTrim,
+        17 => error.ImageTooSmall,
         else => error.InvalidArgument,
     };
 }

@@ -83,6 +83,9 @@ def _declare(L):
         "zb_gaussian_taps": ([f, fp, i, P(i)], i),
         "zb_sobel": ([img, img, i, vp], i),
         "zb_canny": ([img, img, i, f, f, f, vp], i),
+        "zb_psnr": ([img, img, i, P(C.c_double), vp], i),
+        "zb_ssim": ([img, img, i, P(C.c_double), vp], i),
+        "zb_mean_pixel_error": ([img, img, i, P(C.c_double), vp], i),
         "zb_order_blur": ([img, img, i, u32, i, C.c_double, i, vp], i),
         "zb_insert": ([img, img, i, f, f, f, f, f, f, f, i, f, f, vp], i),
         "zb_extract": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),

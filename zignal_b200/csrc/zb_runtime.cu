@@ -96,6 +96,7 @@ const char* zb_status_name(int status) {
         case ZB_ERR_INVALID_THRESHOLD: return "InvalidThreshold";
         case ZB_ERR_INVALID_PERCENTILE: return "InvalidPercentile";
         case ZB_ERR_INVALID_TRIM: return "InvalidTrim";
+        case ZB_ERR_IMAGE_TOO_SMALL: return "ImageTooSmall";
     }
     return "Unknown";
 }

@@ -275,6 +275,27 @@ class Image:
         check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
         return out
 
+    # ---- quality metrics (image.zig:1105-1147, metrics.zig) ----
+    def _metric(self, fn, other: "Image") -> float:
+        if other.pixfmt != self.pixfmt:
+            raise TypeError("metrics compare images of the same pixel type (Image(T).psnr(other: Image(T)))")
+        out = C.c_double(0.0)
+        a, b = self._zb(), other._zb()
+        check(fn(a, b, int(self.pixfmt), C.byref(out), current_stream()))
+        return out.value
+
+    def psnr(self, other: "Image") -> float:
+        """Image.psnr (image.zig:1105, metrics.zig:10-54): dB, inf for identical images."""
+        return self._metric(lib().zb_psnr, other)
+
+    def ssim(self, other: "Image") -> float:
+        """Image.ssim (image.zig:1126, metrics.zig:56-114): mean SSIM over the interior, 11x11 Gaussian window (sigma 1.5)."""
+        return self._metric(lib().zb_ssim, other)
+
+    def mean_pixel_error(self, other: "Image") -> float:
+        """Image.meanPixelError (image.zig:1145, metrics.zig:116-165): mean absolute component difference / component range."""
+        return self._metric(lib().zb_mean_pixel_error, other)
+
     # ---- order-statistic filters (image.zig:650-790, order_statistic_blur.zig) ----
     def _order(self, radius: int, mode: int, param: float, border: BorderMode, out: Optional["Image"]) -> "Image":
         if out is None:

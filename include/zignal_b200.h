@@ -194,6 +194,16 @@ int zb_canny(const zb_image* src, zb_image* dst_u8, int pixfmt, float sigma, flo
 enum { ZB_ORDER_PERCENTILE = 0, ZB_ORDER_MIDPOINT = 1, ZB_ORDER_ALPHA_TRIMMED = 2 };
 int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border, zb_stream s);
 
+/* Image.motionBlur(out, allocator, .{ .linear = .{ .angle, .distance } })   image/motion_blur.zig:65-250.  cos / sin of the angle cross the
+ * ABI as data (like rotateInto).  distance 0 copies; |sin| < 0.001 or |cos| < 0.001 is the reference's convolveSeparable branch (uniform
+ * kernel, .replicate: the fused / tile convolution kernels); any other angle is the per-pixel line integral of bilinear samples
+ * (src must not alias dst there). */
+int zb_motion_blur_linear(const zb_image* src, zb_image* dst, int pixfmt, float angle, float cos_a, float sin_a, uint32_t distance, zb_stream s);
+/* Image.motionBlur(..., .{ .radial_zoom | .radial_spin = .{ .center_x, .center_y, .strength } })   motion_blur.zig:252-436; spin != 0 selects
+ * radial_spin.  Zoom is bit-exact; spin evaluates atan2 / cos / sin per sample on the device (last-bit libm differences: 1e-5 relative,
+ * at most one 8-bit step on isolated pixels). */
+int zb_motion_blur_radial(const zb_image* src, zb_image* dst, int pixfmt, float center_x, float center_y, float strength, int spin, zb_stream s);
+
 /* Image.psnr(other) / Image.ssim(other) / Image.meanPixelError(other)   image.zig:1105-1147, image/metrics.zig:10-165: f64 quality
  * metrics of two device images of the same pixel format (U8, F32, RGB8, RGBA8, RGBAF32); *out is a HOST double, so each call waits
  * for the stream.  8-bit psnr / meanPixelError reproduce the reference's value exactly (integer sums); float formats and ssim
@@ -214,6 +224,13 @@ int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, flo
  * (Blending != .none) and mixed pixel types are not on this path. */
 int zb_insert(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
               float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, zb_stream s);
+/* Image.insert(source, rect, angle, method, blend_mode) with a Blending mode (blending.zig:8-22, enum order): Rgba(u8) samples are
+ * composited onto the Rgba(u8) destination by blendColors(u8, dest, sample, mode) (blending.zig:26-156, f32 arithmetic, Porter-Duff
+ * "over" for the alpha); for every other pixel type the sample is assigned, as image.zig:67-95 assignPixel does. */
+enum { ZB_BLEND_NONE = 0, ZB_BLEND_NORMAL, ZB_BLEND_MULTIPLY, ZB_BLEND_SCREEN, ZB_BLEND_OVERLAY, ZB_BLEND_SOFT_LIGHT, ZB_BLEND_HARD_LIGHT,
+       ZB_BLEND_COLOR_DODGE, ZB_BLEND_COLOR_BURN, ZB_BLEND_DARKEN, ZB_BLEND_LIGHTEN, ZB_BLEND_DIFFERENCE, ZB_BLEND_EXCLUSION };
+int zb_insert_blend(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+                    float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int blend_mode, zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Linear algebra behind fdm / pca

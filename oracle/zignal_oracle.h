@@ -112,6 +112,10 @@ int zo_psnr(const zo_image* a, const zo_image* b, int pixfmt, double* out);
 int zo_ssim(const zo_image* a, const zo_image* b, int pixfmt, double* out);
 int zo_mean_pixel_error(const zo_image* a, const zo_image* b, int pixfmt, double* out);
 void zo_ssim_window(double* w121);
+/* motion_blur.zig:115-250: the diagonal branch of MotionBlur.linear (distance > 0; cos / sin of the angle are data) and :252-436 radial
+ * zoom (spin = 0) / spin (spin = 1); center in normalised [0, 1] coordinates.  Any of the five pixel formats. */
+int zo_motion_blur_line(const zo_image* src, zo_image* dst, int pixfmt, float cos_angle, float sin_angle, uint32_t distance);
+int zo_motion_blur_radial(const zo_image* src, zo_image* dst, int pixfmt, float center_x, float center_y, float strength, int spin);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 
@@ -138,6 +142,13 @@ int zo_extract(const zo_image* src, zo_image* dst, int pixfmt, float rl, float r
 /* transforms.zig:293-376 (insert) for blend_mode == .none and a source of the destination's pixel type: `self` is modified in place. */
 int zo_insert(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
               float sin_a, int method, float mitchell_b, float mitchell_c);
+/* blending.zig:8-22 Blending (enum order) and :26-156 blendColors(u8, ...); insert with a blend mode blends Rgba(u8) samples into an
+ * Rgba(u8) destination (image.zig:67-95 assignPixel) and assigns for every other pixel type. */
+enum { ZO_BLEND_NONE = 0, ZO_BLEND_NORMAL, ZO_BLEND_MULTIPLY, ZO_BLEND_SCREEN, ZO_BLEND_OVERLAY, ZO_BLEND_SOFT_LIGHT, ZO_BLEND_HARD_LIGHT,
+       ZO_BLEND_COLOR_DODGE, ZO_BLEND_COLOR_BURN, ZO_BLEND_DARKEN, ZO_BLEND_LIGHTEN, ZO_BLEND_DIFFERENCE, ZO_BLEND_EXCLUSION };
+void zo_blend_rgba8(const uint8_t* base4, const uint8_t* overlay4, int mode, uint8_t* out4);
+int zo_insert_blend(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+                    float sin_a, int method, float mb, float mc, int blend);
 /* transforms.zig:522-531 with project() of geometry/transforms.zig:39,147,224.
  * m is row-major: similarity/affine: {m00,m01,m10,m11,b0,b1}; projective: 9 values. */
 int zo_warp(const zo_image* src, zo_image* dst, int pixfmt, int xform_kind, const float* m,

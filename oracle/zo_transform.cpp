@@ -173,11 +173,66 @@ static void extract(const zo_image* src, zo_image* dst, float rl, float rt, floa
     }
 }
 
-// transforms.zig:293-376 (insert, blend_mode == .none, source and destination of the same pixel type): a gather over the
+// blending.zig:26-156 blendColors(u8, base, overlay, mode): Rgba(u8) in / out, f32 arithmetic in the reference's operation order
+// (separately rounded; the Makefile's -ffp-contract=off keeps it that way).  mode follows the enum order of blending.zig:8-22.
+static Rgba8 blend_rgba8(Rgba8 base, Rgba8 overlay, int mode) {
+    if (mode == ZO_BLEND_NONE) return overlay;                                   // :27
+    if (overlay.v[3] == 0) return base;                                          // :30
+    if (base.v[3] == 0) return overlay;                                          // :33
+    if (mode == ZO_BLEND_NORMAL && overlay.v[3] == 255) return overlay;          // :36
+    float b[4], o[4], bl[3];
+    for (int k = 0; k < 4; ++k) { b[k] = (float)base.v[k] / 255.0f; o[k] = (float)overlay.v[k] / 255.0f; }   // color.zig:484-494 as(f32)
+    for (int k = 0; k < 3; ++k) {
+        const float bv = b[k], ov = o[k];
+        float r;
+        switch (mode) {
+            case ZO_BLEND_NORMAL: r = ov; break;
+            case ZO_BLEND_MULTIPLY: r = bv * ov; break;
+            case ZO_BLEND_SCREEN: r = 1.0f - (1.0f - bv) * (1.0f - ov); break;
+            case ZO_BLEND_OVERLAY: r = bv < 0.5f ? 2.0f * bv * ov : 1.0f - 2.0f * (1.0f - bv) * (1.0f - ov); break;
+            case ZO_BLEND_SOFT_LIGHT:
+                r = ov <= 0.5f ? bv - (1.0f - 2.0f * ov) * bv * (1.0f - bv) : bv + (2.0f * ov - 1.0f) * (std::sqrt(bv) - bv);
+                break;
+            case ZO_BLEND_HARD_LIGHT: r = ov < 0.5f ? 2.0f * ov * bv : 1.0f - 2.0f * (1.0f - ov) * (1.0f - bv); break;
+            case ZO_BLEND_COLOR_DODGE: r = bv == 0.0f ? 0.0f : (ov >= 1.0f ? 1.0f : std::fmin(1.0f, bv / (1.0f - ov))); break;
+            case ZO_BLEND_COLOR_BURN: r = bv >= 1.0f ? 1.0f : (ov <= 0.0f ? 0.0f : std::fmax(0.0f, 1.0f - (1.0f - bv) / ov)); break;
+            case ZO_BLEND_DARKEN: r = std::fmin(bv, ov); break;
+            case ZO_BLEND_LIGHTEN: r = std::fmax(bv, ov); break;
+            case ZO_BLEND_DIFFERENCE: r = std::fabs(bv - ov); break;
+            default: r = bv + ov - 2.0f * bv * ov; break;                        // exclusion
+        }
+        bl[k] = r;
+    }
+    float out[4];
+    if (overlay.v[3] == 255) {                                                   // :127-136
+        out[0] = bl[0]; out[1] = bl[1]; out[2] = bl[2]; out[3] = 1.0f;
+    } else {                                                                     // :137-154 Porter-Duff "over"
+        const float result_a = o[3] + b[3] * (1.0f - o[3]);
+        if (result_a <= 0) return Rgba8{{0, 0, 0, 0}};
+        const float base_weight = b[3] * (1.0f - o[3]);
+        const float inv_result_a = 1.0f / result_a;
+        for (int k = 0; k < 3; ++k) out[k] = (bl[k] * o[3] + b[k] * base_weight) * inv_result_a;
+        out[3] = result_a;
+    }
+    Rgba8 res;
+    for (int k = 0; k < 4; ++k) {                                                // color.zig:496-501 as(u8): @round(255 * clamp(v, 0, 1))
+        const float c = std::fmax(0.0f, std::fmin(out[k], 1.0f));
+        res.v[k] = (uint8_t)std::round(255.0f * c);
+    }
+    return res;
+}
+
+// image.zig:67-95 assignPixel for source and destination of the same pixel type: only Rgba(u8) samples blend (:74).
+template <typename T> static inline void assign_pixel(T& dest, const T& sample, int) { dest = sample; }
+template <> inline void assign_pixel<Rgba8>(Rgba8& dest, const Rgba8& sample, int blend) {
+    dest = blend == ZO_BLEND_NONE ? sample : blend_rgba8(dest, sample, blend);
+}
+
+// transforms.zig:293-376 (insert, source and destination of the same pixel type): a gather over the
 // destination pixels of the rotated rectangle's bounding box; pixels outside the rectangle or with a null sample stay untouched.
 template <typename PX>
 static void insert(zo_image* self_img, const zo_image* source_img, float rl, float rt, float rr, float rb, float angle, float cos_a,
-                   float sin_a, int method, float mb, float mc) {
+                   float sin_a, int method, float mb, float mc, int blend) {
     using T = typename PX::T;
     Img<T> self(self_img), source(source_img);
     if (source.rows == 0 || source.cols == 0) return;
@@ -190,7 +245,7 @@ static void insert(zo_image* self_img, const zo_image* source_img, float rl, flo
             const int64_t y = (int64_t)dst_top + r;
             for (uint32_t c = 0; c < source.cols; ++c) {
                 const int64_t x = (int64_t)dst_left + c;
-                if (y >= 0 && y < (int64_t)self.rows && x >= 0 && x < (int64_t)self.cols) self.at((uint32_t)y, (uint32_t)x) = source.at(r, c);
+                if (y >= 0 && y < (int64_t)self.rows && x >= 0 && x < (int64_t)self.cols) assign_pixel(self.at((uint32_t)y, (uint32_t)x), source.at(r, c), blend);
             }
         }
         return;
@@ -218,7 +273,7 @@ static void insert(zo_image* self_img, const zo_image* source_img, float rl, flo
             const float src_x = source.cols == 1 ? 0.0f : norm_x * (fcols - 1);
             const float src_y = source.rows == 1 ? 0.0f : norm_y * (frows - 1);
             T val;
-            if (interpolate<PX>(source, src_x, src_y, method, mb, mc, ZO_BORDER_MIRROR, &val)) self.at(r, c) = val;
+            if (interpolate<PX>(source, src_x, src_y, method, mb, mc, ZO_BORDER_MIRROR, &val)) assign_pixel(self.at(r, c), val, blend);
         }
     }
 }
@@ -227,15 +282,26 @@ static void insert(zo_image* self_img, const zo_image* source_img, float rl, flo
 
 extern "C" {
 
+void zo_blend_rgba8(const uint8_t* base, const uint8_t* overlay, int mode, uint8_t* out) {
+    const zo::Rgba8 r = zo::blend_rgba8(zo::Rgba8{{base[0], base[1], base[2], base[3]}}, zo::Rgba8{{overlay[0], overlay[1], overlay[2], overlay[3]}}, mode);
+    for (int k = 0; k < 4; ++k) out[k] = r.v[k];
+}
+
 int zo_insert(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a, float sin_a,
               int method, float mb, float mc) {
+    return zo_insert_blend(self, source, pixfmt, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, ZO_BLEND_NONE);
+}
+
+int zo_insert_blend(zo_image* self, const zo_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
+                    float sin_a, int method, float mb, float mc, int blend) {
     using namespace zo;
+    if (blend < ZO_BLEND_NONE || blend > ZO_BLEND_EXCLUSION) return ZO_ERR_INVALID_ARGUMENT;
     switch (pixfmt) {
-        case ZO_PIX_U8: insert<PxU8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
-        case ZO_PIX_F32: insert<PxF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
-        case ZO_PIX_RGB8: insert<PxRgb8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
-        case ZO_PIX_RGBA8: insert<PxRgba8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
-        case ZO_PIX_RGBAF32: insert<PxRgbaF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc); return ZO_OK;
+        case ZO_PIX_U8: insert<PxU8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, blend); return ZO_OK;
+        case ZO_PIX_F32: insert<PxF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, blend); return ZO_OK;
+        case ZO_PIX_RGB8: insert<PxRgb8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, blend); return ZO_OK;
+        case ZO_PIX_RGBA8: insert<PxRgba8>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, blend); return ZO_OK;
+        case ZO_PIX_RGBAF32: insert<PxRgbaF32>(self, source, rl, rt, rr, rb, angle, cos_a, sin_a, method, mb, mc, blend); return ZO_OK;
     }
     return ZO_ERR_UNSUPPORTED;
 }

@@ -79,6 +79,8 @@ def _declare(L):
     L.zo_order_blur.argtypes = [img, img, C.c_int, C.c_uint32, C.c_int, C.c_double, C.c_int]
     for fn in (L.zo_psnr, L.zo_ssim, L.zo_mean_pixel_error):
         fn.argtypes = [img, img, C.c_int, C.POINTER(C.c_double)]
+    L.zo_motion_blur_line.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_uint32]
+    L.zo_motion_blur_radial.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
     L.zo_canny.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -89,6 +91,9 @@ def _declare(L):
     L.zo_warp.argtypes = [img, img, C.c_int, C.c_int, fp, C.c_int, C.c_float, C.c_float]
     L.zo_extract.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float, C.c_int]
     L.zo_insert.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float]
+    L.zo_insert_blend.argtypes = [img, img, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_float, C.c_float, C.c_int]
+    L.zo_blend_rgba8.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+    L.zo_blend_rgba8.restype = None
     L.zo_svd_f64.argtypes = [dp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, dp, dp, dp]
     L.zo_svd_f64.restype = C.c_int64
     L.zo_svd_f32.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, fp, fp, fp]
@@ -297,6 +302,32 @@ def mean_pixel_error(a, b):
     return _metric(lib().zo_mean_pixel_error, "mean_pixel_error", a, b)
 
 
+def motion_blur_linear(src, angle, distance, cos_sin=None):
+    """MotionBlurOps.linear (motion_blur.zig:65-250): copy, the two convolveSeparable branches, or the diagonal line integral."""
+    a32 = np.float32(angle)
+    if cos_sin is None:
+        cos_sin = (np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32))
+    if distance == 0:
+        return src.copy()
+    kernel = np.full(distance, np.float32(1.0) / np.float32(distance), dtype=np.float32)
+    identity = np.ones(1, np.float32)
+    if abs(float(cos_sin[1])) < 0.001:
+        return conv_separable(src, kernel, identity, "replicate")
+    if abs(float(cos_sin[0])) < 0.001:
+        return conv_separable(src, identity, kernel, "replicate")
+    out = np.zeros_like(src)
+    _check(lib().zo_motion_blur_line(as_image(src), as_image(out), pixfmt_of(src), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), distance),
+           "motion_blur_line")
+    return out
+
+
+def motion_blur_radial(src, center_x, center_y, strength, spin=False):
+    out = np.zeros_like(src)
+    _check(lib().zo_motion_blur_radial(as_image(src), as_image(out), pixfmt_of(src), C.c_float(center_x), C.c_float(center_y),
+                                       C.c_float(strength), int(bool(spin))), "motion_blur_radial")
+    return out
+
+
 def canny(src, sigma, low, high):
     out = np.zeros(src.shape[:2], np.uint8)
     s, d = as_image(src), as_image(out)
@@ -317,15 +348,27 @@ def extract(src, out, rect, angle=0.0, method="bilinear", border="zero", cos_sin
     return out
 
 
-def insert(dest, source, rect, angle=0.0, method="bilinear", cos_sin=None, b=1.0 / 3.0, c=1.0 / 3.0):
-    """dest.insert(source, rect, angle, method, .none) (transforms.zig:293-376); returns the modified copy of dest."""
+BLEND = {name: i for i, name in enumerate(["none", "normal", "multiply", "screen", "overlay", "soft_light", "hard_light", "color_dodge",
+                                            "color_burn", "darken", "lighten", "difference", "exclusion"])}
+
+
+def blend_rgba8(base, overlay, mode):
+    """blendColors(u8, base, overlay, mode) (blending.zig:26-156) on 4-tuples."""
+    out = C.create_string_buffer(4)
+    lib().zo_blend_rgba8(bytes(bytearray(base)), bytes(bytearray(overlay)), BLEND[mode], out)
+    return tuple(out.raw)
+
+
+def insert(dest, source, rect, angle=0.0, method="bilinear", cos_sin=None, b=1.0 / 3.0, c=1.0 / 3.0, blend="none"):
+    """dest.insert(source, rect, angle, method, blend) (transforms.zig:293-376); returns the modified copy of dest."""
     a32 = np.float32(angle)
     if cos_sin is None:
         cos_sin = (np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32))
     out = np.ascontiguousarray(dest).copy()
     d, s = as_image(out), as_image(source)
-    _check(lib().zo_insert(d, s, pixfmt_of(out), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]), C.c_float(a32),
-                           C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), INTERP[method], C.c_float(b), C.c_float(c)), "insert")
+    _check(lib().zo_insert_blend(d, s, pixfmt_of(out), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                                 C.c_float(a32), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]), INTERP[method], C.c_float(b), C.c_float(c),
+                                 BLEND[blend]), "insert")
     return out
 
 

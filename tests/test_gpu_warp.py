@@ -198,3 +198,56 @@ def test_insert(zb, fmt):
         ext = zb.Image.from_numpy(src).extract(zb.Image.init(30, 30, zb.PixFmt.U8), rect, angle, zb.Interpolation.BILINEAR, zb.BorderMode.MIRROR)
         canvas = zb.Image.from_numpy(np.zeros((64, 64), np.uint8)).insert(ext, rect, angle, zb.Interpolation.BILINEAR).to_numpy()
         assert np.abs(src[21:39, 21:39].astype(int) - canvas[21:39, 21:39].astype(int)).mean() < 25
+
+
+BLEND_MODES = ["none", "normal", "multiply", "screen", "overlay", "soft_light", "hard_light", "color_dodge", "color_burn", "darken", "lighten",
+               "difference", "exclusion"]
+
+
+def test_insert_blend_modes(zb):
+    """Image.insert with a Blending mode (blending.zig:26-156 through image.zig:67-95 assignPixel): Rgba(u8) onto Rgba(u8), all thirteen
+    modes, bit-exact; alpha values 0 / 255 and the channel extremes 0 / 255 are over-represented so every early return and every
+    dodge / burn guard is hit.  Other pixel types ignore the mode."""
+    rng = np.random.default_rng(2024)
+
+    def biased(shape):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        pick = rng.random(shape)
+        img[pick < 0.12] = 0
+        img[pick > 0.88] = 255
+        img[rng.random(shape) < 0.1] = 128
+        return img
+
+    dest = biased((70, 90, 4))
+    cases = [((40, 50), (10.0, 8.0, 60.0, 48.0), 0.0, "nearest"),          # axis-aligned copy path with blending
+             ((23, 31), (5.5, 4.0, 80.0, 66.0), 0.35, "bilinear"),
+             ((17, 12), (-8.0, 30.0, 40.0, 75.0), -1.1, "bicubic")]
+    for src_shape, rect, angle, method in cases:
+        source = biased(src_shape + (4,))
+        for i, mode in enumerate(BLEND_MODES):
+            dev = zb.Image.from_numpy(dest.copy())
+            got = dev.insert(zb.Image.from_numpy(source), rect, angle, getattr(zb.Interpolation, method.upper()), blend=zb.Blending(i)).to_numpy()
+            want = zo.insert(dest, source, rect, angle, method, blend=mode)
+            assert np.array_equal(got, want), (src_shape, mode, int((got != want).sum()))
+    # exhaustive over one channel pair at several alphas: 256 x 256 base / overlay values per mode through the copy path
+    b, o = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for alpha_b, alpha_o in [(255, 255), (255, 128), (77, 201), (1, 254)]:
+        base = np.stack([b, b[::-1], o, np.full_like(b, alpha_b)], axis=-1)
+        over = np.stack([o, o, b[::-1], np.full_like(b, alpha_o)], axis=-1)
+        for i, mode in enumerate(BLEND_MODES[1:], start=1):
+            got = zb.Image.from_numpy(base.copy()).insert(zb.Image.from_numpy(over), (0.0, 0.0, 256.0, 256.0), 0.0, zb.Interpolation.NEAREST,
+                                                          blend=zb.Blending(i)).to_numpy()
+            want = zo.insert(base, over, (0.0, 0.0, 256.0, 256.0), 0.0, "nearest", blend=mode)
+            assert np.array_equal(got, want), (mode, alpha_b, alpha_o, int((got != want).sum()))
+    rgb = biased((30, 30, 3))
+    patch = biased((10, 10, 3))
+    got = zb.Image.from_numpy(rgb.copy()).insert(zb.Image.from_numpy(patch), (5.0, 5.0, 15.0, 15.0), 0.0, zb.Interpolation.NEAREST,
+                                                 blend=zb.Blending.MULTIPLY).to_numpy()
+    assert np.array_equal(got, zo.insert(rgb, patch, (5.0, 5.0, 15.0, 15.0), 0.0, "nearest", blend="multiply"))
+    with pytest.raises(zb.ZignalError):
+        zb.lib().zb_insert_blend  # symbol exists
+        from zignal_b200._ffi import check
+        d = zb.Image.from_numpy(rgb.copy())
+        import ctypes as C
+        check(zb.lib().zb_insert_blend(d._zb(), d._zb(), int(d.pixfmt), C.c_float(0), C.c_float(0), C.c_float(1), C.c_float(1), C.c_float(0),
+                                       C.c_float(1), C.c_float(0), 0, C.c_float(0), C.c_float(0), 13, None))

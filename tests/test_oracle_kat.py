@@ -712,6 +712,45 @@ def test_metrics_kats():
     assert 0.0 < zo.ssim(xf, yf) < 1.0 and abs(zo.mean_pixel_error(xf, yf) - np.abs(xf.astype(np.float64) - yf).mean()) < 1e-12
 
 
+def test_blend_kats():
+    """blending.zig:194-421: the reference's own blendColors(u8, ...) expectations, and insert with a blend mode on an Rgba(u8) canvas."""
+    B = zo.blend_rgba8
+    r = B((100, 100, 100, 255), (200, 200, 200, 128), "normal")
+    assert all(140 < v < 160 for v in r[:3])
+    assert B((255, 255, 255, 255), (128, 128, 128, 255), "multiply")[:3] == (128, 128, 128)
+    assert B((0, 0, 0, 255), (128, 128, 128, 255), "screen")[:3] == (128, 128, 128)
+    assert B((100, 100, 100, 255), (200, 200, 200, 0), "normal") == (100, 100, 100, 255)
+    r = B((100, 100, 100, 128), (200, 200, 200, 128), "normal")
+    assert 190 <= r[3] <= 192 and 130 < r[0] < 170
+    r = B((0, 0, 0, 0), (200, 150, 100, 180), "normal")
+    assert r[3] == 180 and abs(r[0] - 200) <= 1 and abs(r[1] - 150) <= 1 and abs(r[2] - 100) <= 1
+    m, sc = B((100, 100, 100, 200), (50, 50, 50, 100), "multiply"), B((100, 100, 100, 200), (50, 50, 50, 100), "screen")
+    assert abs(m[3] - 221) <= 2 and abs(sc[3] - 221) <= 2 and m[0] < sc[0]
+    for mode in ("multiply", "screen", "exclusion"):
+        assert B((25, 75, 125, 0), (200, 150, 100, 180), mode) == (200, 150, 100, 180)
+    assert B((100, 100, 100, 255), (200, 200, 200, 255), "none") == (200, 200, 200, 255)
+    assert B((100, 200, 100, 255), (200, 100, 100, 255), "darken")[:3] == (100, 100, 100)
+    assert B((100, 200, 100, 255), (200, 100, 100, 255), "lighten")[:3] == (200, 200, 100)
+    assert B((200, 100, 50, 255), (50, 200, 200, 255), "difference")[:3] == (150, 100, 150)
+    assert B((0, 128, 255, 255), (255, 255, 255, 255), "color_dodge")[:3] == (0, 255, 255)      # B = 0 -> 0; S = 1 -> 1 (W3C)
+    assert B((255, 128, 0, 255), (0, 0, 0, 255), "color_burn")[:3] == (255, 0, 0)                # B = 1 -> 1; S = 0 -> 0
+    # float identities from the f32 tests, on values exactly representable as n / 255: overlay / hard light swap roles.
+    for b in (0, 51, 102, 153, 204, 255):
+        for o in (0, 85, 170, 255):
+            assert B((b, b, b, 255), (o, o, o, 255), "overlay") == B((o, o, o, 255), (b, b, b, 255), "hard_light")
+            e = b / 255 + o / 255 - 2 * (b / 255) * (o / 255)
+            assert abs(B((b, b, b, 255), (o, o, o, 255), "exclusion")[0] - 255 * e) <= 0.5 + 1e-3
+    canvas = np.full((6, 6, 4), 255, np.uint8)
+    canvas[..., :3] = 100
+    patch = np.zeros((2, 2, 4), np.uint8)
+    patch[...] = (200, 200, 200, 128)
+    out = zo.insert(canvas, patch, (2.0, 2.0, 4.0, 4.0), 0.0, "nearest", blend="normal")
+    assert tuple(out[2, 2]) == B((100, 100, 100, 255), (200, 200, 200, 128), "normal") and tuple(out[0, 0]) == (100, 100, 100, 255)
+    gray = np.full((6, 6), 9, np.uint8)
+    assert np.array_equal(zo.insert(gray, np.full((2, 2), 77, np.uint8), (2.0, 2.0, 4.0, 4.0), 0.0, "nearest", blend="multiply")[2:4, 2:4],
+                          np.full((2, 2), 77, np.uint8))                                         # non-Rgba samples are assigned (image.zig:90-94)
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

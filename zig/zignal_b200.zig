@@ -36,8 +36,11 @@ pub const c = struct {
     // widening rows (SURVEY 8f): extract / crop, insert (.none), sobel, setBorder(zeroes), and the sharding extension
     pub extern fn zb_extract(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, border: c_int, s: Stream) c_int;
     pub extern fn zb_insert(self: *ZbImage, source: *const ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, s: Stream) c_int;
+    pub extern fn zb_insert_blend(self: *ZbImage, source: *const ZbImage, pixfmt: c_int, l: f32, t: f32, r: f32, b: f32, angle: f32, cos_a: f32, sin_a: f32, method: c_int, mb: f32, mc: f32, blend_mode: c_int, s: Stream) c_int;
     pub extern fn zb_sobel(src: *const ZbImage, dst_u8: *ZbImage, pixfmt: c_int, s: Stream) c_int;
     pub extern fn zb_order_blur(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, radius: u32, mode: c_int, param: f64, border: c_int, s: Stream) c_int;
+    pub extern fn zb_motion_blur_linear(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, angle: f32, cos_a: f32, sin_a: f32, distance: u32, s: Stream) c_int;
+    pub extern fn zb_motion_blur_radial(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, center_x: f32, center_y: f32, strength: f32, spin: c_int, s: Stream) c_int;
     pub extern fn zb_psnr(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_ssim(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_mean_pixel_error(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;

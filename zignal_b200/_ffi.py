@@ -83,11 +83,14 @@ def _declare(L):
         "zb_gaussian_taps": ([f, fp, i, P(i)], i),
         "zb_sobel": ([img, img, i, vp], i),
         "zb_canny": ([img, img, i, f, f, f, vp], i),
+        "zb_motion_blur_linear": ([img, img, i, f, f, f, u32, vp], i),
+        "zb_motion_blur_radial": ([img, img, i, f, f, f, i, vp], i),
         "zb_psnr": ([img, img, i, P(C.c_double), vp], i),
         "zb_ssim": ([img, img, i, P(C.c_double), vp], i),
         "zb_mean_pixel_error": ([img, img, i, P(C.c_double), vp], i),
         "zb_order_blur": ([img, img, i, u32, i, C.c_double, i, vp], i),
         "zb_insert": ([img, img, i, f, f, f, f, f, f, f, i, f, f, vp], i),
+        "zb_insert_blend": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
         "zb_extract": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
         "zb_set_border_zero": ([img, i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp], i),
         "zb_conv_separable": ([img, img, i, fp, i, fp, i, i, vp], i),

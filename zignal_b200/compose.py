@@ -63,20 +63,22 @@ class ImagePyramid:
 
 
 def motion_blur_linear(image: Image, out: Image, angle: float, distance: int) -> Image:
-    """MotionBlur.linear for axis-aligned motion (motion_blur.zig:65-114).  Diagonal motion is a per-pixel line integral
-    (:115-250) outside this path: it raises Unsupported."""
-    if distance == 0:                                                            # :66-69
-        image.copy(out)
-        return out
-    cos_a, sin_a = np.cos(np.float32(angle)), np.sin(np.float32(angle))
-    eps = 0.001
-    kernel = np.full(distance, np.float32(1.0) / np.float32(distance), dtype=np.float32)   # :88-91
-    identity = np.ones(1, np.float32)
-    if abs(float(sin_a)) < eps:                                                  # horizontal, :80-97
-        return image.convolve_separable(kernel, identity, BorderMode.REPLICATE, out=out)
-    if abs(float(cos_a)) < eps:                                                  # vertical, :98-114
-        return image.convolve_separable(identity, kernel, BorderMode.REPLICATE, out=out)
-    raise ZignalError(3, "Unsupported")
+    """MotionBlur.linear (motion_blur.zig:65-250): copy for distance 0, convolveSeparable with a uniform kernel for axis-aligned motion,
+    the per-pixel line integral of bilinear samples for any other angle.  cos / sin are taken in f32 on the host (`@cos(angle)`)."""
+    a32 = np.float32(angle)
+    cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
+    a, d = image._zb(), out._zb()
+    check(lib().zb_motion_blur_linear(a, d, int(image.pixfmt), C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), C.c_uint32(distance),
+                                      current_stream()))
+    return out
+
+
+def motion_blur_radial(image: Image, out: Image, center_x: float, center_y: float, strength: float, spin: bool = False) -> Image:
+    """MotionBlur.radial_zoom / radial_spin (motion_blur.zig:252-436): center in normalised [0, 1] coordinates, strength in [0, 1]."""
+    a, d = image._zb(), out._zb()
+    check(lib().zb_motion_blur_radial(a, d, int(image.pixfmt), C.c_float(center_x), C.c_float(center_y), C.c_float(strength), int(bool(spin)),
+                                      current_stream()))
+    return out
 
 
 def set_border_zero(img: Image, rect: Rectangle) -> None:

@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "zb_host_stage.h"
+#include "zb_blend.cuh"
 #include "zb_sample.cuh"
 #include "zb_warp.h"
 
@@ -359,13 +360,15 @@ int extract_dispatch(const zb_image* src, zb_image* dst, int pixfmt, float rl, f
     return ZB_ERR_UNSUPPORTED;
 }
 
-// ---- Image.insert (transforms.zig:293-376), blend_mode .none, same pixel type: the complement of extract -----------------------
+// ---- Image.insert (transforms.zig:293-376), same pixel type: the complement of extract; Rgba(u8) samples composite under a blend
+// mode (image.zig:67-95 assignPixel), every other pixel type assigns -----------------------------------------------------------
 struct InsertParams {
     float cx, cy, cos_a, sin_a, half_w, half_h, inv_w, inv_h, fcols1, frows1;
     int copy_rect, dst_top, dst_left;      // fast path: source pixel (r, c) lands on (dst_top + r, dst_left + c)
     int min_r, min_c, n_r, n_c;            // destination window this launch covers
     int src_rows, src_cols, method;
     float mb, mc;
+    int blend;                             // ZB_BLEND_*; only Rgba(u8) pixels composite
 };
 
 template <typename CT, int N, int METHOD>
@@ -389,6 +392,9 @@ __global__ void __launch_bounds__(256) insert_kernel(SrcView source, CT* __restr
         const float src_y = p.src_rows == 1 ? 0.0f : norm_y * p.frows1;
         if (!interpolate<CT, N, METHOD, ZB_BORDER_MIRROR>(source, src_x, src_y, p.mb, p.mc, ZB_BORDER_MIRROR, lut, val)) return;
     }
+    if constexpr (sizeof(CT) == 1 && N == 4) {
+        if (p.blend != ZB_BLEND_NONE) val.u = blend_rgba8(load_px<CT, N>(self, (size_t)r * self_stride + c).u, val.u, p.blend);
+    }
     store_px<CT, N>(self, (size_t)r * self_stride + c, val);
 }
 
@@ -404,8 +410,9 @@ int insert_typed(zb_image* self, const zb_image* source, const InsertParams& p, 
 }
 
 int insert_dispatch(zb_image* self, const zb_image* source, int pixfmt, float rl, float rt, float rr, float rb, float angle, float cos_a,
-                    float sin_a, int method, float mb, float mc, cudaStream_t s) {
+                    float sin_a, int method, float mb, float mc, int blend, cudaStream_t s) {
     if (!self || !source) return ZB_ERR_INVALID_ARGUMENT;
+    if (blend < ZB_BLEND_NONE || blend > ZB_BLEND_EXCLUSION) return ZB_ERR_INVALID_ARGUMENT;
     if (channels_of(pixfmt) == 0) return ZB_ERR_UNSUPPORTED;
     if (method < ZB_INTERP_NEAREST || method > ZB_INTERP_LANCZOS) return ZB_ERR_INVALID_ARGUMENT;
     if (source->rows == 0 || source->cols == 0) return ZB_OK;   // :294
@@ -420,6 +427,7 @@ int insert_dispatch(zb_image* self, const zb_image* source, int pixfmt, float rl
     const float epsilon = 1e-6f;
     p.src_rows = (int)source->rows; p.src_cols = (int)source->cols;
     p.method = method; p.mb = mb; p.mc = mc;
+    p.blend = blend;
     long long r0, r1, c0, c1;   // destination window [r0, r1) x [c0, c1)
     if (std::fabs(angle) < epsilon && std::fabs(rect_width - fcols) < epsilon && std::fabs(rect_height - frows) < epsilon) {   // :305-323
         p.copy_rect = 1;
@@ -531,7 +539,13 @@ int zb_rotate_into_batch(const zb_image* src0, uint64_t src_image_pitch_px, zb_i
 int zb_insert(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
               float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, zb_stream s) {
     return insert_dispatch(self, source, pixfmt, rect_l, rect_t, rect_r, rect_b, angle, cos_a, sin_a, method, mitchell_b, mitchell_c,
-                           (cudaStream_t)s);
+                           ZB_BLEND_NONE, (cudaStream_t)s);
+}
+
+int zb_insert_blend(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
+                    float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int blend_mode, zb_stream s) {
+    return insert_dispatch(self, source, pixfmt, rect_l, rect_t, rect_r, rect_b, angle, cos_a, sin_a, method, mitchell_b, mitchell_c,
+                           blend_mode, (cudaStream_t)s);
 }
 
 int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,

@@ -36,6 +36,22 @@ class BorderMode(IntEnum):  # reference border.zig:10-19
     WRAP = 3
 
 
+class Blending(IntEnum):  # reference blending.zig:8-22
+    NONE = 0
+    NORMAL = 1
+    MULTIPLY = 2
+    SCREEN = 3
+    OVERLAY = 4
+    SOFT_LIGHT = 5
+    HARD_LIGHT = 6
+    COLOR_DODGE = 7
+    COLOR_BURN = 8
+    DARKEN = 9
+    LIGHTEN = 10
+    DIFFERENCE = 11
+    EXCLUSION = 12
+
+
 class Interpolation(IntEnum):  # reference interpolation.zig:53-68
     NEAREST = 0
     BILINEAR = 1
@@ -349,13 +365,15 @@ class Image:
         return out
 
     def insert(self, source: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
-               b: float = 1 / 3, c: float = 1 / 3) -> "Image":
-        """Image.insert(source, rect, angle, method, .none) (transforms.zig:293-376): modifies self in place."""
+               b: float = 1 / 3, c: float = 1 / 3, blend: "Blending" = Blending.NONE) -> "Image":
+        """Image.insert(source, rect, angle, method, blend_mode) (transforms.zig:293-376): modifies self in place.  Rgba(u8) samples are
+        composited under a blend mode (blending.zig:26-156); other pixel types are assigned (image.zig:67-95)."""
         a32 = np.float32(angle)
         cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
         d, s = self._zb(), source._zb()
-        check(lib().zb_insert(d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
-                              C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        check(lib().zb_insert_blend(d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                                    C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(blend),
+                                    current_stream()))
         return self
 
     def crop(self, rect) -> "Image":

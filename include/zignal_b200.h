@@ -85,7 +85,10 @@ typedef enum zb_status {
     ZB_ERR_INVALID_THRESHOLD = 14, /* error.InvalidThreshold (edges.zig:225-226) */
     ZB_ERR_INVALID_PERCENTILE = 15, /* error.InvalidPercentile (order_statistic_blur.zig:49) */
     ZB_ERR_INVALID_TRIM = 16,      /* error.InvalidTrim (order_statistic_blur.zig:161) */
-    ZB_ERR_IMAGE_TOO_SMALL = 17    /* error.ImageTooSmall (metrics.zig:61) */
+    ZB_ERR_IMAGE_TOO_SMALL = 17,   /* error.ImageTooSmall (metrics.zig:61) */
+    ZB_ERR_NOT_SQUARE = 18,        /* error.NotSquare (eigen.zig:36) */
+    ZB_ERR_NOT_SYMMETRIC = 19,     /* error.NotSymmetric (eigen.zig:54) */
+    ZB_ERR_NOT_FINITE = 20         /* error.NotFinite (eigen.zig:49) */
 } zb_status;
 
 /* ------------------------------------------------------------------------------------------------
@@ -253,6 +256,11 @@ int zb_center_columns_f64(const double* x, uint32_t n, uint32_t dim, double* mea
  * *converged receives 0 or the failing index (svd.zig:79). */
 int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged);
 int zb_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v, float* u, float* s, float* v, uint64_t* converged);
+/* Matrix.eigh(allocator)   matrix/eigen.zig:34-136: symmetric eigendecomposition by cyclic Jacobi rotations (HOST pointers, row-major
+ * n x n).  values[n] ascending, vectors[n * n] with the matching unit eigenvectors as columns.  ZB_ERR_NOT_SQUARE, ZB_ERR_NOT_FINITE
+ * (NaN / inf entry), ZB_ERR_NOT_SYMMETRIC (|a_ij - a_ji| > max|a| * sqrt(eps)).  A host routine like the SVD: replicas only. */
+int zb_eigh_f64(const double* a, uint32_t rows, uint32_t cols, double* values, double* vectors);
+int zb_eigh_f32(const float* a, uint32_t rows, uint32_t cols, float* values, float* vectors);
 
 /* ------------------------------------------------------------------------------------------------
  * Feature distribution matching   fdm.zig:19-275

@@ -63,7 +63,7 @@ enum {
     ZO_OK = 0, ZO_ERR_DIMENSION_MISMATCH = 1, ZO_ERR_INVALID_SIGMA = 2, ZO_ERR_UNSUPPORTED = 3,
     ZO_ERR_NOT_CONVERGED = 4, ZO_ERR_INVALID_ARGUMENT = 5 /* also error.InvalidParameter */,
     ZO_ERR_INVALID_THRESHOLD = 14 /* edges.zig:225-226 */, ZO_ERR_INVALID_PERCENTILE = 15, ZO_ERR_INVALID_TRIM = 16 /* order_statistic_blur.zig:15-20 */,
-    ZO_ERR_IMAGE_TOO_SMALL = 17 /* metrics.zig:61 */
+    ZO_ERR_IMAGE_TOO_SMALL = 17 /* metrics.zig:61 */, ZO_ERR_NOT_SQUARE = 18, ZO_ERR_NOT_SYMMETRIC = 19, ZO_ERR_NOT_FINITE = 20 /* eigen.zig:34-54 */
 };
 
 /* Number of OpenMP threads the row-parallel loops may use (1 = the reference's behaviour). */
@@ -156,6 +156,9 @@ int zo_warp(const zo_image* src, zo_image* dst, int pixfmt, int xform_kind, cons
 
 /* svd.zig:149-496 on a row-major m x n matrix (m >= n).  u is m x (mode==FULL ? m : n) (ignored
  * for NO_U), s is n, v is n x n (only if with_v).  Returns `converged` (0 = ok, k = failed). */
+/* matrix/eigen.zig:34-136 Matrix.eigh: row-major n x n symmetric input; values[n] ascending, vectors[n*n] with eigenvectors as columns. */
+int zo_eigh_f64(const double* a, uint32_t rows, uint32_t cols, double* values, double* vectors);
+int zo_eigh_f32(const float* a, uint32_t rows, uint32_t cols, float* values, float* vectors);
 int64_t zo_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v,
                    double* u, double* s, double* v);
 int64_t zo_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v,

@@ -401,6 +401,21 @@ def svd(a, mode="skinny_u", with_v=True):
     return u, s, v, rc
 
 
+def eigh(a):
+    """Matrix.eigh (eigen.zig:34-136) -> (values ascending, vectors as columns); raises OracleStatus (18 NotSquare, 19 NotSymmetric, 20 NotFinite)."""
+    a = np.ascontiguousarray(a)
+    rows, cols = a.shape
+    values = np.zeros(rows, a.dtype)
+    vectors = np.zeros((rows, rows), a.dtype)
+    if a.dtype == np.float64:
+        rc = lib().zo_eigh_f64(_dptr(a), rows, cols, _dptr(values), _dptr(vectors))
+    else:
+        rc = lib().zo_eigh_f32(_fptr(a), rows, cols, _fptr(values), _fptr(vectors))
+    if rc != 0:
+        raise OracleStatus(rc, "eigh")
+    return values, vectors
+
+
 def gemm(a, b, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, c=None, vec_len=0):
     a = np.ascontiguousarray(a)
     b = np.ascontiguousarray(b, dtype=a.dtype)

@@ -49,8 +49,68 @@ def test_motion_blur_linear_axis_aligned(zb, shape, distance):
     assert np.array_equal(got_h, zo.conv_separable(img, k, one, "replicate"))
     assert np.array_equal(got_v, zo.conv_separable(img, one, k, "replicate"))
     assert np.array_equal(motion_blur_linear(dev, zb.Image.init_like(dev), 0.3, 0).to_numpy(), img)   # distance 0: copy
+
+
+MOTION_CASES = [((37, 45), np.uint8), ((40, 33, 3), np.uint8), ((29, 31, 4), np.uint8), ((35, 36), np.float32), ((23, 27, 4), np.float32),
+                ((1, 9), np.uint8), ((7, 1), np.uint8)]
+
+
+@pytest.mark.parametrize("shape,dtype", MOTION_CASES)
+def test_motion_blur_linear_diagonal(zb, shape, dtype):
+    """The line-integral branch of MotionBlur.linear (motion_blur.zig:115-250): bit-exact for every pixel type, u8 and f32."""
+    from zignal_b200.compose import motion_blur_linear
+    rng = np.random.default_rng(shape[0] + 31 * shape[1])
+    img = rand_image(rng, shape, dtype)
+    dev = zb.Image.from_numpy(img)
+    for angle, distance in [(np.pi / 4, 3), (0.7, 5), (-1.1, 12), (2.5, 1), (0.0011, 7), (3.0, 40)]:
+        got = motion_blur_linear(dev, zb.Image.init_like(dev), float(angle), distance).to_numpy()
+        assert zb.lib().zb_last_kernel().decode() == "motion_line"
+        assert np.array_equal(got, zo.motion_blur_linear(img, float(angle), distance)), (angle, distance)
     with pytest.raises(zb.ZignalError):
-        motion_blur_linear(dev, zb.Image.init_like(dev), 0.7, 5)
+        motion_blur_linear(dev, dev, 0.7, 5)                      # a gather cannot run in place
+
+
+@pytest.mark.parametrize("shape,dtype", MOTION_CASES)
+def test_motion_blur_radial(zb, shape, dtype):
+    """radial_zoom is bit-exact; radial_spin evaluates atan2 / cos / sin per sample, so it is compared at 1e-5 (f32) / one 8-bit step on at
+    most 0.5 % of the samples (motion_blur.zig:252-436)."""
+    from zignal_b200.compose import motion_blur_radial
+    rng = np.random.default_rng(shape[0] * 5 + shape[1])
+    img = rand_image(rng, shape, dtype)
+    dev = zb.Image.from_numpy(img)
+    for cx, cy, strength in [(0.5, 0.5, 0.5), (0.2, 0.8, 1.0), (0.0, 0.0, 0.3), (1.0, 0.4, 0.05), (0.5, 0.5, 7.0)]:
+        got = motion_blur_radial(dev, zb.Image.init_like(dev), cx, cy, strength).to_numpy()
+        assert zb.lib().zb_last_kernel().decode() == "motion_zoom"
+        assert np.array_equal(got, zo.motion_blur_radial(img, cx, cy, strength)), (cx, cy, strength)
+        got = motion_blur_radial(dev, zb.Image.init_like(dev), cx, cy, strength, spin=True).to_numpy()
+        want = zo.motion_blur_radial(img, cx, cy, strength, spin=True)
+        if dtype == np.uint8:
+            diff = np.abs(got.astype(int) - want.astype(int))
+            assert diff.max() <= 1 and (diff != 0).mean() <= 0.005, (cx, cy, strength, int(diff.max()), float((diff != 0).mean()))
+        else:
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-6), (cx, cy, strength)
+    assert np.array_equal(motion_blur_radial(dev, zb.Image.init_like(dev), 0.5, 0.5, 0.0).to_numpy(), img)       # strength 0: copy
+
+
+def test_motion_blur_reference_cases(zb):
+    """image/tests/filters.zig:1021-1160 through the device path."""
+    from zignal_b200.compose import motion_blur_linear, motion_blur_radial
+    spot = np.zeros((5, 5), np.uint8)
+    spot[2, 2] = 255
+    d = zb.Image.from_numpy(spot)
+    b = motion_blur_linear(d, zb.Image.init_like(d), float(np.float32(np.pi / 4)), 3).to_numpy()
+    assert b[1, 1] > 0 and b[2, 2] > 0 and b[3, 3] > 0
+    yy, xx = np.mgrid[0:7, 0:7].astype(np.float32)
+    dist = np.sqrt((xx - 3) ** 2 + (yy - 3) ** 2)
+    ring = np.where((dist > 1.5) & (dist < 2.5), 255, 0).astype(np.uint8)
+    dr = zb.Image.from_numpy(ring)
+    z = motion_blur_radial(dr, zb.Image.init_like(dr), 0.5, 0.5, 0.5).to_numpy()
+    assert abs(int(z[3, 3]) - int(ring[3, 3])) < 20
+    pt = np.zeros((7, 7), np.uint8)
+    pt[2, 4] = 255
+    dp = zb.Image.from_numpy(pt)
+    sp = motion_blur_radial(dp, zb.Image.init_like(dp), 0.5, 0.5, 0.5, spin=True).to_numpy()
+    assert sp[2, 4] > 0 and int((sp > 0).sum()) > 1
 
 
 @pytest.mark.parametrize("src_shape,dst_shape", [((60, 100, 3), (64, 64)), ((100, 60, 4), (48, 90)), ((40, 40, 3), (80, 80)), ((30, 50, 3), (30, 50))])

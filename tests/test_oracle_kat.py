@@ -751,6 +751,49 @@ def test_blend_kats():
                           np.full((2, 2), 77, np.uint8))                                         # non-Rgba samples are assigned (image.zig:90-94)
 
 
+def test_motion_blur_kats():
+    """image/tests/filters.zig:969-1160: horizontal / vertical / diagonal streaks of a bright spot, zero distance, RGB, radial zoom keeps the
+    centre, radial spin spreads a point, zero strength copies; plus a float64 numpy restatement of the diagonal line integral."""
+    spot = np.zeros((5, 5), np.uint8)
+    spot[2, 2] = 255
+    h = zo.motion_blur_linear(spot, 0.0, 3)
+    assert h[2, 1] > 0 and h[2, 2] > 0 and h[2, 3] > 0 and h[1, 2] == 0 and h[3, 2] == 0
+    v = zo.motion_blur_linear(spot, float(np.float32(np.pi / 2)), 3)
+    assert v[1, 2] > 0 and v[2, 2] > 0 and v[3, 2] > 0 and v[2, 1] == 0 and v[2, 3] == 0
+    d = zo.motion_blur_linear(spot, float(np.float32(np.pi / 4)), 3)
+    assert d[1, 1] > 0 and d[2, 2] > 0 and d[3, 3] > 0
+    assert np.array_equal(zo.motion_blur_linear(spot, 0.0, 0), spot)
+    yy, xx = np.mgrid[0:7, 0:7].astype(np.float32)
+    dist = np.sqrt((xx - 3) ** 2 + (yy - 3) ** 2)
+    ring = np.where((dist > 1.5) & (dist < 2.5), 255, 0).astype(np.uint8)
+    assert abs(int(zo.motion_blur_radial(ring, 0.5, 0.5, 0.5)[3, 3]) - int(ring[3, 3])) < 20
+    pt = np.zeros((7, 7), np.uint8)
+    pt[2, 4] = 255
+    sp = zo.motion_blur_radial(pt, 0.5, 0.5, 0.5, spin=True)
+    assert sp[2, 4] > 0 and int((sp > 0).sum()) > 1
+    seq = np.arange(9, dtype=np.uint8).reshape(3, 3)
+    assert np.array_equal(zo.motion_blur_radial(seq, 0.5, 0.5, 0.0), seq)
+    rng = np.random.default_rng(17)
+    img = rng.random((9, 11)).astype(np.float32)
+    angle, distance = np.float32(0.6), 4
+    ca, sa = np.float64(np.cos(angle, dtype=np.float32)), np.float64(np.sin(angle, dtype=np.float32))
+    want = np.zeros(img.shape)
+    for r in range(img.shape[0]):
+        for c in range(img.shape[1]):
+            acc, n, t = 0.0, 0, -distance / 2.0
+            while t <= distance / 2.0:
+                sx, sy = np.float32(np.float32(c) + np.float32(np.float32(t) * np.float32(ca))), np.float32(np.float32(r) + np.float32(np.float32(t) * np.float32(sa)))
+                if 0 <= sx < img.shape[1] and 0 <= sy < img.shape[0]:
+                    x0, y0 = int(np.floor(sx)), int(np.floor(sy))
+                    x1, y1 = min(x0 + 1, img.shape[1] - 1), min(y0 + 1, img.shape[0] - 1)
+                    fx, fy = float(sx) - x0, float(sy) - y0
+                    acc += (img[y0, x0] * (1 - fx) + img[y0, x1] * fx) * (1 - fy) + (img[y1, x0] * (1 - fx) + img[y1, x1] * fx) * fy
+                    n += 1
+                t += 1.0
+            want[r, c] = acc / n if n else img[r, c]
+    assert np.allclose(zo.motion_blur_linear(img, float(angle), distance), want, rtol=2e-6, atol=1e-7)
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

@@ -41,6 +41,8 @@ pub const c = struct {
     pub extern fn zb_order_blur(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, radius: u32, mode: c_int, param: f64, border: c_int, s: Stream) c_int;
     pub extern fn zb_motion_blur_linear(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, angle: f32, cos_a: f32, sin_a: f32, distance: u32, s: Stream) c_int;
     pub extern fn zb_motion_blur_radial(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, center_x: f32, center_y: f32, strength: f32, spin: c_int, s: Stream) c_int;
+    pub extern fn zb_eigh_f64(a: [*]const f64, rows: u32, cols: u32, values: [*]f64, vectors: [*]f64) c_int;
+    pub extern fn zb_eigh_f32(a: [*]const f32, rows: u32, cols: u32, values: [*]f32, vectors: [*]f32) c_int;
     pub extern fn zb_psnr(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_ssim(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_mean_pixel_error(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
@@ -59,7 +61,7 @@ pub const c = struct {
 };
 
 /// Zig error set the status codes map onto (names as in the reference: image.zig:637,970,531-536; fdm.zig:114,142).
-pub const Error = error{ DimensionMismatch, InvalidSigma, Unsupported, NotConverged, InvalidArgument, OutOfMemory, DeviceFailure, InvalidScaleFactor, InvalidDimensions, NoTargetSet, NoSourceSet, InsufficientData, InvalidComponents, InvalidThreshold, InvalidPercentile, InvalidTrim, ImageTooSmall };
+pub const Error = error{ DimensionMismatch, InvalidSigma, Unsupported, NotConverged, InvalidArgument, OutOfMemory, DeviceFailure, InvalidScaleFactor, InvalidDimensions, NoTargetSet, NoSourceSet, InsufficientData, InvalidComponents, InvalidThreshold, InvalidPercentile, InvalidTrim, ImageTooSmall, NotSquare, NotSymmetric, NotFinite };
 
 pub fn check(status: c_int) Error!void {
     return switch (status) {
@@ -80,6 +82,9 @@ pub fn check(status: c_int) Error!void {
         15 => error.InvalidPercentile,
         16 => error.InvalidTrim,
         17 => error.ImageTooSmall,
+        18 => error.NotSquare,
+        19 => error.NotSymmetric,
+        20 => error.NotFinite,
         else => error.InvalidArgument,
     };
 }

@@ -97,6 +97,9 @@ const char* zb_status_name(int status) {
         case ZB_ERR_INVALID_PERCENTILE: return "InvalidPercentile";
         case ZB_ERR_INVALID_TRIM: return "InvalidTrim";
         case ZB_ERR_IMAGE_TOO_SMALL: return "ImageTooSmall";
+        case ZB_ERR_NOT_SQUARE: return "NotSquare";
+        case ZB_ERR_NOT_SYMMETRIC: return "NotSymmetric";
+        case ZB_ERR_NOT_FINITE: return "NotFinite";
     }
     return "Unknown";
 }

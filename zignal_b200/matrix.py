@@ -81,3 +81,22 @@ def svd(a: np.ndarray, mode: str = "full_u", with_v: bool = False):
     else:
         raise TypeError("svd supports f32 and f64")
     return u, s, v, conv.value
+
+
+def eigh(a: np.ndarray):
+    """Matrix.eigh(allocator) (matrix/eigen.zig:34-136) -> (values ascending, vectors with eigenvectors as columns).  Host routine."""
+    a = np.ascontiguousarray(a)
+    if a.ndim != 2:
+        raise ZignalError(18, "NotSquare")
+    rows, cols = a.shape
+    values = np.zeros(rows, a.dtype)
+    vectors = np.zeros((rows, rows), a.dtype)
+    if a.dtype == np.float64:
+        P = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        check(lib().zb_eigh_f64(P(a), rows, cols, P(values), P(vectors)))
+    elif a.dtype == np.float32:
+        P = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        check(lib().zb_eigh_f32(P(a), rows, cols, P(values), P(vectors)))
+    else:
+        raise TypeError("eigh supports f32 and f64")
+    return values, vectors

@@ -204,7 +204,8 @@ int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radiu
 int zb_motion_blur_linear(const zb_image* src, zb_image* dst, int pixfmt, float angle, float cos_a, float sin_a, uint32_t distance, zb_stream s);
 /* Image.motionBlur(..., .{ .radial_zoom | .radial_spin = .{ .center_x, .center_y, .strength } })   motion_blur.zig:252-436; spin != 0 selects
  * radial_spin.  Zoom is bit-exact; spin evaluates atan2 / cos / sin per sample on the device (last-bit libm differences: 1e-5 relative,
- * at most one 8-bit step on isolated pixels). */
+ * at most one 8-bit step on isolated pixels; on the outermost pixel ring the reference's own bounds test sits within an ulp of the image
+ * edge, so a sample may be kept by one libm and dropped by another). */
 int zb_motion_blur_radial(const zb_image* src, zb_image* dst, int pixfmt, float center_x, float center_y, float strength, int spin, zb_stream s);
 
 /* Image.psnr(other) / Image.ssim(other) / Image.meanPixelError(other)   image.zig:1105-1147, image/metrics.zig:10-165: f64 quality

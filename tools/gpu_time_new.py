@@ -43,6 +43,14 @@ def main():
     res["median_r2_rgba_ms"] = timed(lambda: c.median_blur(2, out=outc))
     res["min_r3_rgba_ms"] = timed(lambda: c.min_blur(3, out=outc))
     res["alpha_trim_r2_gray_ms"] = timed(lambda: g.alpha_trimmed_mean_blur(2, 0.2, out=outg))
+    from zignal_b200.compose import motion_blur_linear, motion_blur_radial
+    res["motion_linear_diag_d15_rgba_ms"] = timed(lambda: motion_blur_linear(c, outc, 0.6, 15))
+    res["motion_linear_horiz_d15_rgba_ms"] = timed(lambda: motion_blur_linear(c, outc, 0.0, 15))
+    res["motion_zoom_rgba_ms"] = timed(lambda: motion_blur_radial(c, outc, 0.5, 0.5, 0.5))
+    res["motion_spin_rgba_ms"] = timed(lambda: motion_blur_radial(c, outc, 0.5, 0.5, 0.5, spin=True))
+    src = zb.Image.from_numpy(rng.integers(0, 256, (1024, 1024, 4), dtype=np.uint8))
+    res["insert_blend_overlay_1024_into_4096_ms"] = timed(lambda: c.insert(src, (500.0, 400.0, 2500.0, 2400.0), 0.3, zb.Interpolation.BILINEAR,
+                                                                            blend=zb.Blending.OVERLAY))
     res["psnr_rgba_ms"] = timed(lambda: c.psnr(c2))
     res["ssim_rgba_ms"] = timed(lambda: c.ssim(c2))
     res["ssim_gray_ms"] = timed(lambda: g.ssim(outg))

@@ -94,7 +94,8 @@ def test_motion_blur_radial(zb, shape, dtype):
             diff = np.abs(gi.astype(int) - wi.astype(int))
             assert diff.max() <= 1 and (diff != 0).mean() <= 0.005, (cx, cy, strength, int(diff.max()), float((diff != 0).mean()))
         else:
-            assert np.allclose(gi, wi, rtol=1e-5, atol=2e-6), (cx, cy, strength, float(np.abs(gi - wi).max()))
+            # an angle error of a few f32 ulps moves a sample by ~1e-7 * distance pixels: <= 2e-5 of the value range on these image sizes
+            assert np.allclose(gi, wi, rtol=1e-5, atol=2e-5), (cx, cy, strength, float(np.abs(gi - wi).max()))
     assert np.array_equal(motion_blur_radial(dev, zb.Image.init_like(dev), 0.5, 0.5, 0.0).to_numpy(), img)       # strength 0: copy
 
 

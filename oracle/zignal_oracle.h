@@ -116,6 +116,9 @@ void zo_ssim_window(double* w121);
  * zoom (spin = 0) / spin (spin = 1); center in normalised [0, 1] coordinates.  Any of the five pixel formats. */
 int zo_motion_blur_line(const zo_image* src, zo_image* dst, int pixfmt, float cos_angle, float sin_angle, uint32_t distance);
 int zo_motion_blur_radial(const zo_image* src, zo_image* dst, int pixfmt, float center_x, float center_y, float strength, int spin);
+/* image.zig:396-421 Image.convert / convertInto: per pixel convertColor(Target, px) (color.zig:108-151) between any two of the five pixel
+ * formats (the same format copies). */
+int zo_convert(const zo_image* src, int src_pixfmt, zo_image* dst, int dst_pixfmt);
 /* image.zig:785-799 / integral.zig:273-422. */
 int zo_sharpen(const zo_image* src, zo_image* dst, int pixfmt, uint32_t radius);
 

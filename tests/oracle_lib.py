@@ -81,6 +81,7 @@ def _declare(L):
         fn.argtypes = [img, img, C.c_int, C.POINTER(C.c_double)]
     L.zo_motion_blur_line.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_uint32]
     L.zo_motion_blur_radial.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+    L.zo_convert.argtypes = [img, C.c_int, img, C.c_int]
     L.zo_canny.argtypes = [img, img, C.c_int, C.c_float, C.c_float, C.c_float]
     L.zo_interpolate.argtypes = [img, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.zo_resize.argtypes = [img, img, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -325,6 +326,17 @@ def motion_blur_radial(src, center_x, center_y, strength, spin=False):
     out = np.zeros_like(src)
     _check(lib().zo_motion_blur_radial(as_image(src), as_image(out), pixfmt_of(src), C.c_float(center_x), C.c_float(center_y),
                                        C.c_float(strength), int(bool(spin))), "motion_blur_radial")
+    return out
+
+
+_FMT_SHAPE = {0: ((), np.uint8), 1: ((), np.float32), 2: ((3,), np.uint8), 3: ((4,), np.uint8), 4: ((4,), np.float32)}
+
+
+def convert(src, dst_pixfmt):
+    """Image.convert (image.zig:396-421); dst_pixfmt is a ZO_PIX_* value (0 u8, 1 f32, 2 rgb8, 3 rgba8, 4 rgbaf32)."""
+    tail, dtype = _FMT_SHAPE[int(dst_pixfmt)]
+    out = np.zeros(src.shape[:2] + tail, dtype)
+    _check(lib().zo_convert(as_image(src), pixfmt_of(src), as_image(out), int(dst_pixfmt)), "convert")
     return out
 
 

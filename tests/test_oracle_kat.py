@@ -794,6 +794,34 @@ def test_motion_blur_kats():
     assert np.allclose(zo.motion_blur_linear(img, float(angle), distance), want, rtol=2e-6, atol=1e-7)
 
 
+def test_convert_kats():
+    """color.zig:1556-1582, 1854-1866 (scalar colours, grayscale conversion, clamping) through Image.convert's per-pixel convertColor."""
+    U8, F32, RGB8, RGBA8, RGBAF32 = range(5)
+    one = lambda v, dt: np.array([[v]], dt)
+    assert tuple(zo.convert(one(128, np.uint8), RGB8)[0, 0]) == (128, 128, 128)            # convertColor(Rgb(u8), u8 128)
+    assert tuple(zo.convert(one(0.5, np.float32), RGB8)[0, 0]) == (128, 128, 128)          # convertColor(Rgb(u8), 0.5)
+    assert abs(float(zo.convert(one(128, np.uint8), F32)[0, 0]) - 128.0 / 255.0) < 1e-7
+    assert zo.convert(one(0.5, np.float32), U8)[0, 0] == 128
+    assert zo.convert(one(-0.5, np.float32), U8)[0, 0] == 0 and zo.convert(one(1.5, np.float32), U8)[0, 0] == 255
+    assert zo.convert(np.array([[[128, 128, 128]]], np.uint8), U8)[0, 0] == 128            # Rgb.to(.gray)
+    assert zo.convert(np.array([[[255, 0, 0]]], np.uint8), U8)[0, 0] == 54
+    assert zo.convert(np.array([[[255, 0, 0, 128]]], np.uint8), U8)[0, 0] == 54            # Rgba ignores alpha
+    over = np.array([[[1.2, -0.2, 0.5, 2.0]]], np.float32)                                 # Rgb(f32){1.2, -0.2, 0.5}.as(u8) = 255, 0, 128
+    assert tuple(zo.convert(over, RGBA8)[0, 0]) == (255, 0, 128, 255) and tuple(zo.convert(over, RGB8)[0, 0]) == (255, 0, 128)
+    assert tuple(zo.convert(np.array([[[10, 20, 30]]], np.uint8), RGBA8)[0, 0]) == (10, 20, 30, 255)
+    assert tuple(zo.convert(np.array([[[10, 20, 30, 40]]], np.uint8), RGB8)[0, 0]) == (10, 20, 30)
+    f = zo.convert(np.array([[[255, 0, 51]]], np.uint8), RGBAF32)[0, 0]
+    assert f[0] == 1.0 and f[1] == 0.0 and f[2] == np.float32(51) / np.float32(255) and f[3] == 1.0
+    g = zo.convert(one(0.25, np.float32), RGBAF32)[0, 0]
+    assert tuple(g) == (0.25, 0.25, 0.25, 1.0)
+    y = zo.convert(np.array([[[1.0, 0.0, 0.0, 0.3]]], np.float32), F32)[0, 0]
+    assert abs(float(y) - 0.2126) < 1e-6
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (5, 7, 4), dtype=np.uint8)
+    assert np.array_equal(zo.convert(zo.convert(img, RGBAF32), RGBA8), img)                 # u8 -> f32 -> u8 is the identity
+    assert np.array_equal(zo.convert(img, RGBA8), img)                                      # same type copies
+
+
 def test_insert_extract_inverse_kat():
     """image/tests/transforms.zig:316-381: extract then insert reproduces the centre of the source (avg error < 25); and the
     documented properties of insert: pixels outside the rectangle stay untouched, an empty source is a no-op."""

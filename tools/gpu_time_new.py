@@ -51,6 +51,9 @@ def main():
     src = zb.Image.from_numpy(rng.integers(0, 256, (1024, 1024, 4), dtype=np.uint8))
     res["insert_blend_overlay_1024_into_4096_ms"] = timed(lambda: c.insert(src, (500.0, 400.0, 2500.0, 2400.0), 0.3, zb.Interpolation.BILINEAR,
                                                                             blend=zb.Blending.OVERLAY))
+    outf = zb.Image.init(n, n, zb.PixFmt.RGBAF32, device="cuda")
+    res["convert_rgba8_to_rgbaf32_ms"] = timed(lambda: c.convert(zb.PixFmt.RGBAF32, out=outf))
+    res["convert_rgba8_to_u8_ms"] = timed(lambda: c.convert(zb.PixFmt.U8, out=outg))
     res["psnr_rgba_ms"] = timed(lambda: c.psnr(c2))
     res["ssim_rgba_ms"] = timed(lambda: c.ssim(c2))
     res["ssim_gray_ms"] = timed(lambda: g.ssim(outg))

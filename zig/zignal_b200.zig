@@ -43,6 +43,7 @@ pub const c = struct {
     pub extern fn zb_motion_blur_radial(src: *const ZbImage, dst: *ZbImage, pixfmt: c_int, center_x: f32, center_y: f32, strength: f32, spin: c_int, s: Stream) c_int;
     pub extern fn zb_eigh_f64(a: [*]const f64, rows: u32, cols: u32, values: [*]f64, vectors: [*]f64) c_int;
     pub extern fn zb_eigh_f32(a: [*]const f32, rows: u32, cols: u32, values: [*]f32, vectors: [*]f32) c_int;
+    pub extern fn zb_convert(src: *const ZbImage, src_pixfmt: c_int, dst: *ZbImage, dst_pixfmt: c_int, s: Stream) c_int;
     pub extern fn zb_psnr(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_ssim(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;
     pub extern fn zb_mean_pixel_error(a: *const ZbImage, b: *const ZbImage, pixfmt: c_int, out: *f64, s: Stream) c_int;

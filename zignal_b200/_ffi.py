@@ -87,6 +87,7 @@ def _declare(L):
         "zb_motion_blur_radial": ([img, img, i, f, f, f, i, vp], i),
         "zb_eigh_f64": ([P(C.c_double), u32, u32, P(C.c_double), P(C.c_double)], i),
         "zb_eigh_f32": ([P(f), u32, u32, P(f), P(f)], i),
+        "zb_convert": ([img, i, img, i, vp], i),
         "zb_psnr": ([img, img, i, P(C.c_double), vp], i),
         "zb_ssim": ([img, img, i, P(C.c_double), vp], i),
         "zb_mean_pixel_error": ([img, img, i, P(C.c_double), vp], i),

@@ -291,6 +291,17 @@ class Image:
         check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
         return out
 
+    def convert(self, target: PixFmt, out: Optional["Image"] = None) -> "Image":
+        """Image.convert(allocator, TargetType) / convertInto (image.zig:396-421): per-pixel convertColor into another pixel type."""
+        target = PixFmt(target)
+        if out is None:
+            out = Image.init(self.rows, self.cols, target, device=self._t.device)
+        elif out.pixfmt != target:
+            raise TypeError("out must have the target pixel type")
+        a, d = self._zb(), out._zb()
+        check(lib().zb_convert(a, int(self.pixfmt), d, int(target), current_stream()))
+        return out
+
     # ---- quality metrics (image.zig:1105-1147, metrics.zig) ----
     def _metric(self, fn, other: "Image") -> float:
         if other.pixfmt != self.pixfmt:

@@ -156,7 +156,7 @@ def test_order_statistic_filters_match_oracle(zb, shape):
     rng = np.random.default_rng(shape[0] * 13 + shape[1])
     img = rand_image(rng, shape, np.uint8)
     dev = zb.Image.from_numpy(img)
-    for radius in (1, 2, 5):
+    for radius in (1, 2, 3, 5):
         for bname, border in [("zero", zb.BorderMode.ZERO), ("replicate", zb.BorderMode.REPLICATE), ("mirror", zb.BorderMode.MIRROR),
                               ("wrap", zb.BorderMode.WRAP)]:
             for pct in (0.0, 0.25, 0.5, 0.9, 1.0):
@@ -170,6 +170,28 @@ def test_order_statistic_filters_match_oracle(zb, shape):
         assert np.array_equal(dev.median_blur(radius).to_numpy(), zo.order_blur(img, radius, "percentile", 0.5, "mirror"))
         assert np.array_equal(dev.min_blur(radius, zb.BorderMode.REPLICATE).to_numpy(), zo.order_blur(img, radius, "percentile", 0.0, "replicate"))
         assert np.array_equal(dev.max_blur(radius, zb.BorderMode.REPLICATE).to_numpy(), zo.order_blur(img, radius, "percentile", 1.0, "replicate"))
+
+
+@pytest.mark.parametrize("shape", [(45, 61), (33, 40, 4)])
+def test_order_statistic_register_and_tile_kernels_agree(zb, shape):
+    """Radius 1-3 run kernels whose window lives in registers; zb_set_force_generic selects the any-radius kernel that re-reads the shared
+    tile.  Both must give the oracle's result."""
+    rng = np.random.default_rng(shape[1])
+    img = rand_image(rng, shape, np.uint8)
+    dev = zb.Image.from_numpy(img)
+    for radius in (1, 2, 3):
+        fast = [dev.percentile_blur(radius, 0.5, zb.BorderMode.WRAP).to_numpy(), dev.percentile_blur(radius, 0.81, zb.BorderMode.ZERO).to_numpy(),
+                dev.midpoint_blur(radius, zb.BorderMode.MIRROR).to_numpy(), dev.alpha_trimmed_mean_blur(radius, 0.27, zb.BorderMode.REPLICATE).to_numpy()]
+        zb.lib().zb_set_force_generic(1)
+        try:
+            slow = [dev.percentile_blur(radius, 0.5, zb.BorderMode.WRAP).to_numpy(), dev.percentile_blur(radius, 0.81, zb.BorderMode.ZERO).to_numpy(),
+                    dev.midpoint_blur(radius, zb.BorderMode.MIRROR).to_numpy(), dev.alpha_trimmed_mean_blur(radius, 0.27, zb.BorderMode.REPLICATE).to_numpy()]
+        finally:
+            zb.lib().zb_set_force_generic(0)
+        want = [zo.order_blur(img, radius, "percentile", 0.5, "wrap"), zo.order_blur(img, radius, "percentile", 0.81, "zero"),
+                zo.order_blur(img, radius, "midpoint", 0.0, "mirror"), zo.order_blur(img, radius, "alpha_trimmed", 0.27, "replicate")]
+        for f, g, w in zip(fast, slow, want):
+            assert np.array_equal(f, w) and np.array_equal(g, w), radius
 
 
 def test_order_statistic_reference_cases(zb):

@@ -40,6 +40,8 @@ def main():
     res["canny_rgba_sigma1.0_ms"] = timed(lambda: c.canny(1.0, 20.0, 60.0, out=out8))
     res["median_r1_gray_ms"] = timed(lambda: g.median_blur(1, out=outg))
     res["median_r2_gray_ms"] = timed(lambda: g.median_blur(2, out=outg))
+    res["median_r3_gray_ms"] = timed(lambda: g.median_blur(3, out=outg))
+    res["median_r5_gray_ms"] = timed(lambda: g.median_blur(5, out=outg))
     res["median_r2_rgba_ms"] = timed(lambda: c.median_blur(2, out=outc))
     res["min_r3_rgba_ms"] = timed(lambda: c.min_blur(3, out=outc))
     res["alpha_trim_r2_gray_ms"] = timed(lambda: g.alpha_trimmed_mean_blur(2, 0.2, out=outg))

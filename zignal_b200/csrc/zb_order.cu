@@ -4,7 +4,8 @@
 // The reference slides a 256-bin histogram over each row (O(256) per pixel and per channel, strictly sequential along the row).
 // The value it returns depends only on the multiset of the (2r+1)^2 border-resolved window samples (out-of-range under .zero
 // counts as the value 0, :338-347), so the device evaluates each pixel independently from a shared-memory tile:
-//   percentile   the smallest v with #{x <= v} > rank: an 8-step bisection over v, each step one pass over the window
+//   percentile   the smallest v with #{x <= v} > rank: an 8-step bisection over v, each step one pass over the window (radius 1-3: the
+//                window lives in registers and the passes are unrolled compare-and-add chains)
 //                (rank 0 / area-1, i.e. minBlur / maxBlur, is a single min / max pass);
 //   midpoint     (min + max + 1) / 2 from one pass;
 //   alpha-trim   two bisections give the t-th smallest and t-th largest value, one more pass the sums below / above them; the
@@ -33,10 +34,12 @@ struct OrderParams {
     int trim_each;   // alpha-trimmed: elements dropped at each end
 };
 
-template <int CH, int MODE>
+// RADIUS > 0: the window size is a compile-time constant, so the (2r+1)^2 samples of a channel are loaded into registers once and every
+// counting pass is a fully unrolled compare-and-add chain; RADIUS == 0: any radius up to kMaxRadius, passes re-read the shared tile.
+template <int CH, int MODE, int RADIUS>
 __global__ void __launch_bounds__(kTileW* kTileH) order_kernel(const OrderParams p) {
     extern __shared__ uint8_t tile[];
-    const int R = p.radius, win = 2 * R + 1, area = win * win;
+    const int R = RADIUS > 0 ? RADIUS : p.radius, win = 2 * R + 1, area = win * win;
     const int tw = kTileW + 2 * R, th = kTileH + 2 * R;
     const int pitch = (tw * CH + 3) & ~3;
     const int row0 = blockIdx.y * kTileH - R, col0 = blockIdx.x * kTileW - R;
@@ -54,33 +57,39 @@ __global__ void __launch_bounds__(kTileW* kTileH) order_kernel(const OrderParams
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
         const uint8_t* w0 = tile + threadIdx.y * pitch + threadIdx.x * CH + k;
-        auto count_le = [&](int v) {
-            int n = 0;
-            for (int dy = 0; dy < win; ++dy) {
-                const uint8_t* row = w0 + dy * pitch;
-                for (int dx = 0; dx < win; ++dx) n += (int)row[dx * CH] <= v;
+        constexpr int kRegs = RADIUS > 0 ? (2 * RADIUS + 1) * (2 * RADIUS + 1) : 1;
+        int regs[kRegs];
+        if constexpr (RADIUS > 0) {
+#pragma unroll
+            for (int dy = 0; dy < 2 * RADIUS + 1; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2 * RADIUS + 1; ++dx) regs[dy * (2 * RADIUS + 1) + dx] = w0[dy * pitch + dx * CH];
+        }
+        auto visit = [&](auto&& f) {           // f(sample) for every sample of the window
+            if constexpr (RADIUS > 0) {
+#pragma unroll
+                for (int i = 0; i < kRegs; ++i) f(regs[i]);
+            } else {
+                for (int dy = 0; dy < win; ++dy) {
+                    const uint8_t* row = w0 + dy * pitch;
+                    for (int dx = 0; dx < win; ++dx) f((int)row[dx * CH]);
+                }
             }
-            return n;
         };
-        auto select = [&](int rank) {      // smallest v whose cumulative count exceeds rank (histogram.zig:603-610)
+        auto select = [&](int rank) {          // smallest v whose cumulative count exceeds rank (histogram.zig:603-610)
             int lo = 0, hi = 255;
+#pragma unroll 1
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (count_le(mid) > rank) hi = mid; else lo = mid + 1;
+                int n = 0;
+                visit([&](int x) { n += x <= mid; });
+                if (n > rank) hi = mid; else lo = mid + 1;
             }
             return lo;
         };
         int mn = 255, mx = 0;
-        if (MODE == MODE_MIDPOINT || (MODE == MODE_PERCENTILE && (p.rank == 0 || p.rank == area - 1))) {
-            for (int dy = 0; dy < win; ++dy) {
-                const uint8_t* row = w0 + dy * pitch;
-                for (int dx = 0; dx < win; ++dx) {
-                    const int v = row[dx * CH];
-                    mn = min(mn, v);
-                    mx = max(mx, v);
-                }
-            }
-        }
+        if (MODE == MODE_MIDPOINT || (MODE == MODE_PERCENTILE && (p.rank == 0 || p.rank == area - 1)))
+            visit([&](int x) { mn = min(mn, x); mx = max(mx, x); });
         int result;
         if (MODE == MODE_MIDPOINT) {
             result = (mn + mx + 1) >> 1;                                       // :357-365
@@ -89,23 +98,18 @@ __global__ void __launch_bounds__(kTileW* kTileH) order_kernel(const OrderParams
         } else {
             const int t = p.trim_each;
             const int kept = area - 2 * t;                                     // low_count == high_count == t (the window always holds `area` samples)
-            unsigned total = 0;
             int v_lo = 0, v_hi = 255;
             if (t > 0) {
                 v_lo = select(t - 1);          // the t-th smallest sample
                 v_hi = select(area - t);       // the t-th largest sample
             }
-            unsigned sum_lt = 0, sum_gt = 0;
+            unsigned total = 0, sum_lt = 0, sum_gt = 0;
             int cnt_lt = 0, cnt_gt = 0;
-            for (int dy = 0; dy < win; ++dy) {
-                const uint8_t* row = w0 + dy * pitch;
-                for (int dx = 0; dx < win; ++dx) {
-                    const int v = row[dx * CH];
-                    total += v;
-                    if (v < v_lo) { sum_lt += v; ++cnt_lt; }
-                    if (v > v_hi) { sum_gt += v; ++cnt_gt; }
-                }
-            }
+            visit([&](int x) {
+                total += x;
+                if (x < v_lo) { sum_lt += x; ++cnt_lt; }
+                if (x > v_hi) { sum_gt += x; ++cnt_gt; }
+            });
             unsigned kept_sum = total;
             if (t > 0) kept_sum -= sum_lt + (unsigned)(t - cnt_lt) * v_lo + sum_gt + (unsigned)(t - cnt_gt) * v_hi;   // :377-400
             const unsigned rounded = (kept_sum + (unsigned)kept / 2) / (unsigned)kept;                                 // :405
@@ -115,18 +119,28 @@ __global__ void __launch_bounds__(kTileW* kTileH) order_kernel(const OrderParams
     }
 }
 
+template <int CH, int RADIUS>
+int launch_radius(const OrderParams& p, int mode, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    switch (mode) {
+        case MODE_PERCENTILE: order_kernel<CH, MODE_PERCENTILE, RADIUS><<<grid, block, smem, s>>>(p); break;
+        case MODE_MIDPOINT: order_kernel<CH, MODE_MIDPOINT, RADIUS><<<grid, block, smem, s>>>(p); break;
+        default: order_kernel<CH, MODE_ALPHA, RADIUS><<<grid, block, smem, s>>>(p); break;
+    }
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
 template <int CH>
 int launch_mode(const OrderParams& p, int mode, cudaStream_t s) {
     const int tw = kTileW + 2 * p.radius, th = kTileH + 2 * p.radius;
     const size_t smem = (size_t)th * ((tw * CH + 3) & ~3);
     dim3 grid(div_up(p.cols, kTileW), div_up(p.rows, kTileH)), block(kTileW, kTileH);
-    switch (mode) {
-        case MODE_PERCENTILE: order_kernel<CH, MODE_PERCENTILE><<<grid, block, smem, s>>>(p); break;
-        case MODE_MIDPOINT: order_kernel<CH, MODE_MIDPOINT><<<grid, block, smem, s>>>(p); break;
-        default: order_kernel<CH, MODE_ALPHA><<<grid, block, smem, s>>>(p); break;
+    switch (g_force_generic.load() ? 0 : p.radius) {     // zb_set_force_generic: the any-radius kernel, as the cross-check of the unrolled ones
+        case 1: return launch_radius<CH, 1>(p, mode, grid, block, smem, s);
+        case 2: return launch_radius<CH, 2>(p, mode, grid, block, smem, s);
+        case 3: return launch_radius<CH, 3>(p, mode, grid, block, smem, s);
+        default: return launch_radius<CH, 0>(p, mode, grid, block, smem, s);
     }
-    ZB_LAUNCHED();
-    return ZB_OK;
 }
 
 }  // namespace

@@ -179,5 +179,90 @@ pub fn Ops(comptime Image: type, comptime T: type, comptime host: bool) type {
             // cos/sin are computed here, with Zig's own @cos/@sin (transforms.zig:190-191), and cross the ABI as data
             _ = c.zb_rotate_into_cs(&a, &d, pixfmtOf(T), angle, @cos(angle), @sin(angle), tag, 0, 0, @intFromEnum(border), null);
         }
+
+        // ---- device-resident only (host = false): the SURVEY 8(f) callers.  `OutU8` is the caller's Image(u8). ----
+        pub fn sobel(self: Image, out: anytype) Error!void { // image.zig:999
+            var a = raw(self);
+            var d: c.ZbImage = .{ .data = @ptrCast(out.data.ptr), .rows = out.rows, .cols = out.cols, .stride = out.stride };
+            try check(c.zb_sobel(&a, &d, pixfmtOf(T), null));
+        }
+        pub fn canny(self: Image, out: anytype, sigma: f32, low_threshold: f32, high_threshold: f32) Error!void { // image.zig:1041
+            var a = raw(self);
+            var d: c.ZbImage = .{ .data = @ptrCast(out.data.ptr), .rows = out.rows, .cols = out.cols, .stride = out.stride };
+            try check(c.zb_canny(&a, &d, pixfmtOf(T), sigma, low_threshold, high_threshold, null));
+        }
+        pub fn medianBlur(self: Image, out: Image, radius: usize) Error!void { // image.zig:650 (percentile 0.5, .mirror)
+            try orderBlur(self, out, radius, 0, 0.5, 2);
+        }
+        pub fn percentileBlur(self: Image, out: Image, radius: usize, percentile: f64, border: anytype) Error!void { // image.zig:672
+            try orderBlur(self, out, radius, 0, percentile, @intFromEnum(border));
+        }
+        pub fn minBlur(self: Image, out: Image, radius: usize, border: anytype) Error!void { // image.zig:696
+            try orderBlur(self, out, radius, 0, 0.0, @intFromEnum(border));
+        }
+        pub fn maxBlur(self: Image, out: Image, radius: usize, border: anytype) Error!void { // image.zig:719
+            try orderBlur(self, out, radius, 0, 1.0, @intFromEnum(border));
+        }
+        pub fn midpointBlur(self: Image, out: Image, radius: usize, border: anytype) Error!void { // image.zig:742
+            try orderBlur(self, out, radius, 1, 0.0, @intFromEnum(border));
+        }
+        pub fn alphaTrimmedMeanBlur(self: Image, out: Image, radius: usize, trim_fraction: f64, border: anytype) Error!void { // image.zig:767
+            try orderBlur(self, out, radius, 2, trim_fraction, @intFromEnum(border));
+        }
+        fn orderBlur(self: Image, out: Image, radius: usize, mode: c_int, param: f64, border: c_int) Error!void {
+            var a = raw(self);
+            var d = raw(out);
+            try check(c.zb_order_blur(&a, &d, pixfmtOf(T), @intCast(@min(radius, std.math.maxInt(u32))), mode, param, border, null));
+        }
+        /// `blur` is the reference's `MotionBlur` union (motion_blur.zig:12-55)
+        pub fn motionBlur(self: Image, out: Image, blur: anytype) Error!void {
+            var a = raw(self);
+            var d = raw(out);
+            switch (blur) {
+                .linear => |l| try check(c.zb_motion_blur_linear(&a, &d, pixfmtOf(T), l.angle, @cos(l.angle), @sin(l.angle), @intCast(l.distance), null)),
+                .radial_zoom => |z| try check(c.zb_motion_blur_radial(&a, &d, pixfmtOf(T), z.center_x, z.center_y, z.strength, 0, null)),
+                .radial_spin => |z| try check(c.zb_motion_blur_radial(&a, &d, pixfmtOf(T), z.center_x, z.center_y, z.strength, 1, null)),
+            }
+        }
+        /// `rect` is the reference's Rectangle(f32); `blend_mode` its `Blending` enum (blending.zig:8-22, same order as ZB_BLEND_*)
+        pub fn insert(self: Image, source: Image, rect: anytype, angle: f32, method: anytype, blend_mode: anytype) void { // image.zig:604
+            var d = raw(self);
+            var a = raw(source);
+            const tag: c_int = @intFromEnum(std.meta.activeTag(method));
+            _ = c.zb_insert_blend(&d, &a, pixfmtOf(T), rect.l, rect.t, rect.r, rect.b, angle, @cos(angle), @sin(angle), tag, 0, 0, @intFromEnum(blend_mode), null);
+        }
+        pub fn extract(self: Image, out: Image, rect: anytype, angle: f32, method: anytype, border: anytype) void { // image.zig:594
+            var a = raw(self);
+            var d = raw(out);
+            const tag: c_int = @intFromEnum(std.meta.activeTag(method));
+            _ = c.zb_extract(&a, &d, pixfmtOf(T), rect.l, rect.t, rect.r, rect.b, angle, @cos(angle), @sin(angle), tag, 0, 0, @intFromEnum(border), null);
+        }
+        pub fn psnr(self: Image, other: Image) Error!f64 { // image.zig:1105
+            var a = raw(self);
+            var b = raw(other);
+            var out: f64 = 0;
+            try check(c.zb_psnr(&a, &b, pixfmtOf(T), &out, null));
+            return out;
+        }
+        pub fn ssim(self: Image, other: Image) Error!f64 { // image.zig:1126
+            var a = raw(self);
+            var b = raw(other);
+            var out: f64 = 0;
+            try check(c.zb_ssim(&a, &b, pixfmtOf(T), &out, null));
+            return out;
+        }
+        pub fn meanPixelError(self: Image, other: Image) Error!f64 { // image.zig:1145
+            var a = raw(self);
+            var b = raw(other);
+            var out: f64 = 0;
+            try check(c.zb_mean_pixel_error(&a, &b, pixfmtOf(T), &out, null));
+            return out;
+        }
+        /// Image.convertInto(TargetType, out) (image.zig:396)
+        pub fn convertInto(self: Image, comptime TargetType: type, out: anytype) Error!void {
+            var a = raw(self);
+            var d: c.ZbImage = .{ .data = @ptrCast(out.data.ptr), .rows = out.rows, .cols = out.cols, .stride = out.stride };
+            try check(c.zb_convert(&a, pixfmtOf(T), &d, pixfmtOf(TargetType), null));
+        }
     };
 }

@@ -43,3 +43,17 @@ def test_fdm_fixtures(zb):
         f.match(s, zb.Image.from_numpy(tgt))
         f.deinit()
         assert sha(s.to_numpy()) == c["output_sha256"], name
+
+
+def test_8f_fixtures(zb):
+    """The device results of the 8(f) additions hash to tests/golden/golden_8f.json (all listed operations are bit-exact)."""
+    import json
+    from pathlib import Path
+
+    from golden_8f import CASES
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "golden_8f.json").read_text())
+    for name, (build, _oracle, device) in CASES.items():
+        img = build()
+        res = device(zb, img)
+        assert list(res.shape) == g["cases"][name]["shape"] and str(res.dtype) == g["cases"][name]["dtype"], name
+        assert sha(res) == g["cases"][name]["output_sha256"], name

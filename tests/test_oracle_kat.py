@@ -314,6 +314,54 @@ def test_single_pixel_image():  # :587-601
         assert zo.interpolate(img, 0.0, 0.0, m) == 77
 
 
+def test_interpolation_zig_remaining_cases():
+    """image/tests/interpolation.zig: mitchell custom parameters (:164-180), boundary conditions under .mirror (:182-232), exact linear bilinear
+    (:422-449), nearest discontinuity (:451-470), symmetry (:472-493), mitchell parameter effects (:495-529), lanczos weight normalisation
+    (:531-548), extreme values (:550-585) and the clamping stress tests (:355-420, :603-630: every sample exists and stays a valid u8)."""
+    img = _gradient(10, 10)
+    for b, c in ((1.0, 0.0), (0.0, 0.5), (0.0, 0.75)):
+        assert zo.interpolate(img, 5.5, 5.5, "mitchell", b=b, c=c) is not None
+    for x, y in ((-0.4, 0), (9.4, 9.4), (-1, 0), (0, -1), (10, 0), (0, 10)):
+        assert zo.interpolate(img, x, y, "nearest", "mirror") is not None
+    for x, y in ((0, 0), (8.9, 8.9), (9.1, 9.1), (-0.1, 0)):
+        assert zo.interpolate(img, x, y, "bilinear", "mirror") is not None
+    for x, y in ((1, 1), (7.9, 7.9), (0.5, 0.5), (8.1, 8.1)):
+        assert zo.interpolate(img, x, y, "bicubic", "mirror") is not None
+    for x, y in ((2, 2), (6.9, 6.9), (1.5, 1.5), (7.1, 7.1)):
+        assert zo.interpolate(img, x, y, "lanczos", "mirror") is not None
+    q = np.array([[0, 100], [50, 150]], np.uint8)
+    assert zo.interpolate(q, 0.5, 0, "bilinear") == 50 and zo.interpolate(q, 0, 0.5, "bilinear") == 25
+    assert zo.interpolate(q, 0.5, 0.5, "bilinear") == 75 and zo.interpolate(q, 0.25, 0, "bilinear") == 25
+    d = np.array([[0, 255], [100, 200]], np.uint8)
+    assert zo.interpolate(d, 0.49, 0, "nearest") == 0 and zo.interpolate(d, 0.51, 0, "nearest") == 255
+    r, c = np.mgrid[0:5, 0:5]
+    sym = np.minimum(255, (np.abs(r - 2) + np.abs(c - 2)) * 50).astype(np.uint8)
+    assert zo.interpolate(sym, 1.5, 2, "bilinear") == zo.interpolate(sym, 2.5, 2, "bilinear")
+    assert zo.interpolate(sym, 2, 1.5, "bilinear") == zo.interpolate(sym, 2, 2.5, "bilinear")
+    band = np.full((6, 6), 50, np.uint8)
+    band[2:4] = 200
+    vals = [int(zo.interpolate(band, 2.5, 1.8, "mitchell", b=b, c=c)) for b, c in ((1 / 3, 1 / 3), (1.0, 0.0), (0.0, 0.75))]
+    assert len(set(vals)) > 1
+    assert zo.interpolate(np.full((8, 8), 128, np.uint8), 4.3, 4.7, "lanczos") == 128
+    ch = _checker(4, 4)
+    assert abs(int(zo.interpolate(ch, 2, 2, "lanczos"))) <= 1
+    assert zo.interpolate(ch, 0, 0, "nearest") == 0 and zo.interpolate(ch, 0, 0, "bilinear") == 0
+    edge = np.tile(np.where(np.arange(6) < 3, 0, 255).astype(np.uint8), (6, 1))
+    assert zo.interpolate(edge, 3.1, 2.5, "bicubic") is not None
+    ch8 = _checker(8, 8)
+    for method, kw in (("bicubic", {}), ("catmull_rom", {}), ("lanczos", {}), ("mitchell", {}), ("mitchell", {"b": 0.0, "c": 0.75})):
+        y = np.float32(2.0)
+        while y < 6.0:
+            x = np.float32(2.0)
+            while x < 6.0:
+                assert zo.interpolate(ch8, float(x), float(y), method, **kw) is not None
+                x = np.float32(x + np.float32(0.3))
+            y = np.float32(y + np.float32(0.3))
+    rgb = np.repeat(_checker(4, 4)[..., None], 3, axis=2)
+    v = zo.interpolate(rgb, 1.3, 1.7, "bicubic")
+    assert v is not None and v[0] == v[1] == v[2]                      # identical channels stay identical through the clamp
+
+
 def test_interpolate_rejects_non_finite():  # interpolation.zig:73-75
     img = _gradient(4, 4)
     assert zo.interpolate(img, float("nan"), 0.0, "bilinear") is None
@@ -506,6 +554,104 @@ def test_pca_10d_reconstruct():  # :559-588
     v = np.arange(10, dtype=np.float64)
     coeffs = comps.T @ (v - mean)
     assert np.allclose(_reconstruct(mean, comps, coeffs), v, atol=1e-10)
+
+
+def test_filters_zig_remaining_cases():
+    """The tests of image/tests/filters.zig that bound a property rather than a value, ported so that every reference test on this path has a
+    counterpart: boxBlur basic / zero radius / struct / struct comprehensive (:84-270), sharpen basic / zero radius / struct (:272-362),
+    convolve blur kernel / border modes / 3x3 edge kernel / colour channels (:391-466, :628-690), convolveSeparable Gaussian approximation
+    (:468-490), gaussianBlur basic / sigma variations (:492-545), the uniform-channel .zero-border regression (:570-596)."""
+    assert np.all(zo.box_blur(np.full((5, 5), 128, np.uint8), 1) == 128)
+    seq = np.arange(9, dtype=np.uint8).reshape(3, 3)
+    assert np.array_equal(zo.box_blur(seq, 0), seq) and np.array_equal(zo.sharpen(seq + 10, 0), seq + 10)
+    rgba = np.array([[[255, 0, 0, 255], [0, 255, 0, 255], [0, 0, 255, 255]], [[255, 255, 0, 255], [255, 255, 255, 255], [255, 0, 255, 255]],
+                     [[0, 255, 255, 255], [128, 128, 128, 255], [0, 0, 0, 255]]], np.uint8)
+    centre = zo.box_blur(rgba, 1)[1, 1]
+    assert centre[0] != 255 and centre[1] != 255 and centre[2] != 255
+    for size in (8, 32):
+        for radius in (1, 3):
+            rr, cc = np.mgrid[0:size, 0:size]
+            img = np.stack([(255 * cc) // size, np.full_like(cc, 128), (255 * rr) // size, np.full_like(cc, 255)], axis=-1).astype(np.uint8)
+            b = zo.box_blur(img, radius)
+            assert np.all(b[..., 3] == 255)
+            col = b[1:size, size // 2, 0].astype(int)
+            assert np.all(np.abs(np.diff(col)) <= 15)
+    edge = np.tile(np.where(np.arange(5) < 2, 64, 192).astype(np.uint8), (5, 1))
+    sh = zo.sharpen(edge, 1)
+    assert sh[2, 0] <= 64 and sh[2, 4] >= 192
+    spot = np.full((3, 3, 4), 64, np.uint8)
+    spot[..., 3] = 255
+    spot[1, 1, :3] = 192
+    assert np.all(zo.sharpen(spot, 1)[1, 1, :3] >= 192)
+    step = np.tile(np.where(np.arange(5) < 2, 0, 255).astype(np.uint8), (5, 1))
+    box = np.full((3, 3), np.float32(1.0) / np.float32(9.0), np.float32)
+    assert 0 < zo.convolve(step, box, "replicate")[2, 2] < 255
+    dot = np.zeros((3, 3), np.uint8)
+    dot[1, 1] = 255
+    k = np.array([[0.25, 0.25, 0], [0.25, 0.25, 0], [0, 0, 0]], np.float32)
+    assert zo.convolve(dot, k, "replicate")[0, 0] == 0
+    for border in ("zero", "mirror"):
+        zo.convolve(dot, k, border)
+    rr, cc = np.mgrid[0:10, 0:10]
+    pat = ((rr * 7 + cc * 13) % 256).astype(np.uint8)
+    lap = np.array([[-1, -1, -1], [-1, 8, -1], [-1, -1, -1]], np.float32)
+    res = zo.convolve(pat, lap, "zero")
+    assert res.shape == pat.shape
+    want = np.zeros((10, 10), np.int64)                        # independent restatement of the u8 path: SCALE 256, round half up, clamp
+    padded = np.pad(pat.astype(np.int64), 1)
+    for dy in range(3):
+        for dx in range(3):
+            want += int(lap[dy, dx] * 256) * padded[dy:dy + 10, dx:dx + 10]
+    assert np.array_equal(res, np.clip((want + 128) >> 8, 0, 255).astype(np.uint8))
+    rr, cc = np.mgrid[0:5, 0:5]
+    rgb = np.stack([(rr * 20) % 256, (cc * 20) % 256, ((rr + cc) * 10) % 256], axis=-1).astype(np.uint8)
+    ident = np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], np.float32)
+    assert np.array_equal(zo.convolve(rgb, ident, "zero")[1:-1, 1:-1], rgb[1:-1, 1:-1])
+    imp = np.zeros((7, 7), np.float32)
+    imp[3, 3] = 1.0
+    g1 = np.array([0.25, 0.5, 0.25], np.float32)
+    r = zo.conv_separable(imp, g1, g1, "zero")
+    assert r[3, 3] < 1.0 and r[3, 2] > 0 and r[3, 3] > r[3, 2] and r[3, 3] == np.float32(0.25) and r[3, 2] == np.float32(0.125)
+    sq = np.zeros((11, 11), np.uint8)
+    sq[3:8, 3:8] = 255
+    bl = zo.gaussian_blur(sq, 1.0)
+    assert sq[2, 5] == 0 and bl[2, 5] > 0 and bl[5, 5] > 200
+    pix = np.zeros((15, 15), np.float32)
+    pix[7, 7] = 1.0
+    small, large = zo.gaussian_blur(pix, 0.5), zo.gaussian_blur(pix, 2.0)
+    assert small[7, 7] > large[7, 7] and large[7, 5] > small[7, 5]
+    white = np.full((5, 5, 3), 255, np.uint8)
+    corner = zo.convolve(white, box, "zero")[0, 0]
+    assert corner[0] != 255 and abs(int(corner[0]) - 113) <= 1
+
+
+def test_integral_and_transform_remaining_cases():
+    """image/tests/integral.zig:49-150 (per-channel planes of an all-ones Rgba image, Rgb vs Rgba planes agree, box sums from the table) and
+    image/tests/transforms.zig:211-229, 382-406 (a 45 degree rotation grows the canvas; insert copies under .none and composites under .normal)."""
+    ones = np.ones((21, 13), np.uint8)
+    area = (np.arange(1, 22)[:, None] * np.arange(1, 14)[None, :]).astype(np.float32)
+    assert np.array_equal(zo.integral_plane(ones), area)                     # the struct test applies this plane per channel (:49-68)
+    seed, vals = 0, []
+    for _ in range(100):
+        seed = (seed + 17) % 256
+        vals.append((seed, (seed + 50) % 256, (seed + 100) % 256))
+    rgb = np.array(vals, np.uint8).reshape(10, 10, 3)
+    rgba = np.concatenate([rgb, np.full((10, 10, 1), 255, np.uint8)], axis=-1)
+    for ch in range(3):
+        assert np.array_equal(zo.integral_plane(np.ascontiguousarray(rgb[..., ch])), zo.integral_plane(np.ascontiguousarray(rgba[..., ch])))
+    sat = zo.integral_plane(np.arange(1, 10, dtype=np.uint8).reshape(3, 3))
+
+    def box_sum(r1, c1, r2, c2):                                              # integral.zig:85-90
+        return sat[r2, c2] - (sat[r2, c1 - 1] if c1 > 0 else 0) - (sat[r1 - 1, c2] if r1 > 0 else 0) + (sat[r1 - 1, c1 - 1] if r1 > 0 and c1 > 0 else 0)
+    assert box_sum(0, 0, 2, 2) == 45 and box_sum(0, 0, 1, 1) == 12 and box_sum(1, 1, 2, 2) == 28 and box_sum(1, 1, 1, 1) == 5
+    chk = _checker(10, 10)
+    rot = zo.rotate(255 - chk, float(np.float32(np.pi / 4)), "bilinear", "mirror")
+    assert rot.shape[0] > 10 and rot.shape[1] > 10
+    base, overlay = (0, 0, 255, 255), (255, 0, 0, 128)
+    dest = np.array([[base]], np.uint8)
+    src = np.array([[overlay]], np.uint8)
+    assert tuple(zo.insert(dest, src, (0.0, 0.0, 1.0, 1.0), 0.0, "nearest", blend="none")[0, 0]) == overlay
+    assert tuple(zo.insert(dest, src, (0.0, 0.0, 1.0, 1.0), 0.0, "nearest", blend="normal")[0, 0]) == zo.blend_rgba8(base, overlay, "normal")
 
 
 def test_extract_kats():

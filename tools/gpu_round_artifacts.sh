@@ -8,6 +8,7 @@ timeout 900 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; ta
 timeout 600 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; cut -c1-300 $o/${tag}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_reference.json 2>> $o/${tag}_bench.err; cut -c1-300 $o/${tag}_bench_reference.json
 timeout 600 python tools/gpu_bench_all.py > $o/${tag}_bench_all.log 2>&1; cp $o/all_configs.json $o/${tag}_all_configs.json
+timeout 300 python tools/gpu_time_new.py > $o/${tag}_new_timings.json 2> $o/${tag}_new_timings.err   # the 8(f) additions at 4096x4096
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_ncu_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e > $o/${tag}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -f -o $o/${tag}_ncu_fused -k regex:fused_sep -c 1 python bench.py --steps 1 --warmup 3 --no-e2e > /dev/null 2>&1
 ncu -i $o/${tag}_ncu_fused.ncu-rep --page raw --csv > $o/${tag}_ncu_fused.csv 2>/dev/null; rm -f $o/${tag}_ncu_fused.ncu-rep

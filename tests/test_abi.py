@@ -149,3 +149,50 @@ def test_scale_shapes_and_errors_host_logic():
     with pytest.raises(zb.ZignalError) as e:
         img.scale(0.001)
     assert e.value.name == "InvalidDimensions"
+
+
+def test_public_header_is_valid_c99(tmp_path):
+    """The boundary is a C ABI: include/zignal_b200.h must compile as plain C (what cgo / Zig's translate-c / a C caller would consume)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "zignal_b200.h"\nint main(void) { return ZB_BLEND_EXCLUSION + ZB_ORDER_ALPHA_TRIMMED + ZB_ERR_NOT_FINITE + ZB_PIX_RGBAF32; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(_ffi.HEADER.parent), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+
+def test_8f_status_names_and_argument_errors_before_the_device():
+    """Error behaviour of the 8(f) entry points that is decided on the host (reference error names; no kernel is launched)."""
+    L = zb.lib()
+    names = {14: "InvalidThreshold", 15: "InvalidPercentile", 16: "InvalidTrim", 17: "ImageTooSmall", 18: "NotSquare", 19: "NotSymmetric",
+             20: "NotFinite", 12: "InsufficientData", 13: "InvalidComponents"}
+    for k, v in names.items():
+        assert L.zb_status_name(k).decode() == v
+    a = np.zeros((12, 12), np.uint8)
+    b = np.zeros((12, 13), np.uint8)
+    ia, ib = zb.image._np_image(a), zb.image._np_image(b)
+    f32 = C.c_float
+    assert L.zb_canny(ia, ia, 0, f32(float("nan")), f32(1), f32(2), None) == 5       # InvalidParameter (edges.zig:221)
+    assert L.zb_canny(ia, ia, 0, f32(-1.0), f32(1), f32(2), None) == 2                # InvalidSigma (:224)
+    assert L.zb_canny(ia, ia, 0, f32(1.0), f32(3), f32(2), None) == 14               # InvalidThreshold (:226)
+    assert L.zb_canny(ia, ib, 0, f32(1.0), f32(1), f32(2), None) == 1                # DimensionMismatch
+    assert L.zb_canny(ia, ia, 4, f32(1.0), f32(1), f32(2), None) == 3                # Rgba(f32) is not a canny input here
+    assert L.zb_order_blur(ia, ib, 0, 1, 0, C.c_double(0.5), 2, None) == 1           # image.zig:679
+    assert L.zb_order_blur(ia, ia, 0, 1, 2, C.c_double(0.5), 2, None) == 16          # InvalidTrim (order_statistic_blur.zig:160)
+    assert L.zb_order_blur(ia, ia, 0, 1, 0, C.c_double(1.5), 2, None) == 15          # InvalidPercentile (:48)
+    assert L.zb_order_blur(ia, ia, 1, 1, 0, C.c_double(0.5), 2, None) == 3           # UnsupportedPixelType (:66)
+    assert L.zb_order_blur(ia, ia, 0, 32, 0, C.c_double(0.5), 2, None) == 3          # radius limit of this build
+    assert L.zb_order_blur(ia, ia, 0, 1, 7, C.c_double(0.5), 2, None) == 5           # unknown mode
+    out = C.c_double(0.0)
+    assert L.zb_psnr(ia, ib, 0, C.byref(out), None) == 1                             # metrics.zig:11
+    small = zb.image._np_image(np.zeros((10, 30), np.uint8))
+    assert L.zb_ssim(small, small, 0, C.byref(out), None) == 17                      # ImageTooSmall (metrics.zig:60)
+    assert L.zb_ssim(ia, ia, 9, C.byref(out), None) == 3
+    assert L.zb_convert(ia, 0, ib, 1, None) == 1                                     # image.zig:397
+    assert L.zb_convert(ia, 0, ia, 9, None) == 3
+    assert L.zb_motion_blur_linear(ia, ib, 0, f32(0.5), f32(0.8), f32(0.5), 3, None) == 1
+    assert L.zb_motion_blur_radial(ia, ib, 0, f32(0.5), f32(0.5), f32(0.5), 0, None) == 1
+    assert L.zb_insert_blend(ia, ia, 0, f32(0), f32(0), f32(1), f32(1), f32(0), f32(1), f32(0), 0, f32(0), f32(0), 13, None) == 5   # unknown blend mode

@@ -176,3 +176,48 @@ def test_sharded_covariance_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(a and b for _, a, b in res), res
+
+
+def _nbhd_worker(rank, world, port, border, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zignal_b200 import BorderMode, PixFmt, shard
+        rows, cols, halo = 11, 17, 3
+        full = np.random.default_rng(5).integers(0, 256, (rows * world, cols, 4), dtype=np.uint8)
+        results = []
+        for name, reach, op in [("median r2", 2, lambda a: zo.order_blur(a, 2, "percentile", 0.5, border)),
+                                ("max r3", 3, lambda a: zo.order_blur(a, 3, "percentile", 1.0, border)),
+                                ("dense 3x3", 1, lambda a: zo.convolve(a, np.full((3, 3), 1.0 / 9.0, np.float32), border))]:
+            want = op(full)
+            src = shard.RowBlock(rows, cols, PixFmt.RGBA8, halo, "cpu", rank, world)
+            dst = shard.RowBlock(rows, cols, PixFmt.RGBA8, halo, "cpu", rank, world)
+            src.extended_tensor().fill_(0xEE)                       # poison: a halo that is used without being exchanged shows up
+            src.interior_tensor().copy_(torch.from_numpy(full[rank * rows:(rank + 1) * rows]))
+
+            def fn(s, d, op=op):                                     # the local operator is the CPU oracle on the view the block hands out
+                res = op(s.to_numpy())
+                d._t[d._off * 4:(d._off + d.rows * d.stride) * 4] = torch.from_numpy(np.ascontiguousarray(res).reshape(-1))
+            src.apply_neighbourhood(dst, fn, reach, BorderMode[border.upper()])
+            results.append(bool(np.array_equal(dst.interior_tensor().numpy(), want[rank * rows:(rank + 1) * rows])))
+        q.put((rank, results))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("border", ["mirror", "zero", "replicate", "wrap"])
+def test_sharded_neighbourhood_filters_reproduce_the_single_image_result(world, border):
+    """RowBlock.apply_neighbourhood: order-statistic and dense filters on a row-sharded image equal the filter of the whole image, for
+    every border mode (global edges come from the filter's own border handling on a view that leaves the outer halo out)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nbhd_worker, args=(r, world, port, border, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(all(flags) for _, flags in res), res

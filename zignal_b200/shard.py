@@ -140,6 +140,25 @@ class RowBlock:
                 r.wait()
         return out
 
+    def apply_neighbourhood(self, out: "RowBlock", fn, reach: int, border: BorderMode = BorderMode.MIRROR):
+        """Any same-shape filter whose output row r reads input rows [r - reach, r + reach] -- boxBlur, sharpen, dense convolve, sobel,
+        the order-statistic filters, motionBlur.linear (reach = distance / 2 + 1) -- on the global image this block belongs to: one
+        neighbour exchange, then `fn(src, dst)` once on the rows this block holds.  `src` / `dst` are Image views of the two
+        blocks; a halo beyond a global image edge is left out of the views, so the filter's own border handling (`border`, which
+        `fn` must use) makes the true edge, exactly as in `conv_plan`.  Rows of `dst` within `reach` of a neighbour-side end of the
+        view are computed from an incomplete neighbourhood, but those are halo rows of `out`: its interior rows are exact."""
+        assert self.halo >= reach and out.halo == self.halo and out.rows == self.rows and out.cols == self.cols
+        if self.world == 1 and BorderMode(border) == BorderMode.WRAP and self.halo:
+            self.exchange_halo(border)                 # single rank, wrap: local copy into the halos
+        for r in self.post_halo_exchange(border):
+            r.wait()
+        lo, hi, _ = self.conv_plan(reach, border)
+        cols = self.cols
+        src = Image(self.t.reshape(-1), self.pixfmt, hi - lo, cols, cols, lo * cols)
+        dst = Image(out.t.reshape(-1), out.pixfmt, hi - lo, cols, cols, lo * cols)
+        fn(src, dst)
+        return out
+
     # -- the one exchange step of the convolution path ------------------------------------------------
     def exchange_halo(self, border: BorderMode = BorderMode.MIRROR):
         h, n = self.halo, self.rows

@@ -221,3 +221,36 @@ def test_sharded_neighbourhood_filters_reproduce_the_single_image_result(world, 
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(flags) for _, flags in res), res
+
+
+def test_conv_plan_invariants_for_every_rank_up_to_eight_gpus():
+    """conv_plan is pure bookkeeping, so it can be checked for every (world, rank) of the 1..8-GPU scaling run without a process group:
+    the windows tile the interior exactly once, windows flagged halo-free never read a neighbour's halo row, halo windows exist only next
+    to a neighbour, and edge blocks leave the outer halo out of the view."""
+    from zignal_b200 import BorderMode, PixFmt, shard
+    rng = np.random.default_rng(11)
+    for world in range(1, 9):
+        for rank in range(world):
+            for border in (BorderMode.ZERO, BorderMode.REPLICATE, BorderMode.MIRROR, BorderMode.WRAP):
+                for _ in range(6):
+                    half = int(rng.integers(0, 9))
+                    halo = half + int(rng.integers(0, 3)) if (world > 1 or border == BorderMode.WRAP) else int(rng.integers(0, 10))
+                    rows = int(rng.integers(max(halo + 1, 1), 40))
+                    blk = shard.RowBlock(rows, 5, PixFmt.U8, halo, "cpu", rank, world)
+                    lo, hi, steps = blk.conv_plan(half, border)
+                    if world == 1 and (border != BorderMode.WRAP or halo == 0):
+                        assert (lo, hi) == (halo, halo + rows) and steps == [(0, rows, False)]
+                        continue
+                    up, down = blk.neighbours(border) if world > 1 else (0, 0)
+                    assert lo == (0 if up is not None else halo) and hi == (rows + 2 * halo if down is not None else rows + halo)
+                    first = halo - lo
+                    last = first + rows
+                    covered = sorted((a, b) for a, b, _ in steps)
+                    assert covered[0][0] == first and covered[-1][1] == last, (world, rank, border, rows, halo, half, steps)
+                    assert all(x[1] == y[0] for x, y in zip(covered, covered[1:])) and all(b > a for a, b in covered if rows > 0)
+                    for a, b, needs in steps:
+                        reads_up_halo = up is not None and a - half < first
+                        reads_down_halo = down is not None and b - 1 + half >= last
+                        if not needs:
+                            assert not reads_up_halo and not reads_down_halo, (world, rank, border, rows, halo, half, steps)
+                    assert all(not needs for _, _, needs in steps) or up is not None or down is not None

@@ -2,8 +2,11 @@
 
 * ImagePyramid.build   (reference src/image/pyramid.zig:31-104): per level, Gaussian blur of the ORIGINAL with an adaptive
   sigma, then a bilinear resize -- two kernels per level, no host round trip;
-* motion_blur_linear   (reference src/image/motion_blur.zig:65-114): horizontal / vertical motion blur is convolveSeparable
-  with a uniform kernel of `distance` taps against the identity, border .replicate.
+* motion_blur_linear   (reference src/image/motion_blur.zig:65-250): horizontal / vertical motion blur is convolveSeparable
+  with a uniform kernel of `distance` taps against the identity, border .replicate; any other angle is the library's line-integral
+  kernel (zb_motion_blur_linear decides, with the reference's 0.001 thresholds on |sin| and |cos|);
+* motion_blur_radial   (:252-436): radial zoom / spin through zb_motion_blur_radial;
+* letterbox / set_border_zero (src/image/transforms.zig:49-108, image.zig:198-229): resize into the content view + zeroed border.
 
 The scalar set-up (level scale, sigma, sizes) is evaluated in f32 exactly as the reference writes it; `pow` is numpy's powf,
 which may differ from Zig's std.math.pow in the last ulp (it only matters if a level size or a tap lands on a rounding edge).

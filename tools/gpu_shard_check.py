@@ -4,7 +4,6 @@ import os
 import sys
 from pathlib import Path
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

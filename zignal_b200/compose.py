@@ -19,8 +19,8 @@ import numpy as np
 
 import ctypes as C
 
-from ._ffi import ZignalError, check, lib
-from .image import BorderMode, Image, Interpolation, Rectangle, current_stream
+from ._ffi import check, lib
+from .image import Image, Interpolation, Rectangle, current_stream
 
 
 class ImagePyramid:

@@ -13,7 +13,7 @@ import ctypes as C
 import math
 from dataclasses import dataclass
 from enum import IntEnum
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

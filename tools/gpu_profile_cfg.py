@@ -1,5 +1,5 @@
 """Runs ONE configuration a couple of times so that `ncu -k regex:<kernel> -c N` can capture it.
-usage: python tools/gpu_profile_cfg.py rotate|boxblur|sharpen|bicubic|lanczos|bilinear|gemm|fdm|gauss8|conv3"""
+usage: python tools/gpu_profile_cfg.py rotate|boxblur|sharpen|bicubic|lanczos|bilinear|gemm|fdm|gauss8|conv3|canny|median|ssim|motion|convert"""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -49,6 +49,16 @@ elif cfg == "fdm":
     f.set_target(ti)
     f.set_source(si)
     fn = lambda: f.update()
+elif cfg in ("canny", "median", "ssim", "motion", "convert"):             # the 8(f) additions at 4096 x 4096
+    from zignal_b200.compose import motion_blur_linear
+    gray = Image.from_tensor(torch.randint(0, 256, (4096, 4096), device="cuda", dtype=torch.uint8, generator=g))
+    rgba = Image.from_tensor(torch.randint(0, 256, (4096, 4096, 4), device="cuda", dtype=torch.uint8, generator=g))
+    rgba2 = Image.from_tensor(torch.randint(0, 256, (4096, 4096, 4), device="cuda", dtype=torch.uint8, generator=g))
+    out8, outc = Image.init_like(gray), Image.init_like(rgba)
+    outf = Image.init(4096, 4096, PixFmt.RGBAF32, device="cuda")
+    fn = {"canny": lambda: gray.canny(1.4, 20.0, 60.0, out=out8), "median": lambda: rgba.median_blur(2, out=outc),
+          "ssim": lambda: rgba.ssim(rgba2), "motion": lambda: motion_blur_linear(rgba, outc, 0.6, 15),
+          "convert": lambda: rgba.convert(PixFmt.RGBAF32, out=outf)}[cfg]
 else:
     raise SystemExit("unknown config " + cfg)
 for _ in range(reps):

@@ -196,28 +196,51 @@ class Image:
 
     def copy(self, dst: "Image") -> None:  # image.zig:375-392
         assert self.has_same_shape(dst)
+        self._peer(dst, what="dst")
         a, d = self._zb(), dst._zb()
-        check(lib().zb_copy(a, d, int(self.pixfmt), current_stream()))
+        self._run(lib().zb_copy, a, d, int(self.pixfmt))
 
     def dupe(self) -> "Image":  # image.zig:367-371
         out = Image.init_like(self)
         self.copy(out)
         return out
 
-    def _out(self, out: Optional["Image"]) -> "Image":
-        return Image.init_like(self) if out is None else out
+    def _peer(self, other: "Image", fmt: Optional[PixFmt] = None, what: str = "out") -> "Image":
+        """Zig's Image(T) typing makes a mismatched `out` a compile error; the C ABI takes one pixfmt for both buffers, so the
+        mirror checks it here: same pixel type (or the op's fixed result type) and same CUDA device as self."""
+        fmt = self.pixfmt if fmt is None else PixFmt(fmt)
+        if not isinstance(other, Image):
+            raise TypeError(f"{what} must be an Image")
+        if other.pixfmt != fmt:
+            raise TypeError(f"{what} must be an Image of pixel type {fmt.name}, got {other.pixfmt.name}")
+        if other._t.device != self._t.device:
+            raise ValueError(f"{what} lives on {other._t.device}, self on {self._t.device}")
+        return other
+
+    def _run(self, fn, *args) -> None:
+        """Call a stream-taking entry point on self's device and on that device's current stream (not the stream of whatever
+        device happens to be current)."""
+        torch = _torch()
+        dev = self._t.device
+        with torch.cuda.device(dev):
+            check(fn(*args, torch.cuda.current_stream(dev).cuda_stream))
+
+    def _out(self, out: Optional["Image"], fmt: Optional[PixFmt] = None) -> "Image":
+        if out is None:
+            return Image.init(self.rows, self.cols, self.pixfmt if fmt is None else fmt, self._t.device)
+        return self._peer(out, fmt)
 
     # ---- filters (image.zig:635-648, 785-799, 917-994) --------------------------------------------
     def box_blur(self, radius: int, out: Optional["Image"] = None) -> "Image":
         out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_box_blur(a, d, int(self.pixfmt), int(radius), current_stream()))
+        self._run(lib().zb_box_blur, a, d, int(self.pixfmt), int(radius))
         return out
 
     def sharpen(self, radius: int, out: Optional["Image"] = None) -> "Image":
         out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_sharpen(a, d, int(self.pixfmt), int(radius), current_stream()))
+        self._run(lib().zb_sharpen, a, d, int(self.pixfmt), int(radius))
         return out
 
     def convolve(self, kernel, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
@@ -226,7 +249,7 @@ class Image:
             raise ValueError("Kernel must be a 2D array")  # convolution.zig:200
         out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_convolve(a, d, int(self.pixfmt), _fptr(k), k.shape[0], k.shape[1], int(border), current_stream()))
+        self._run(lib().zb_convolve, a, d, int(self.pixfmt), _fptr(k), k.shape[0], k.shape[1], int(border))
         return out
 
     def convolve_separable(self, kernel_x, kernel_y, border: BorderMode = BorderMode.MIRROR,
@@ -235,20 +258,20 @@ class Image:
         ky = np.ascontiguousarray(kernel_y, dtype=np.float32)
         out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_conv_separable(a, d, int(self.pixfmt), _fptr(kx), kx.size, _fptr(ky), ky.size, int(border),
-                                      current_stream()))
+        self._run(lib().zb_conv_separable, a, d, int(self.pixfmt), _fptr(kx), kx.size, _fptr(ky), ky.size, int(border))
         return out
 
     def gaussian_blur(self, sigma: float, out: Optional["Image"] = None) -> "Image":
         out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_gaussian_blur(a, d, int(self.pixfmt), C.c_float(sigma), current_stream()))
+        self._run(lib().zb_gaussian_blur, a, d, int(self.pixfmt), C.c_float(sigma))
         return out
 
     # ---- resampling (image.zig:523-541) -----------------------------------------------------------
     def resize(self, out: "Image", method: Interpolation = Interpolation.BILINEAR, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        self._peer(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_resize(a, d, int(self.pixfmt), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        self._run(lib().zb_resize, a, d, int(self.pixfmt), int(method), C.c_float(b), C.c_float(c))
         return out
 
     def scale(self, factor: float, method: Interpolation = Interpolation.BILINEAR) -> "Image":
@@ -263,18 +286,19 @@ class Image:
     # ---- geometry (image.zig:558-623) -------------------------------------------------------------
     def rotate_bounds(self, angle: float) -> Tuple[int, int]:
         r, c = C.c_uint32(), C.c_uint32()
-        check(lib().zb_rotate_bounds(self.rows, self.cols, C.c_float(angle), C.byref(r), C.byref(c)))
+        self._run(lib().zb_rotate_bounds, self.rows, self.cols, C.c_float(angle), C.byref(r), C.byref(c)))
         return r.value, c.value
 
     def rotate_into(self, out: "Image", angle: float, method: Interpolation = Interpolation.BILINEAR,
                     border: BorderMode = BorderMode.ZERO, cos_sin=None, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        self._peer(out)
         a, d = self._zb(), out._zb()
         if cos_sin is None:
             check(lib().zb_rotate_into(a, d, int(self.pixfmt), C.c_float(angle), int(method), C.c_float(b), C.c_float(c),
-                                       int(border), current_stream()))
+                                       int(border))
         else:
-            check(lib().zb_rotate_into_cs(a, d, int(self.pixfmt), C.c_float(angle), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
-                                          int(method), C.c_float(b), C.c_float(c), int(border), current_stream()))
+            self._run(lib().zb_rotate_into_cs, a, d, int(self.pixfmt), C.c_float(angle), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
+                                          int(method), C.c_float(b), C.c_float(c), int(border))
         return out
 
     def rotate(self, angle: float, method: Interpolation = Interpolation.BILINEAR, border: BorderMode = BorderMode.ZERO,
@@ -285,30 +309,25 @@ class Image:
 
     def sobel(self, out: Optional["Image"] = None) -> "Image":
         """Image.sobel (image.zig:999-1009): gradient magnitude into an Image(u8) of the same shape."""
-        if out is None:
-            out = Image.init(self.rows, self.cols, PixFmt.U8, device=self._t.device)
+        out = self._out(out, PixFmt.U8)
         a, d = self._zb(), out._zb()
-        check(lib().zb_sobel(a, d, int(self.pixfmt), current_stream()))
+        self._run(lib().zb_sobel, a, d, int(self.pixfmt))
         return out
 
     def convert(self, target: PixFmt, out: Optional["Image"] = None) -> "Image":
         """Image.convert(allocator, TargetType) / convertInto (image.zig:396-421): per-pixel convertColor into another pixel type."""
         target = PixFmt(target)
-        if out is None:
-            out = Image.init(self.rows, self.cols, target, device=self._t.device)
-        elif out.pixfmt != target:
-            raise TypeError("out must have the target pixel type")
+        out = self._out(out, target)
         a, d = self._zb(), out._zb()
-        check(lib().zb_convert(a, int(self.pixfmt), d, int(target), current_stream()))
+        self._run(lib().zb_convert, a, int(self.pixfmt), d, int(target))
         return out
 
     # ---- quality metrics (image.zig:1105-1147, metrics.zig) ----
     def _metric(self, fn, other: "Image") -> float:
-        if other.pixfmt != self.pixfmt:
-            raise TypeError("metrics compare images of the same pixel type (Image(T).psnr(other: Image(T)))")
+        self._peer(other, what="other")  # Image(T).psnr(other: Image(T))
         out = C.c_double(0.0)
         a, b = self._zb(), other._zb()
-        check(fn(a, b, int(self.pixfmt), C.byref(out), current_stream()))
+        self._run(fn, a, b, int(self.pixfmt), C.byref(out))
         return out.value
 
     def psnr(self, other: "Image") -> float:
@@ -325,10 +344,9 @@ class Image:
 
     # ---- order-statistic filters (image.zig:650-790, order_statistic_blur.zig) ----
     def _order(self, radius: int, mode: int, param: float, border: BorderMode, out: Optional["Image"]) -> "Image":
-        if out is None:
-            out = Image.init(self.rows, self.cols, self.pixfmt, device=self._t.device)
+        out = self._out(out)
         a, d = self._zb(), out._zb()
-        check(lib().zb_order_blur(a, d, int(self.pixfmt), int(radius), mode, C.c_double(param), int(border), current_stream()))
+        self._run(lib().zb_order_blur, a, d, int(self.pixfmt), int(radius), mode, C.c_double(param), int(border))
         return out
 
     def percentile_blur(self, radius: int, percentile: float, border: BorderMode = BorderMode.MIRROR, out: Optional["Image"] = None) -> "Image":
@@ -358,21 +376,20 @@ class Image:
 
     def canny(self, sigma: float, low_threshold: float, high_threshold: float, out: Optional["Image"] = None) -> "Image":
         """Image.canny (image.zig:1041-1063, edges.zig:212-274): binary (0 / 255) edge map into an Image(u8) of the same shape."""
-        if out is None:
-            out = Image.init(self.rows, self.cols, PixFmt.U8, device=self._t.device)
+        out = self._out(out, PixFmt.U8)
         a, d = self._zb(), out._zb()
-        check(lib().zb_canny(a, d, int(self.pixfmt), C.c_float(sigma), C.c_float(low_threshold), C.c_float(high_threshold), current_stream()))
+        self._run(lib().zb_canny, a, d, int(self.pixfmt), C.c_float(sigma), C.c_float(low_threshold), C.c_float(high_threshold))
         return out
 
     def extract(self, out: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
                 border: BorderMode = BorderMode.ZERO, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
         """Image.extract (transforms.zig:232-283): rect = (l, t, r, b) floats in source coordinates, rotated by `angle` CCW."""
+        self._peer(out)
         a32 = np.float32(angle)
         cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
         a, d = self._zb(), out._zb()
-        check(lib().zb_extract(a, d, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
-                               C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(border),
-                               current_stream()))
+        self._run(lib().zb_extract, a, d, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                               C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(border))
         return out
 
     def insert(self, source: "Image", rect, angle: float = 0.0, method: Interpolation = Interpolation.BILINEAR,
@@ -381,10 +398,10 @@ class Image:
         composited under a blend mode (blending.zig:26-156); other pixel types are assigned (image.zig:67-95)."""
         a32 = np.float32(angle)
         cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
+        self._peer(source, what="source")
         d, s = self._zb(), source._zb()
-        check(lib().zb_insert_blend(d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
-                                    C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(blend),
-                                    current_stream()))
+        self._run(lib().zb_insert_blend, d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
+                                    C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(blend))
         return self
 
     def crop(self, rect) -> "Image":
@@ -398,9 +415,10 @@ class Image:
         return self.extract(chip, rect, 0.0, Interpolation.NEAREST, BorderMode.ZERO)
 
     def warp(self, out: "Image", transform, method: Interpolation = Interpolation.BILINEAR, b: float = 1 / 3, c: float = 1 / 3) -> "Image":
+        self._peer(out)
         kind, m = transform.as_f32()
         a, d = self._zb(), out._zb()
-        check(lib().zb_warp(a, d, int(self.pixfmt), kind, _fptr(m), int(method), C.c_float(b), C.c_float(c), current_stream()))
+        self._run(lib().zb_warp, a, d, int(self.pixfmt), kind, _fptr(m), int(method), C.c_float(b), C.c_float(c))
         return out
 
 

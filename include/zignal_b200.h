@@ -292,6 +292,63 @@ int zb_fdm_update_with_moments(zb_fdm* f, const uint64_t* source_sums11, zb_stre
 int zb_fdm_status(zb_fdm* f, zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, a large image sharded into row blocks.
+ * The reference is single-process, so there is no reference counterpart: these entry points are what a
+ * Zig host running one process per GPU binds to shard Image.convolveSeparable / gaussianBlur (image.zig:935-994),
+ * any other neighbourhood filter, fdm.update (fdm.zig:141-273) and batches of rotate / resize.
+ *
+ * Plumbing: NCCL (dlopen'ed at run time) bootstraps the communicator and exchanges CUDA IPC handles; the data
+ * path is NVLink peer memory.  The RGBA f32 convolution kernel TMA-loads the `half` edge rows of the row
+ * neighbours straight from their memory -- one launch per step, no separate exchange -- and carries the whole
+ * synchronisation in a pair of flags per neighbour; every other filter uses zb_shard_halo_exchange (one pull
+ * kernel over NVLink; NCCL send/recv when IPC mappings are unavailable) followed by its ordinary entry point
+ * on the extended block.  All ranks must issue the same sequence of zb_shard_* calls (SPMD).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct zb_shard_comm zb_shard_comm;     /* one per process / GPU */
+typedef struct zb_shard_image zb_shard_image;   /* a global image = `world` row blocks stacked in rank order */
+#define ZB_SHARD_ID_BYTES 128
+/* Rank 0 creates the id and hands it to the other ranks out of band (the host's own launcher); then every rank
+ * creates its communicator on its current device.  world == 1 needs no id (and no NCCL). */
+int zb_shard_unique_id(uint8_t* id128);
+int zb_shard_comm_create(zb_shard_comm** out, int rank, int world, const uint8_t* id128);
+int zb_shard_comm_destroy(zb_shard_comm* c);
+int zb_shard_comm_info(const zb_shard_comm* c, int* rank, int* world, int* peer_access /* 1: IPC peer mappings in use */);
+/* Waits for the stream; ZB_ERR_DEVICE_FAILURE if a kernel gave up waiting for a neighbour (a rank died or the ranks'
+ * call sequences diverged) instead of hanging the GPU. */
+int zb_shard_status(zb_shard_comm* c, zb_stream s);
+/* Symmetric allocation (collective, same order and size on every rank): device memory every rank can address. */
+int zb_shard_alloc(zb_shard_comm* c, size_t bytes, void** out);
+int zb_shard_free(zb_shard_comm* c, void* p);
+/* Describe this rank's row block (inside a zb_shard_alloc allocation, with `halo_cap` spare rows of the same stride above
+ * and below it) of the global image (collective: the ranks learn each other's block heights and addresses). */
+int zb_shard_image_create(zb_shard_comm* c, const zb_image* block, uint32_t halo_cap, int pixfmt, zb_shard_image** out);
+int zb_shard_image_destroy(zb_shard_image* img);
+int zb_shard_image_block(const zb_shard_image* img, zb_image* block);   /* this rank's block as a plain zb_image */
+/* Contiguous share [lo, hi) of n_items for `rank` (batches of rotate / resize / warp: no exchange).  Pure host arithmetic. */
+int zb_shard_split(uint32_t n_items, int rank, int world, uint32_t* lo, uint32_t* hi);
+/* Fill the `reach` halo rows next to each row neighbour with the neighbour's edge rows (global edges are left to the filter's own
+ * border mode; ZB_BORDER_WRAP closes the ring).  One kernel on `s`; when it completes, no neighbour is still reading this block. */
+int zb_shard_halo_exchange(zb_shard_comm* c, zb_shard_image* img, uint32_t reach, int border, zb_stream s);
+/* The block plus the halo rows that zb_shard_halo_exchange filled, as a zb_image for any zb_* filter; *interior_first = index of
+ * the block's first row inside the view.  Rows of the result within `reach` of a neighbour-side end are halo rows (discard). */
+int zb_shard_view(const zb_shard_image* img, uint32_t reach, int border, zb_image* view, uint32_t* interior_first);
+/* Image.convolveSeparable / gaussianBlur of the GLOBAL image; src / dst: the same partition.  Bit-identical to the single-GPU
+ * call on the whole image. */
+int zb_shard_conv_separable(zb_shard_comm* c, const zb_shard_image* src, zb_shard_image* dst,
+                            const float* kx, int nx, const float* ky, int ny, int border, zb_stream s);
+int zb_shard_gaussian_blur(zb_shard_comm* c, const zb_shard_image* src, zb_shard_image* dst, float sigma, zb_stream s);
+/* In-place sum over all ranks of a device buffer (dtype 0 = f32, 1 = f64, 2 = u64): PCA's partial X^T X products (pca.zig:338),
+ * moment sums.  NCCL all-reduce. */
+int zb_shard_allreduce(zb_shard_comm* c, void* dev_buf, size_t count, int dtype, zb_stream s);
+/* fdm on a row-sharded image: every rank passes its block.  set_target: local moments + one all-reduce; update (zb_fdm_set_source
+ * with the local block first): the statistics kernel all-gathers the 11 sums over NVLink peer memory in its last block, solves and
+ * the map follows -- nothing leaves the device.  The result equals the single-GPU result on the whole image bit for bit. */
+int zb_shard_fdm_set_target(zb_shard_comm* c, zb_fdm* f, const zb_image* target_block, zb_stream s);
+int zb_shard_fdm_update(zb_shard_comm* c, zb_fdm* f, zb_stream s);
+/* Testing aid: 0 = automatic, 1 = force the NCCL send/recv halo exchange, 2 = force the peer pull kernel for every format. */
+int zb_shard_tune_path(int path);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-pointer twins (H2D + op + D2H inside the call; returns when dst is valid on the host).
  * ---------------------------------------------------------------------------------------------- */
 int zb_host_conv_separable(const zb_image* src, zb_image* dst, int pixfmt,

@@ -70,6 +70,8 @@ enum {
 void zo_set_threads(int n);
 int  zo_get_threads(void);
 int  zo_hw_threads(void);
+/* benchmark helper: thread-parallel first-touch fill of an f32 plane with uniform [0, 1) values */
+void zo_parallel_fill_f32(float* p, uint64_t rows, uint64_t cols, uint64_t seed);
 
 /* border.zig:46-63.  Returns -1 for "null" (contributes zero). */
 int64_t zo_resolve_index(int64_t idx, int64_t length, int border);

@@ -472,6 +472,22 @@ void zo_set_threads(int n) { zo::g_threads = n < 1 ? 1 : n; }
 int zo_get_threads(void) { return zo::g_threads; }
 int zo_hw_threads(void) { return omp_get_num_procs(); }
 
+// Benchmark helper (not a reference function): fill a rows x cols f32 plane with uniform [0, 1) values, rows split across the
+// threads exactly like the row-parallel convolution loops (static schedule), so every page is first touched -- and therefore
+// placed on the NUMA node of -- the thread that will later read and write it.
+void zo_parallel_fill_f32(float* p, uint64_t rows, uint64_t cols, uint64_t seed) {
+    const int g_threads = zo::g_threads;
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (g_threads > 1)
+    for (int64_t r = 0; r < (int64_t)rows; ++r) {
+        uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)r * 0xD1B54A32D192ED03ull + 1;
+        float* row = p + (size_t)r * cols;
+        for (uint64_t c = 0; c < cols; ++c) {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;                       // xorshift64*
+            row[c] = (float)((x * 0x2545F4914F6CDD1Dull) >> 40) * (1.0f / 16777216.0f);
+        }
+    }
+}
+
 int64_t zo_resolve_index(int64_t idx, int64_t length, int border) { return zo::resolve_index(idx, length, border); }
 uint8_t zo_clamp_u8_f32(float v) { return zo::clamp_u8(v); }
 uint8_t zo_div_clamp_u8(int64_t accum, int64_t scale) { return zo::div_clamp_u8(accum, scale); }

@@ -505,6 +505,17 @@ def pca_transform(data, mean, comps):
     return out
 
 
+def parallel_fill_f32(a: np.ndarray, seed: int):
+    """First-touch `a` (a C-contiguous f32 plane, e.g. from np.empty) with uniform [0, 1) values, rows split across the oracle's
+    threads like its convolution loops -- NUMA placement for the CPU arm of bench.py."""
+    assert a.dtype == np.float32 and a.ndim == 2 and a.flags.c_contiguous
+    fn = lib().zo_parallel_fill_f32
+    fn.argtypes = [C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64]
+    fn.restype = None
+    fn(_fptr(a), a.shape[0], a.shape[1], int(seed))
+    return a
+
+
 def set_threads(n: int):
     lib().zo_set_threads(n)
 

@@ -134,6 +134,25 @@ def _declare(L):
         "zb_host_rotate_into": ([img, img, i, f, i, f, f, i], i),
         "zb_host_warp": ([img, img, i, i, fp, i, f, f], i),
         "zb_host_fdm_match": ([img, img, i], i),
+        "zb_shard_unique_id": ([P(C.c_uint8)], i),
+        "zb_shard_comm_create": ([P(vp), i, i, P(C.c_uint8)], i),
+        "zb_shard_comm_destroy": ([vp], i),
+        "zb_shard_comm_info": ([vp, P(i), P(i), P(i)], i),
+        "zb_shard_status": ([vp, vp], i),
+        "zb_shard_alloc": ([vp, C.c_size_t, P(vp)], i),
+        "zb_shard_free": ([vp, vp], i),
+        "zb_shard_image_create": ([vp, img, u32, i, P(vp)], i),
+        "zb_shard_image_destroy": ([vp], i),
+        "zb_shard_image_block": ([vp, img], i),
+        "zb_shard_split": ([u32, i, i, P(u32), P(u32)], i),
+        "zb_shard_halo_exchange": ([vp, vp, u32, i, vp], i),
+        "zb_shard_view": ([vp, u32, i, img, P(u32)], i),
+        "zb_shard_conv_separable": ([vp, vp, vp, fp, i, fp, i, i, vp], i),
+        "zb_shard_gaussian_blur": ([vp, vp, vp, f, vp], i),
+        "zb_shard_allreduce": ([vp, vp, C.c_size_t, i, vp], i),
+        "zb_shard_fdm_set_target": ([vp, vp, img, vp], i),
+        "zb_shard_fdm_update": ([vp, vp, vp], i),
+        "zb_shard_tune_path": ([i], i),
         "zb_set_exact_f32": ([i], i),
         "zb_set_force_generic": ([i], i),
         "zb_tune": ([C.c_char_p, i], i),

@@ -205,7 +205,7 @@ int zb_conv_separable_rows(const zb_image* src, zb_image* dst, int pixfmt, const
     if (!src || !dst) return ZB_ERR_INVALID_ARGUMENT;
     if (row_end == 0 || row_end > src->rows) row_end = src->rows;
     if (row_begin > row_end) return ZB_ERR_INVALID_ARGUMENT;
-    if (src->data == dst->data) return ZB_ERR_INVALID_ARGUMENT;   // a row window of an in-place convolution would read rows already overwritten
+    if (images_overlap(src, dst, pixel_bytes(pixfmt))) return ZB_ERR_INVALID_ARGUMENT;   // a row window of an in-place convolution would read rows already overwritten
     return conv_separable_dispatch(src, dst, pixfmt, kx, nx, ky, ny, border, (cudaStream_t)s, (int)row_begin, (int)row_end);
 }
 

@@ -481,7 +481,7 @@ int launch_all(const BoxParams& p, bool sharpen, float* offs, float* offs32, cud
 int box_fused_u8(const zb_image* src, zb_image* dst, int channels, uint32_t radius, bool sharpen, cudaStream_t s) {
     if (channels != 1 && channels != 4) return ZB_ERR_UNSUPPORTED;
     if (radius == 0 || radius > 15) return ZB_ERR_UNSUPPORTED;                 // ring <= 64 rows (128 KB), margins <= 16 units
-    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;                     // bands would race with in-place rows
+    if (images_overlap(src, dst, (size_t)channels)) return ZB_ERR_UNSUPPORTED;  // bands would race with in-place / overlapping rows
     if ((uint64_t)src->cols * 255u >= (1u << 24)) return ZB_ERR_UNSUPPORTED;   // row prefixes must be exact in f32
     if (src->rows > (1u << 30) || src->cols > (1u << 28)) return ZB_ERR_UNSUPPORTED;
     const size_t sp = (size_t)src->stride * channels, dp = (size_t)dst->stride * channels;

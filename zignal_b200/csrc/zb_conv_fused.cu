@@ -28,6 +28,7 @@
 // filter code itself has no border branches.
 #include "zb_conv.h"
 #include "zb_device.cuh"
+#include "zb_shard.h"
 #include "zb_tma.cuh"
 
 namespace zb {
@@ -63,6 +64,17 @@ struct FusedParams {
     int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
 };
 
+// Sharded launch (zb_shard_conv_separable): this rank holds one row block of a taller image.  The 8-row chunks that lie
+// above row 0 / below the last row are not border pixels but the neighbours' edge rows: the producer fetches them with
+// TMA straight from the neighbours' memory (IPC mappings, NVLink) through tensor maps of THEIR blocks.
+struct ShardParams {
+    const float4* up_src;      // row 0 of the upper neighbour's block (null: global top edge, border mode applies)
+    const float4* down_src;    // row 0 of the lower neighbour's block (null: global bottom edge)
+    unsigned long long up_pitch_px, down_pitch_px;
+    int up_rows;
+    ShardLink link;
+};
+
 template <bool EXACT>
 __device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {
     if constexpr (EXACT) {
@@ -82,8 +94,9 @@ __device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {
 // Column patches of in-range rows are sourced from the stage itself whenever the resolved column is one
 // TMA delivered (always the case for mirror / replicate): no global-memory latency on the per-chunk path
 // of the edge strips.  Out-of-range rows (image top / bottom only) are fetched from global memory.
-template <int NT>
-__device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool fix_x, bool fix_rows, const FusedParams& p) {
+template <int NT, bool SHARD = false>
+__device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool fix_x, bool fix_rows, const FusedParams& p,
+                                         const ShardParams* sp = nullptr) {
     const int xlimit = p.ngroups * 8;
     auto stage_addr = [&](int rr, int xx) {
         const uint32_t line = (uint32_t)(rr * G + (xx >> 3));
@@ -98,13 +111,22 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const int rr = idx / per_row, e = idx - rr * per_row;
             const int xx = e < nleft ? e : r0 + (e - nleft);
             const int y = y0 + rr, x = xs0 + xx;
-            if (y < 0 || y >= p.rows) continue;                                 // handled by the row pass below
+            const float4* rowp = p.src + (size_t)y * p.src_pitch_px;
+            if (y < 0 || y >= p.rows) {
+                if constexpr (SHARD) {   // a neighbour's row (its pixels arrived by TMA like any other row's)
+                    if (y < 0 && sp->up_src) rowp = sp->up_src + (size_t)(sp->up_rows + y) * sp->up_pitch_px;
+                    else if (y >= p.rows && sp->down_src) rowp = sp->down_src + (size_t)(y - p.rows) * sp->down_pitch_px;
+                    else continue;
+                } else {
+                    continue;                                                   // handled by the row pass below
+                }
+            }
             const int rx = resolve_index(x, p.cols, p.border);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rx >= 0) {
                 const int sx = rx - xs0;
                 if (rx < xlimit && sx >= 0 && sx < G * 8) v = lds128(stage_addr(rr, sx));   // delivered by TMA into this stage
-                else v = __ldg(p.src + (size_t)y * p.src_pitch_px + rx);
+                else v = __ldg(rowp + rx);
             }
             sts128(stage_addr(rr, xx), v);
         }
@@ -115,6 +137,9 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const int xx = idx - rr * (G * 8);
             const int y = y0 + rr, x = xs0 + xx;
             if (y >= 0 && y < p.rows) continue;
+            if constexpr (SHARD) {
+                if ((y < 0 && sp->up_src) || (y >= p.rows && sp->down_src)) continue;   // neighbour rows: not border pixels
+            }
             const int ry = resolve_index(y, p.rows, p.border);
             const int rx = resolve_index(x, p.cols, p.border);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -172,9 +197,9 @@ __device__ __forceinline__ void v_pass(uint32_t v_col, const FusedParams& p, flo
 }
 
 // F2: use the packed fma.rn.f32x2 (FFMA2) -- two lanes per issued instruction, same IEEE result as FFMA.
-template <int HALF, bool EXACT, int STAGES, bool F2>
-__global__ void __launch_bounds__(NTHREADS, 1)
-fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+template <int HALF, bool EXACT, int STAGES, bool F2, bool SHARD>
+__device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, const CUtensorMap* tmap_up, const CUtensorMap* tmap_down,
+                                                       const FusedParams& p, const ShardParams* sp) {
     static_assert(!(EXACT && F2), "exact mode is scalar");
     constexpr int K = 2 * HALF + 1;
     constexpr int NLOAD = CHUNK + 2 * HALF;
@@ -196,9 +221,25 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         const int rb = min(ra + p.band_rows, p.row1);
         const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
         const uint32_t st = pcount % STAGES;
+        const CUtensorMap* tm = &tmap;
+        int y = ra - CHUNK + CHUNK * pi;
+        if constexpr (SHARD) {
+            // chunks never straddle the block (rows, band_rows and row0 are multiples of CHUNK): a chunk is the neighbour's or mine
+            if (y < 0 && sp->up_src) {
+                shard_wait_ge(&sp->link.self->ready_from[0], sp->link.epoch, sp->link.self);
+                asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above orders the async-proxy read below
+                tm = tmap_up;
+                y += sp->up_rows;
+            } else if (y >= p.rows && sp->down_src) {
+                shard_wait_ge(&sp->link.self->ready_from[1], sp->link.epoch, sp->link.self);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                tm = tmap_down;
+                y -= p.rows;
+            }
+        }
         fence_proxy_async();
         mbar_arrive_expect_tx(bar0 + 8 * st, STAGE_BYTES);
-        tma_load_3d(smem0 + st * STAGE_BYTES, &tmap, 0, strip * (TW / 8) - 1, ra - CHUNK + CHUNK * pi, bar0 + 8 * st);
+        tma_load_3d(smem0 + st * STAGE_BYTES, tm, 0, strip * (TW / 8) - 1, y, bar0 + 8 * st);
         ++pcount;
         if (++pi == n_in) { pi = 0; pu += gridDim.x; }
     };
@@ -207,6 +248,13 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
         fence_barrier_init();
+        if constexpr (SHARD) {
+            // this kernel is stream-ordered after whatever produced my source block: tell the neighbours it is complete
+            if (blockIdx.x == 0) {
+                if (sp->link.up) st_release_sys(&sp->link.up->ready_from[1], sp->link.epoch);
+                if (sp->link.down) st_release_sys(&sp->link.down->ready_from[0], sp->link.epoch);
+            }
+        }
     }
     __syncthreads();
     if (tid == 0)
@@ -236,10 +284,15 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             const uint32_t stage = smem0 + st * STAGE_BYTES;
             while (!mbar_try_wait(bar0 + 8 * st, (ccount / STAGES) & 1u)) {}
             const int y0 = ra - CHUNK + CHUNK * i;
-            const bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
+            bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
+            int peer_side = -1;   // this chunk came from the up (0) / down (1) neighbour
+            if constexpr (SHARD) {
+                if (y0 < 0 && sp->up_src) { peer_side = 0; fix_r = false; }
+                else if (y0 >= p.rows && sp->down_src) { peer_side = 1; fix_r = false; }
+            }
             const bool fix_x = (p.fix_left && g0 < 0) || (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
             if (fix_r || fix_x) {
-                fixup_stage<NTHREADS>(stage, y0, g0 * 8, fix_x, fix_r, p);
+                fixup_stage<NTHREADS, SHARD>(stage, y0, g0 * 8, fix_x, fix_r, p, sp);
                 __syncthreads();
             }
 
@@ -287,6 +340,19 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             }
             __syncthreads();  // ring slot complete; stage `st` is free again
 
+            if constexpr (SHARD) {
+                // all reads of the neighbour's rows for this unit are done (TMA landed, column patches loaded): once every strip
+                // of that side has said so, tell the neighbour it may overwrite its source again
+                if (peer_side >= 0 && tid == 0) {
+                    ShardCtrl* me = sp->link.self;
+                    __threadfence();
+                    if (atomicAdd(&me->halo_reads[peer_side], 1u) == (unsigned)p.n_strips - 1u) {
+                        me->halo_reads[peer_side] = 0;
+                        ShardCtrl* nb = peer_side == 0 ? sp->link.up : sp->link.down;
+                        st_release_sys(&nb->done_from[peer_side == 0 ? 1 : 0], sp->link.epoch);
+                    }
+                }
+            }
             if (tid == 0) produce();  // refill the stage just drained (the chunk STAGES ahead, possibly of the next unit)
 
             // ---------------- V(i-2): ring -> global rows [ra+8c, ra+8c+8) ----------------
@@ -305,6 +371,33 @@ fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             __syncthreads();  // V(i-2) done reading the slot H(i+1) will overwrite
         }
     }
+    if constexpr (SHARD) {
+        // The kernel may not complete before both neighbours have finished reading this block's edge rows: whatever runs
+        // next on this stream is then free to overwrite the source.  The last CTA to leave does the waiting.
+        if (tid == 0) {
+            ShardCtrl* me = sp->link.self;
+            __threadfence();
+            if (atomicAdd(&me->exit_ticket, 1u) == gridDim.x - 1u) {
+                me->exit_ticket = 0;
+                if (sp->link.up) shard_wait_ge(&me->done_from[0], sp->link.epoch, me);
+                if (sp->link.down) shard_wait_ge(&me->done_from[1], sp->link.epoch, me);
+            }
+        }
+    }
+}
+
+template <int HALF, bool EXACT, int STAGES, bool F2>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
+    fused_sep_rgbaf32_body<HALF, EXACT, STAGES, F2, false>(tmap, nullptr, nullptr, p, nullptr);
+}
+
+template <int HALF, bool EXACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fused_sep_rgbaf32_shard_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_up,
+                               const __grid_constant__ CUtensorMap tmap_down, const __grid_constant__ FusedParams p,
+                               const __grid_constant__ ShardParams sp) {
+    fused_sep_rgbaf32_body<HALF, EXACT, 3, false, true>(tmap, &tmap_up, &tmap_down, p, &sp);
 }
 
 template <int HALF, bool EXACT, int STAGES, bool F2>
@@ -501,25 +594,40 @@ int launch_fused(const CUtensorMap& tmap, const FusedParams& p, int grid, bool e
 
 }  // namespace
 
-int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                                 bool exact, cudaStream_t s, int row0, int row1) {
+// Tensor map of one row block of RGBA f32 pixels: {32 floats = 8 px, groups, rows}, box {8 px, G groups, CHUNK rows}.
+static int encode_block_map(EncodeTiledFn encode, CUtensorMap& tmap, void* data, int ngroups, int rows, uint64_t stride_px) {
+    const cuuint64_t gdim[3] = {32, (cuuint64_t)ngroups, (cuuint64_t)rows};
+    const cuuint64_t gstr[2] = {128, (cuuint64_t)stride_px * 16};
+    const cuuint32_t box[3] = {32, (cuuint32_t)G, (cuuint32_t)CHUNK};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        snprintf(t_last_error, sizeof(t_last_error), "cuTensorMapEncodeTiled failed: %d", (int)cr);
+        return ZB_ERR_UNSUPPORTED;
+    }
+    return ZB_OK;
+}
+
+// Validates the call, fills the kernel parameters and encodes the tensor map of `src`.
+static int fused_prepare(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border, int row0, int row1,
+                         FusedParams& p, CUtensorMap& tmap, int& grid, int& half_out, EncodeTiledFn& encode) {
     const int half_x = nx / 2, half_y = ny / 2;
     const int half = half_x > half_y ? half_x : half_y;
     if (half < 1 || half > MAX_HALF) return ZB_ERR_UNSUPPORTED;
     if (src->cols < 16 || src->rows < 16) return ZB_ERR_UNSUPPORTED;  // tiny images: generic path
-    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;             // in place: generic path (temp plane)
+    if (images_overlap(src, dst, 16)) return ZB_ERR_UNSUPPORTED;       // in place / overlapping views: generic path (temp plane)
     if (((uintptr_t)src->data & 15u) || ((uintptr_t)dst->data & 15u)) return ZB_ERR_UNSUPPORTED;
     // taps with |k| < 1e-10 are skipped by the reference only in the interior (convolution.zig:459-467): generic path
     for (int i = 0; i < nx; ++i) if (fabsf(kx[i]) < 1e-10f) return ZB_ERR_UNSUPPORTED;
     for (int i = 0; i < ny; ++i) if (fabsf(ky[i]) < 1e-10f) return ZB_ERR_UNSUPPORTED;
-    EncodeTiledFn encode = encode_tiled_fn();
+    encode = encode_tiled_fn();
     if (!encode) return ZB_ERR_UNSUPPORTED;
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
     if (di.smem_optin < (size_t)smem_bytes(3)) return ZB_ERR_UNSUPPORTED;
 
-    FusedParams p;
     memset(&p, 0, sizeof(p));
     // tap i of an n-tap kernel acts at offset i - n/2 (convolution.zig:527,542): place it at index i + (half - n/2)
     for (int i = 0; i < nx; ++i) p.kx[i + (half - half_x)] = kx[i];
@@ -543,7 +651,7 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
     // band height: ~256 rows, then as many bands as fit in the same number of waves
     p.row0 = row0 < 0 ? 0 : row0;
     p.row1 = (row1 < 0 || row1 > p.rows) ? p.rows : row1;
-    if (p.row1 <= p.row0) return ZB_OK;
+    if (p.row1 <= p.row0) { grid = 0; return ZB_OK; }
     const int nrows = p.row1 - p.row0;
     const int band_target = g_tune_band_rows.load();
     int n_bands = (nrows + band_target - 1) / band_target;
@@ -559,19 +667,21 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
     p.fix_left = border != ZB_BORDER_ZERO;
     p.fix_right = (border != ZB_BORDER_ZERO) || (p.cols % 8 != 0);
 
-    CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {32, (cuuint64_t)p.ngroups, (cuuint64_t)p.rows};
-    const cuuint64_t gstr[2] = {128, (cuuint64_t)src->stride * 16};
-    const cuuint32_t box[3] = {32, (cuuint32_t)G, (cuuint32_t)CHUNK};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, src->data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        snprintf(t_last_error, sizeof(t_last_error), "cuTensorMapEncodeTiled failed: %d", (int)cr);
-        return ZB_ERR_UNSUPPORTED;
-    }
+    if ((rc = encode_block_map(encode, tmap, src->data, p.ngroups, p.rows, src->stride))) return rc;
     const int n_units = p.n_strips * p.n_bands;
-    const int grid = n_units < di.sm_count ? n_units : di.sm_count;
+    grid = n_units < di.sm_count ? n_units : di.sm_count;
+    half_out = half;
+    return ZB_OK;
+}
+
+int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
+                                 bool exact, cudaStream_t s, int row0, int row1) {
+    FusedParams p;
+    CUtensorMap tmap;
+    EncodeTiledFn encode;
+    int grid = 0, half = 0;
+    int rc = fused_prepare(src, dst, kx, nx, ky, ny, border, row0, row1, p, tmap, grid, half, encode);
+    if (rc || grid == 0) return rc;
     t_last_kernel = exact ? "fused_sep_rgbaf32_exact" : "fused_sep_rgbaf32";
     switch (half) {
         case 1: return launch_fused<1>(tmap, p, grid, exact, s);
@@ -582,6 +692,67 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
         case 6: return launch_fused<6>(tmap, p, grid, exact, s);
         case 7: return launch_fused<7>(tmap, p, grid, exact, s);
         case 8: return launch_fused<8>(tmap, p, grid, exact, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
+template <int HALF>
+static int launch_shard(const CUtensorMap& tmap, const CUtensorMap& tup, const CUtensorMap& tdown, const FusedParams& p, const ShardParams& sp,
+                        int grid, bool exact, cudaStream_t s) {
+    if (exact) {
+        auto k = fused_sep_rgbaf32_shard_kernel<HALF, true>;
+        ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(3)));
+        k<<<grid, NTHREADS, smem_bytes(3), s>>>(tmap, tup, tdown, p, sp);
+    } else {
+        auto k = fused_sep_rgbaf32_shard_kernel<HALF, false>;
+        ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(3)));
+        k<<<grid, NTHREADS, smem_bytes(3), s>>>(tmap, tup, tdown, p, sp);
+    }
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+// One launch per step: the convolution of this rank's row block of a taller image.  The neighbours' edge rows are TMA-loaded
+// from their memory inside the kernel, which also carries the whole synchronisation (ready / done flags, zb_shard.h).
+int conv_separable_fused_rgbaf32_shard(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
+                                       bool exact, const PeerBlock& up, const PeerBlock& down, const ShardLink& link, cudaStream_t s) {
+    if (src->rows % CHUNK != 0) return ZB_ERR_UNSUPPORTED;   // chunks must not straddle the block
+    if ((up.data && (up.rows < (uint32_t)CHUNK || ((uintptr_t)up.data & 15u))) ||
+        (down.data && (down.rows < (uint32_t)CHUNK || ((uintptr_t)down.data & 15u))))
+        return ZB_ERR_UNSUPPORTED;
+    FusedParams p;
+    CUtensorMap tmap, tup, tdown;
+    EncodeTiledFn encode;
+    int grid = 0, half = 0;
+    int rc = fused_prepare(src, dst, kx, nx, ky, ny, border, 0, -1, p, tmap, grid, half, encode);
+    if (rc) return rc;
+    if (grid == 0) return ZB_ERR_UNSUPPORTED;
+    if (p.band_rows % CHUNK != 0) return ZB_ERR_UNSUPPORTED;
+    tup = tmap;
+    tdown = tmap;
+    if (up.data && (rc = encode_block_map(encode, tup, const_cast<void*>(up.data), p.ngroups, (int)up.rows, up.stride))) return rc;
+    if (down.data && (rc = encode_block_map(encode, tdown, const_cast<void*>(down.data), p.ngroups, (int)down.rows, down.stride))) return rc;
+    ShardParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.up_src = (const float4*)up.data;
+    sp.down_src = (const float4*)down.data;
+    sp.up_pitch_px = up.stride;
+    sp.down_pitch_px = down.stride;
+    sp.up_rows = (int)up.rows;
+    sp.link = link;
+    if (!up.data) sp.link.up = nullptr;
+    if (!down.data) sp.link.down = nullptr;
+    // a neighbour side never takes the border path: rows beyond the block are real rows there
+    t_last_kernel = exact ? "fused_sep_rgbaf32_shard_exact" : "fused_sep_rgbaf32_shard";
+    switch (half) {
+        case 1: return launch_shard<1>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 2: return launch_shard<2>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 3: return launch_shard<3>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 4: return launch_shard<4>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 5: return launch_shard<5>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 6: return launch_shard<6>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 7: return launch_shard<7>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 8: return launch_shard<8>(tmap, tup, tdown, p, sp, grid, exact, s);
     }
     return ZB_ERR_UNSUPPORTED;
 }

@@ -311,7 +311,7 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     const int half = half_x > half_y ? half_x : half_y;
     if (half < 1 || half > MAX_HALF) return ZB_ERR_UNSUPPORTED;
     if (src->cols < 16 || src->rows < 16) return ZB_ERR_UNSUPPORTED;
-    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;
+    if (images_overlap(src, dst, 4)) return ZB_ERR_UNSUPPORTED;   // in place / overlapping views: the temp-plane path
     if (((uintptr_t)src->data & 15u) || (src->stride & 3u)) return ZB_ERR_UNSUPPORTED;  // TMA: 16-byte aligned base and row pitch
     U8Params p;
     memset(&p, 0, sizeof(p));

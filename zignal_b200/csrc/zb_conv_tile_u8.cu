@@ -205,7 +205,7 @@ int launch_half(int half, const TileParams& p, cudaStream_t s) {
 int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, const float* kx, int nx, const float* ky, int ny, int border,
                            cudaStream_t s) {
     if (channels != 1 && channels != 3 && channels != 4) return ZB_ERR_UNSUPPORTED;
-    if (src->data == dst->data) return ZB_ERR_UNSUPPORTED;                         // in place: the temp-plane path
+    if (images_overlap(src, dst, (size_t)channels)) return ZB_ERR_UNSUPPORTED;     // in place / overlapping views: the temp-plane path
     const int half_x = nx / 2, half_y = ny / 2;
     const int half = half_x > half_y ? half_x : half_y;
     if (half < 1 || half > TU_MAX_HALF) return ZB_ERR_UNSUPPORTED;

@@ -19,6 +19,7 @@
 #include "zb_host_stage.h"
 #include "zb_internal.h"
 #include "zb_linalg.h"
+#include "zb_shard.h"
 #include "zb_svd_core.h"
 
 struct FdmTarget {   // what `update` needs from the target (fdm.zig:92-121)
@@ -79,10 +80,24 @@ __device__ __forceinline__ void store_group(uint8_t* __restrict__ img, size_t gr
     }
 }
 
+struct MapParams;
+// What the last block of the statistics kernel does when `update` is queued (fdm.zig:174-254): combine the moments across
+// ranks (sharded images), solve the 3x3 problem, leave the map parameters for the map kernel.
+struct SolveTail {
+    int enabled;
+    int pixfmt;
+    unsigned int* ticket;      // blocks that have added their partial sums
+    MapParams* out;
+    int* status;
+    FdmTarget target;
+    zb::ShardAll all;          // world == 1: single GPU
+};
+__device__ void moments_tail(unsigned long long* sums, const SolveTail& tail);
+
 // sums: {n, Sr, Sg, Sb, Srr, Srg, Srb, Sgg, Sgb, Sbb, non_gray}
 template <int CH>
 __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict__ img, size_t n_px, int as_luma,
-                                                      unsigned long long* __restrict__ sums) {
+                                                      unsigned long long* __restrict__ sums, const SolveTail tail) {
     unsigned long long acc[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) acc[i] = 0;
@@ -179,6 +194,16 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
         unsigned long long v = 0;
         for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
         atomicAdd(&sums[threadIdx.x], v);
+    }
+    if (tail.enabled) {
+        __shared__ int is_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            is_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1u;
+        }
+        __syncthreads();
+        if (is_last && threadIdx.x < 32) moments_tail(sums, tail);
     }
 }
 
@@ -291,6 +316,12 @@ __global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img,
     }
 }
 
+static SolveTail no_tail() {
+    SolveTail t;
+    memset(&t, 0, sizeof(t));
+    return t;
+}
+
 int moments_device(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums11, cudaStream_t s) {
     if (!img || !sums11) return ZB_ERR_INVALID_ARGUMENT;
     if (pixfmt != ZB_PIX_U8 && pixfmt != ZB_PIX_RGB8 && pixfmt != ZB_PIX_RGBA8) return ZB_ERR_UNSUPPORTED;  // fdm.zig:20
@@ -307,9 +338,9 @@ int moments_device(const zb_image* img, int pixfmt, int as_luma, uint64_t* sums1
         const uint8_t* p = (const uint8_t*)img->data;
         auto* ds = d.as<unsigned long long>();
         switch (pixfmt) {
-            case ZB_PIX_U8: moments_kernel<1><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds); break;
-            case ZB_PIX_RGB8: moments_kernel<3><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds); break;
-            default: moments_kernel<4><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds); break;
+            case ZB_PIX_U8: moments_kernel<1><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds, no_tail()); break;
+            case ZB_PIX_RGB8: moments_kernel<3><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds, no_tail()); break;
+            default: moments_kernel<4><<<blocks, 256, 0, s>>>(p, n_px, as_luma, ds, no_tail()); break;
         }
         ZB_LAUNCHED();
     }
@@ -395,6 +426,47 @@ __global__ void fdm_solve_kernel(const unsigned long long* __restrict__ m, FdmTa
     *status = rc;
 }
 
+// Runs in the first warp of the last block of moments_kernel.  Sharded images: every rank stores its 11 sums into its slot of
+// every rank's control block (plain peer stores over NVLink, then one release flag per rank), waits for the other ranks' flags
+// and adds the slots in rank order -- an 88-byte all-gather that costs one NVLink round trip instead of a collective launch.
+__device__ void moments_tail(unsigned long long* sums, const SolveTail& tail) {
+    __shared__ unsigned long long m[11];
+    const int lane = threadIdx.x;
+    __threadfence();
+    if (lane < 11) {
+        m[lane] = atomicAdd(&sums[lane], 0ull);
+        sums[lane] = 0;                                  // ready for the next call: no memset node per update
+    }
+    __syncwarp();
+    const zb::ShardAll& a = tail.all;
+    if (a.world > 1) {
+        const int par = (int)(a.epoch & 1ull);
+        if (lane < 11)
+            for (int r = 0; r < a.world; ++r) a.ctrl[r]->gather[par][a.rank][lane] = m[lane];
+        __threadfence_system();
+        __syncwarp();
+        if (lane < a.world) st_release_sys(&a.ctrl[lane]->gather[par][a.rank][15], a.epoch);
+        zb::ShardCtrl* me = a.ctrl[a.rank];
+        if (lane < a.world) zb::shard_wait_ge(&me->gather[par][lane][15], a.epoch, me);
+        __syncwarp();
+        if (lane < 11) {
+            unsigned long long v = 0;
+            for (int r = 0; r < a.world; ++r) v += *(volatile unsigned long long*)&me->gather[par][r][lane];
+            m[lane] = v;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        *tail.ticket = 0;
+        MapParams p;
+        const int rc = fdm_solve(m, tail.target, tail.pixfmt, p);
+        for (int i = 0; i < 9; ++i) { p.wf[i] = (float)p.w[i]; p.wa[i] = fabsf(p.wf[i]); }
+        for (int j = 0; j < 3; ++j) { p.bf[j] = (float)(255.0 * p.bias[j]) + 0.5f; p.ba[j] = fabsf(p.bf[j]) + 1.0f; }
+        *tail.out = p;
+        *tail.status = rc;
+    }
+}
+
 // fdm.zig:92-121
 int set_target_from_moments(zb_fdm* f, const uint64_t* m) {
     double cov[9];
@@ -414,47 +486,63 @@ int set_target_from_moments(zb_fdm* f, const uint64_t* m) {
 
 int ensure_device_state(zb_fdm* f) {
     if (f->d_m) return ZB_OK;
-    ZB_CUDA(cudaMalloc(&f->d_m, 11 * sizeof(unsigned long long)));
+    ZB_CUDA(cudaMalloc(&f->d_m, 12 * sizeof(unsigned long long)));   // 11 sums + the block ticket of the fused tail
     ZB_CUDA(cudaMalloc(&f->d_params, sizeof(MapParams)));
     ZB_CUDA(cudaMalloc(&f->d_status, sizeof(int)));
+    ZB_CUDA(cudaMemset(f->d_m, 0, 12 * sizeof(unsigned long long)));
     ZB_CUDA(cudaMemset(f->d_status, 0, sizeof(int)));
     return ZB_OK;
 }
 
-// queue the moment pass of `img` into f->d_m (no host synchronisation)
-int moments_enqueue(zb_fdm* f, const zb_image* img, int as_luma, cudaStream_t s) {
+FdmTarget target_of(const zb_fdm* f) {
+    FdmTarget t;
+    memcpy(t.mean, f->target_mean, sizeof(t.mean));
+    memcpy(t.u, f->target_u, sizeof(t.u));
+    memcpy(t.s, f->target_s, sizeof(t.s));
+    t.is_gray = f->target_is_gray ? 1 : 0;
+    return t;
+}
+
+// Queue the moment pass of `img` into f->d_m (no host synchronisation).  With `solve` the last block of the kernel also finishes
+// the statistics (all-gather across ranks when `all` has more than one), solves the 3x3 problem and writes the map parameters:
+// the separate one-thread solve launch and the memset node are gone.  f->d_m is zero on entry and on exit in that mode.
+int moments_enqueue(zb_fdm* f, const zb_image* img, int as_luma, cudaStream_t s, bool solve, const ShardAll* all) {
     if (img->stride != img->cols) return ZB_ERR_UNSUPPORTED;  // the reference walks image.data linearly (fdm.zig:82)
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
     if ((rc = ensure_device_state(f))) return rc;
     const size_t n_px = (size_t)img->rows * img->cols;
-    ZB_CUDA(cudaMemsetAsync(f->d_m, 0, 11 * sizeof(unsigned long long), s));
-    if (n_px > 0) {
-        const unsigned blocks = (unsigned)std::min<size_t>((size_t)di.sm_count * 8, (n_px + 255) / 256);
+    SolveTail tail = no_tail();
+    if (solve) {
+        tail.enabled = 1;
+        tail.pixfmt = f->pixfmt;
+        tail.ticket = reinterpret_cast<unsigned int*>(f->d_m + 11);
+        tail.out = (MapParams*)f->d_params;
+        tail.status = f->d_status;
+        tail.target = target_of(f);
+        if (all) tail.all = *all;
+        else { tail.all.world = 1; tail.all.rank = 0; }
+    } else {
+        ZB_CUDA(cudaMemsetAsync(f->d_m, 0, 11 * sizeof(unsigned long long), s));
+    }
+    if (n_px > 0 || solve) {
+        const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)di.sm_count * 8, (n_px + 255) / 256));
         const uint8_t* p = (const uint8_t*)img->data;
         switch (f->pixfmt) {
-            case ZB_PIX_U8: moments_kernel<1><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
-            case ZB_PIX_RGB8: moments_kernel<3><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
-            default: moments_kernel<4><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m); break;
+            case ZB_PIX_U8: moments_kernel<1><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m, tail); break;
+            case ZB_PIX_RGB8: moments_kernel<3><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m, tail); break;
+            default: moments_kernel<4><<<blocks, 256, 0, s>>>(p, n_px, as_luma, f->d_m, tail); break;
         }
         ZB_LAUNCHED();
     }
     return ZB_OK;
 }
 
-// fdm.zig:174-272 with the source moments already in f->d_m: solve on the device, then map -- all queued on `s`
-int solve_and_map(zb_fdm* f, cudaStream_t s) {
-    FdmTarget t;
-    memcpy(t.mean, f->target_mean, sizeof(t.mean));
-    memcpy(t.u, f->target_u, sizeof(t.u));
-    memcpy(t.s, f->target_s, sizeof(t.s));
-    t.is_gray = f->target_is_gray ? 1 : 0;
+int map_enqueue(zb_fdm* f, cudaStream_t s) {
     const size_t n_px = (size_t)f->source.rows * f->source.cols;
     if (n_px == 0) return ZB_OK;
     MapParams* dp = (MapParams*)f->d_params;
-    fdm_solve_kernel<<<1, 1, 0, s>>>(f->d_m, t, f->pixfmt, dp, f->d_status);
-    ZB_LAUNCHED();
     uint8_t* img = (uint8_t*)f->source.data;
     const unsigned blocks = div_up(n_px / 4 + 1, 256);   // one thread per 4-pixel group, one more for the tail
     switch (channels_of(f->pixfmt)) {
@@ -465,6 +553,16 @@ int solve_and_map(zb_fdm* f, cudaStream_t s) {
     ZB_LAUNCHED();
     t_last_kernel = "fdm_map";
     return ZB_OK;
+}
+
+// fdm.zig:174-272 with the source moments already in f->d_m: solve on the device (one thread), then map -- all queued on `s`
+int solve_and_map(zb_fdm* f, cudaStream_t s) {
+    const size_t n_px = (size_t)f->source.rows * f->source.cols;
+    if (n_px == 0) return ZB_OK;
+    fdm_solve_kernel<<<1, 1, 0, s>>>(f->d_m, target_of(f), f->pixfmt, (MapParams*)f->d_params, f->d_status);
+    ZB_LAUNCHED();
+    ZB_CUDA(cudaMemsetAsync(f->d_m, 0, 11 * sizeof(unsigned long long), s));   // the fused-tail mode expects zeroed sums
+    return map_enqueue(f, s);
 }
 
 }  // namespace
@@ -536,9 +634,44 @@ int zb_fdm_update(zb_fdm* f, zb_stream s) {
     if (!f->has_target) return ZB_ERR_NO_TARGET_SET;
     if (!f->has_source) return ZB_ERR_NO_SOURCE_SET;
     const int as_luma = (f->pixfmt != ZB_PIX_U8 && f->target_is_gray) ? 1 : 0;  // fdm.zig:155-162
-    int rc = moments_enqueue(f, &f->source, as_luma, (cudaStream_t)s);   // statistics pass, solve and map are queued back to back:
-    if (rc) return rc;                                                    // no device-to-host round trip between them
-    return solve_and_map(f, (cudaStream_t)s);
+    if ((size_t)f->source.rows * f->source.cols == 0) return ZB_OK;
+    int rc = moments_enqueue(f, &f->source, as_luma, (cudaStream_t)s, true, nullptr);   // statistics + solve: one kernel
+    if (rc) return rc;                                                                   // no device-to-host round trip
+    return map_enqueue(f, (cudaStream_t)s);
+}
+
+/* ---- sharded image: every rank holds a row block of the source / target ---- */
+int zb_shard_fdm_set_target(zb_shard_comm* c, zb_fdm* f, const zb_image* target_block, zb_stream stream) {
+    if (!c || !f || !target_block) return ZB_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = moments_enqueue(f, target_block, 0, s, false, nullptr);
+    if (rc) return rc;
+    if ((rc = shard_allreduce(c, f->d_m, 11, 2, s))) return rc;          // exact integer sums: order-independent
+    uint64_t m[11];
+    ZB_CUDA(cudaMemcpyAsync(m, f->d_m, sizeof(m), cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemsetAsync(f->d_m, 0, 11 * sizeof(unsigned long long), s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    return set_target_from_moments(f, m);
+}
+
+int zb_shard_fdm_update(zb_shard_comm* c, zb_fdm* f, zb_stream stream) {
+    if (!c || !f) return ZB_ERR_INVALID_ARGUMENT;
+    if (!f->has_target) return ZB_ERR_NO_TARGET_SET;
+    if (!f->has_source) return ZB_ERR_NO_SOURCE_SET;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int as_luma = (f->pixfmt != ZB_PIX_U8 && f->target_is_gray) ? 1 : 0;
+    int rc;
+    if (shard_world(c) > 1 && !shard_peer_ok(c)) {
+        // no peer mappings: NCCL all-reduce of the 11 sums between the statistics kernel and the one-thread solve
+        if ((rc = moments_enqueue(f, &f->source, as_luma, s, false, nullptr))) return rc;
+        if ((rc = shard_allreduce(c, f->d_m, 11, 2, s))) return rc;
+        if ((size_t)f->source.rows * f->source.cols == 0) return ZB_OK;
+        return solve_and_map(f, s);
+    }
+    ShardAll all;
+    shard_all(c, true, &all);
+    if ((rc = moments_enqueue(f, &f->source, as_luma, s, true, &all))) return rc;
+    return map_enqueue(f, s);
 }
 
 int zb_fdm_status(zb_fdm* f, zb_stream s) {

@@ -74,6 +74,16 @@ struct Scratch {
     template <typename T> T* as() const { return (T*)p; }
 };
 
+// Do the byte ranges two image views span intersect?  (Two views of one buffer with different base pointers may still
+// overlap; single-pass kernels read neighbourhoods other blocks are writing, so any overlap must take the snapshot path.)
+static inline bool images_overlap(const zb_image* a, const zb_image* b, size_t pixel_bytes_) {
+    if (!a->data || !b->data || a->rows == 0 || a->cols == 0 || b->rows == 0 || b->cols == 0) return false;
+    const uintptr_t a0 = (uintptr_t)a->data, b0 = (uintptr_t)b->data;
+    const uintptr_t a1 = a0 + ((size_t)(a->rows - 1) * a->stride + a->cols) * pixel_bytes_;
+    const uintptr_t b1 = b0 + ((size_t)(b->rows - 1) * b->stride + b->cols) * pixel_bytes_;
+    return a0 < b1 && b0 < a1;
+}
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace zb

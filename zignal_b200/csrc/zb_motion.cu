@@ -181,7 +181,7 @@ extern "C" int zb_motion_blur_linear(const zb_image* src, zb_image* dst, int pix
         return horizontal ? conv_separable_dispatch(src, dst, pixfmt, kernel.data(), (int)distance, identity, 1, ZB_BORDER_REPLICATE, s, 0, -1)
                           : conv_separable_dispatch(src, dst, pixfmt, identity, 1, kernel.data(), (int)distance, ZB_BORDER_REPLICATE, s, 0, -1);
     }
-    if (src->data == dst->data) return ZB_ERR_INVALID_ARGUMENT;     // a gather: the reference reads `image` while it writes `out`
+    if (images_overlap(src, dst, pixel_bytes(pixfmt))) return ZB_ERR_INVALID_ARGUMENT;     // a gather: the reference reads `image` while it writes `out`
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     MotionParams p = base_params(src, dst);
@@ -201,7 +201,7 @@ extern "C" int zb_motion_blur_radial(const zb_image* src, zb_image* dst, int pix
     cudaStream_t s = (cudaStream_t)stream;
     if (src->rows == 0 || src->cols == 0) return ZB_OK;
     if (strength == 0) return zb_copy(src, dst, pixfmt, stream);                                        // :262-265
-    if (src->data == dst->data) return ZB_ERR_INVALID_ARGUMENT;
+    if (images_overlap(src, dst, pixel_bytes(pixfmt))) return ZB_ERR_INVALID_ARGUMENT;
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     MotionParams p = base_params(src, dst);

@@ -186,7 +186,7 @@ extern "C" int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uin
     // Every block reads a halo that other blocks write when the images alias (:52-60 uses a temporary for the same reason).
     Scratch tmp;
     zb_image staged = *dst;
-    const bool alias = src->data == dst->data;
+    const bool alias = images_overlap(src, dst, (size_t)ch);
     if (alias) {
         if ((rc = tmp.alloc((size_t)p.rows * p.cols * ch, s))) return rc;
         staged.data = tmp.p;

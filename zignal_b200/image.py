@@ -286,7 +286,7 @@ class Image:
     # ---- geometry (image.zig:558-623) -------------------------------------------------------------
     def rotate_bounds(self, angle: float) -> Tuple[int, int]:
         r, c = C.c_uint32(), C.c_uint32()
-        self._run(lib().zb_rotate_bounds, self.rows, self.cols, C.c_float(angle), C.byref(r), C.byref(c)))
+        check(lib().zb_rotate_bounds(self.rows, self.cols, C.c_float(angle), C.byref(r), C.byref(c)))
         return r.value, c.value
 
     def rotate_into(self, out: "Image", angle: float, method: Interpolation = Interpolation.BILINEAR,
@@ -294,8 +294,7 @@ class Image:
         self._peer(out)
         a, d = self._zb(), out._zb()
         if cos_sin is None:
-            check(lib().zb_rotate_into(a, d, int(self.pixfmt), C.c_float(angle), int(method), C.c_float(b), C.c_float(c),
-                                       int(border))
+            self._run(lib().zb_rotate_into, a, d, int(self.pixfmt), C.c_float(angle), int(method), C.c_float(b), C.c_float(c), int(border))
         else:
             self._run(lib().zb_rotate_into_cs, a, d, int(self.pixfmt), C.c_float(angle), C.c_float(cos_sin[0]), C.c_float(cos_sin[1]),
                                           int(method), C.c_float(b), C.c_float(c), int(border))

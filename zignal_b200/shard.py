@@ -1,5 +1,14 @@
 """Row-block sharding of one large image across the GPUs of a box (one process per GPU).
 
+Two layers live here:
+  * `ShardComm` / `ShardImage` -- the ctypes mirror of the C ABI's multi-GPU entry points (zb_shard_*, include/zignal_b200.h):
+    NCCL bootstraps, NVLink peer memory carries the data (the RGBA f32 convolution kernel TMA-loads its neighbours' edge rows
+    itself, everything else goes through one pull kernel), fdm's 11 moments are all-gathered inside the statistics kernel.
+    This is the product path; bench.py and tools/gpu_shard_check.py run it under torchrun.
+  * `RowBlock` -- the same partitioning written against torch.distributed (gloo on CPU tensors, NCCL on CUDA tensors).  It is
+    the host-logic model the world-size-2/3 gloo tests exercise without a GPU, and the fallback when a host cannot use the
+    C ABI's communicator.
+
 The reference is single-process; this is the multi-GPU layer SURVEY.md 8(e) defines for the hot path:
   * convolution / blur: contiguous row blocks, each stored with `halo` extra rows above and below; one
     batched send/recv pair per row neighbour fills the halos (NCCL over NVLink on GPUs, gloo on CPU for
@@ -107,13 +116,15 @@ class RowBlock:
             ops.append(dist.P2POp(dist.irecv, t[0:h], up))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def conv_separable(self, out: "RowBlock", kx, ky, border: BorderMode = BorderMode.MIRROR, stream=None):
+    def conv_separable(self, out: "RowBlock", kx, ky, border: BorderMode = BorderMode.MIRROR):
         """Image.convolveSeparable on the global image this block belongs to (interior rows of `out` receive the result).
         One exchange (NCCL isend/irecv of `halo` rows per neighbour) overlapped with the convolution of every row that
         does not read a halo; the 2 x half boundary rows follow once the halos have landed."""
         from . import _ffi
-        from .image import _fptr, current_stream
+        from .image import _fptr
         import ctypes as C
+        import torch
+        assert out.halo == self.halo and out.rows == self.rows and out.cols == self.cols and out.pixfmt == self.pixfmt
         kx = np.ascontiguousarray(kx, dtype=np.float32)
         ky = np.ascontiguousarray(ky, dtype=np.float32)
         half = max(kx.size, ky.size) // 2
@@ -125,7 +136,9 @@ class RowBlock:
         dst = Image(out.t.reshape(-1), out.pixfmt, hi - lo, cols, cols, lo * cols)
         a, d = src._zb(), dst._zb()
         L = _ffi.lib()
-        st = stream if stream is not None else current_stream()
+        # torch.distributed orders the exchange against the CURRENT stream of the block's device (batch_isend_irecv synchronises
+        # with it when posted, wait() blocks it), so the kernels must be launched on exactly that stream
+        st = torch.cuda.current_stream(self.t.device).cuda_stream
         reqs = self.post_halo_exchange(border)
         waited = False
         for (r0, r1, needs_halo) in steps:
@@ -263,3 +276,184 @@ def sharded_covariance(x_local, gram_fn=None, center_fn=None):
     if world > 1:
         dist.all_reduce(part, op=dist.ReduceOp.SUM)
     return mean, (part / float(n - 1)).to(x_local.dtype)
+
+
+# =====================================================================================================================
+# The C ABI's multi-GPU layer (zb_shard_*): NCCL bootstrap + NVLink peer memory
+# =====================================================================================================================
+class _DevMem:
+    """A raw device allocation exposed through __cuda_array_interface__ so torch can wrap it without owning it."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class ShardComm:
+    """zb_shard_comm: one per process / GPU.  `ShardComm.from_torch_distributed()` takes rank / world from the initialised
+    process group and broadcasts the NCCL unique id through it (any backend); a host without torch passes the id itself."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes = None):
+        import ctypes as C
+        from . import _ffi
+        L = _ffi.lib()
+        self._h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _ffi.check(L.zb_shard_comm_create(C.byref(self._h), int(rank), int(world), idbuf))
+        self.rank, self.world = int(rank), int(world)
+        pa = C.c_int(0)
+        _ffi.check(L.zb_shard_comm_info(self._h, None, None, C.byref(pa)))
+        self.peer_access = bool(pa.value)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _ffi
+        buf = (C.c_uint8 * 128)()
+        _ffi.check(_ffi.lib().zb_shard_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_distributed(cls) -> "ShardComm":
+        dist = _dist()
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(0, 1, None)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(rank, world, box[0])
+
+    def destroy(self):
+        from . import _ffi
+        if self._h:
+            _ffi.lib().zb_shard_comm_destroy(self._h)
+            self._h = None
+
+    def status(self):
+        """Waits for the current stream; raises DeviceFailure if a kernel gave up waiting for a neighbour."""
+        from . import _ffi
+        from .image import current_stream
+        _ffi.check(_ffi.lib().zb_shard_status(self._h, current_stream()))
+
+    def split(self, n_items: int):
+        import ctypes as C
+        from . import _ffi
+        lo, hi = C.c_uint32(), C.c_uint32()
+        _ffi.check(_ffi.lib().zb_shard_split(int(n_items), self.rank, self.world, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def allreduce(self, t):
+        """In-place sum of a contiguous CUDA tensor (f32 / f64 / i64-as-u64) over all ranks (zb_shard_allreduce, NCCL)."""
+        import torch
+        from . import _ffi
+        dt = {torch.float32: 0, torch.float64: 1, torch.int64: 2}[t.dtype]
+        assert t.is_cuda and t.is_contiguous()
+        _ffi.check(_ffi.lib().zb_shard_allreduce(self._h, t.data_ptr(), t.numel(), dt, torch.cuda.current_stream(t.device).cuda_stream))
+        return t
+
+    def image(self, rows: int, cols: int, pixfmt: PixFmt, halo: int = 0) -> "ShardImage":
+        return ShardImage(self, rows, cols, pixfmt, halo)
+
+    # ---- fdm on a row-sharded image ----
+    def fdm_set_target(self, f, target_block: Image):
+        from . import _ffi
+        from .image import current_stream
+        t = target_block._zb()
+        _ffi.check(_ffi.lib().zb_shard_fdm_set_target(self._h, f._h, t, current_stream()))
+
+    def fdm_update(self, f):
+        from . import _ffi
+        from .image import current_stream
+        _ffi.check(_ffi.lib().zb_shard_fdm_update(self._h, f._h, current_stream()))
+
+
+class ShardImage:
+    """This rank's row block (rows x cols, `halo` spare rows above and below) of a global image of world blocks stacked in rank
+    order: symmetric memory from zb_shard_alloc, described to the library by zb_shard_image_create."""
+
+    def __init__(self, comm: ShardComm, rows: int, cols: int, pixfmt: PixFmt, halo: int = 0):
+        import ctypes as C
+        import torch
+        from . import _ffi
+        from ._ffi import ZbImage
+        L = _ffi.lib()
+        self.comm, self.rows, self.cols, self.halo = comm, int(rows), int(cols), int(halo)
+        self.pixfmt = PixFmt(pixfmt)
+        ch = _CH[self.pixfmt]
+        self._np = _NP[self.pixfmt]
+        esz = np.dtype(self._np).itemsize
+        self._pb = ch * esz
+        total_rows = self.rows + 2 * self.halo
+        nbytes = max(16, total_rows * self.cols * self._pb)
+        base = C.c_void_p()
+        _ffi.check(L.zb_shard_alloc(comm._h, nbytes, C.byref(base)))
+        self._base = base.value
+        shape = (total_rows, self.cols) + ((ch,) if ch > 1 else ())
+        self._mem = _DevMem(self._base, shape, "|u1" if self._np == np.uint8 else "<f4")
+        self.t = torch.as_tensor(self._mem, device=torch.device("cuda", torch.cuda.current_device()))
+        self.t.zero_()
+        torch.cuda.synchronize()
+        blk = ZbImage(self._base + self.halo * self.cols * self._pb, self.rows, self.cols, self.cols)
+        self._h = C.c_void_p()
+        _ffi.check(L.zb_shard_image_create(comm._h, blk, self.halo, int(self.pixfmt), C.byref(self._h)))
+
+    def interior_tensor(self):
+        return self.t[self.halo:self.halo + self.rows]
+
+    def block_image(self) -> Image:
+        return Image(self.t.reshape(-1), self.pixfmt, self.rows, self.cols, self.cols, self.halo * self.cols)
+
+    def free(self):
+        from . import _ffi
+        L = _ffi.lib()
+        if self._h:
+            L.zb_shard_image_destroy(self._h)
+            self._h = None
+        if self._base:
+            self.t = None
+            _ffi.check(L.zb_shard_free(self.comm._h, self._base))
+            self._base = None
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.t.device).cuda_stream
+
+    def conv_separable(self, out: "ShardImage", kx, ky, border: BorderMode = BorderMode.MIRROR) -> "ShardImage":
+        from . import _ffi
+        from .image import _fptr
+        kx = np.ascontiguousarray(kx, dtype=np.float32)
+        ky = np.ascontiguousarray(ky, dtype=np.float32)
+        _ffi.check(_ffi.lib().zb_shard_conv_separable(self.comm._h, self._h, out._h, _fptr(kx), kx.size, _fptr(ky), ky.size, int(border),
+                                                      self._stream()))
+        return out
+
+    def gaussian_blur(self, out: "ShardImage", sigma: float) -> "ShardImage":
+        import ctypes as C
+        from . import _ffi
+        _ffi.check(_ffi.lib().zb_shard_gaussian_blur(self.comm._h, self._h, out._h, C.c_float(sigma), self._stream()))
+        return out
+
+    def halo_exchange(self, reach: int, border: BorderMode = BorderMode.MIRROR):
+        from . import _ffi
+        _ffi.check(_ffi.lib().zb_shard_halo_exchange(self.comm._h, self._h, int(reach), int(border), self._stream()))
+
+    def view(self, reach: int, border: BorderMode = BorderMode.MIRROR):
+        """(Image of the block plus the exchanged halo rows, index of the block's first row inside it)."""
+        import ctypes as C
+        from . import _ffi
+        from ._ffi import ZbImage
+        v = ZbImage()
+        first = C.c_uint32()
+        _ffi.check(_ffi.lib().zb_shard_view(self._h, int(reach), int(border), C.byref(v), C.byref(first)))
+        off_rows = self.halo - first.value
+        return Image(self.t.reshape(-1), self.pixfmt, v.rows, self.cols, self.cols, off_rows * self.cols), first.value
+
+    def apply_neighbourhood(self, out: "ShardImage", fn, reach: int, border: BorderMode = BorderMode.MIRROR) -> "ShardImage":
+        """Any same-shape filter whose output row r reads input rows [r - reach, r + reach] (boxBlur, sharpen, dense convolve, sobel,
+        order statistics, motionBlur.linear) on the global image: one halo exchange, then `fn(src_view, dst_view)` once."""
+        assert out.halo == self.halo and out.rows == self.rows and out.cols == self.cols and self.halo >= reach
+        self.halo_exchange(reach, border)
+        sv, first = self.view(reach, border)
+        dv, first2 = out.view(reach, border)
+        assert first == first2
+        fn(sv, dv)
+        return out

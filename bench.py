@@ -262,13 +262,11 @@ def main():
     launches = L.zb_kernel_launch_count() - launches0
     kernel_name = L.zb_last_kernel().decode()
     comm.status()
-    # keep the GPU under the same load a little longer so the clock sampler sees it
-    if rank == 0 and world == 1:
-        t_end = time.time() + 1.2
-        while time.time() < t_end:
-            for _ in range(50):
-                step()
-            torch.cuda.synchronize()
+    # keep the GPU under the same load a little longer so the clock sampler sees it (every rank: the steps are collective)
+    for _ in range(60):
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity of the sharded result, checked inside this run (N > 1) -------------------------------------------------

@@ -257,15 +257,24 @@ int zb_gemm_f64(const double* a, uint32_t a_rows, uint32_t a_cols, int trans_a,
  * centered = x - mean (skipped when NULL).  Pca.transform (pca.zig:300-308) calls it with compute_mean = 0.  DEVICE pointers. */
 int zb_center_columns_f32(const float* x, uint32_t n, uint32_t dim, float* mean, int compute_mean, float* centered, zb_stream s);
 int zb_center_columns_f64(const double* x, uint32_t n, uint32_t dim, double* mean, int compute_mean, double* centered, zb_stream s);
-/* Matrix.svd / SMatrix.svd   Matrix.zig:1570, SMatrix.zig:804, svd.zig:80-496.  HOST matrices
- * (the decomposition is sequential; callers on this path pass 3x3 .. dim x dim covariance matrices).
- * a: m x n row-major, m >= n.  u: m x (mode==FULL ? m : n) or NULL; s: n; v: n x n or NULL.
- * *converged receives 0 or the failing index (svd.zig:79). */
+/* Matrix.svd / SMatrix.svd   Matrix.zig:1570, SMatrix.zig:804, svd.zig:80-496.  HOST matrices.
+ * a: m x n row-major, m >= n.  u: m x (mode==FULL ? m : n) or NULL; s: n (descending); v: n x n or NULL.
+ * *converged receives 0 or a non-zero failure mark (svd.zig:79).
+ * Computed by a one-sided Jacobi method with a parallel pair ordering on the GPU (n >= 24; smaller matrices run the same
+ * algorithm on the host), not by the reference's sequential Golub-Reinsch: singular values agree to sqrt(eps) (to high relative
+ * accuracy, in fact), U and V are orthonormal and reconstruct A, but the SIGN of each (u_i, v_i) pair and the basis inside a
+ * cluster of equal singular values are the decomposition's usual freedom and may differ from the reference's. */
 int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged);
 int zb_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v, float* u, float* s, float* v, uint64_t* converged);
-/* Matrix.eigh(allocator)   matrix/eigen.zig:34-136: symmetric eigendecomposition by cyclic Jacobi rotations (HOST pointers, row-major
- * n x n).  values[n] ascending, vectors[n * n] with the matching unit eigenvectors as columns.  ZB_ERR_NOT_SQUARE, ZB_ERR_NOT_FINITE
- * (NaN / inf entry), ZB_ERR_NOT_SYMMETRIC (|a_ij - a_ji| > max|a| * sqrt(eps)).  A host routine like the SVD: replicas only. */
+/* The same decomposition for a matrix that already lives on the device (Pca.fit: the covariance from zb_gemm never leaves the
+ * GPU, pca.zig:331-425).  d_a: m x n row-major DEVICE (not modified); d_u: m x n skinny U or NULL; d_s: n; d_v: n x n or NULL --
+ * all DEVICE.  Returns after the stream has finished. */
+int zb_svd_dev_f64(const double* d_a, uint32_t m, uint32_t n, double* d_u, double* d_s, double* d_v, uint64_t* converged, zb_stream s);
+int zb_svd_dev_f32(const float* d_a, uint32_t m, uint32_t n, float* d_u, float* d_s, float* d_v, uint64_t* converged, zb_stream s);
+/* Matrix.eigh(allocator)   matrix/eigen.zig:34-136: symmetric eigendecomposition (HOST pointers, row-major n x n).  values[n] ascending,
+ * vectors[n * n] with the matching unit eigenvectors as columns.  ZB_ERR_NOT_SQUARE, ZB_ERR_NOT_FINITE (NaN / inf entry),
+ * ZB_ERR_NOT_SYMMETRIC (|a_ij - a_ji| > max|a| * sqrt(eps)), in the reference's order.  Two-sided Jacobi with a parallel pair
+ * ordering on the GPU (n >= 24, host below): same eigenvalues to eps * |A|, eigenvectors up to sign. */
 int zb_eigh_f64(const double* a, uint32_t rows, uint32_t cols, double* values, double* vectors);
 int zb_eigh_f32(const float* a, uint32_t rows, uint32_t cols, float* values, float* vectors);
 

@@ -114,17 +114,24 @@ L.zb_set_exact_f32(0)
 a.free()
 b.free()
 
-# box blur through the generic neighbourhood route
-for pixfmt in (zb.PixFmt.RGBA8, zb.PixFmt.U8):
-    full = make_full(pixfmt, 200 * world, 640, 3)
-    a, b = comm.image(200, 640, pixfmt, 8), comm.image(200, 640, pixfmt, 8)
-    a.interior_tensor().copy_(full[200 * rank:200 * (rank + 1)])
-    a.apply_neighbourhood(b, lambda s, d: s.box_blur(3, out=d), 4, zb.BorderMode.MIRROR)
-    want = zb.Image.from_tensor(full).box_blur(3).tensor()[200 * rank:200 * (rank + 1)]
-    torch.cuda.synchronize()
-    report(f"box blur r=3 {pixfmt.name}", bool(torch.equal(b.interior_tensor(), want)))
-    a.free()
-    b.free()
+# other neighbourhood filters through zb_shard_halo_exchange + the ordinary entry point on the extended view.
+# (box blur / sharpen evaluate an f32 summed-area table whose column prefix starts at the GLOBAL row 0 -- integral.zig:41-78 -- so
+# a row block reproduces the single-GPU bits only while every prefix stays below 2^24, where f32 sums are exact: 48 columns here.)
+cases = [("box blur r=3 (exact-sum regime)", 48, 4, lambda s_, d_: s_.box_blur(3, out=d_), lambda im: im.box_blur(3)),
+         ("dense 3x3 convolve", 640, 1, lambda s_, d_: s_.convolve(np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.float32) / 16, zb.BorderMode.MIRROR, out=d_),
+          lambda im: im.convolve(np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.float32) / 16, zb.BorderMode.MIRROR)),
+         ("median blur r=2", 640, 2, lambda s_, d_: s_.median_blur(2, out=d_), lambda im: im.median_blur(2))]
+for name, cols, reach, fn, whole_fn in cases:
+    for pixfmt in (zb.PixFmt.RGBA8, zb.PixFmt.U8):
+        full = make_full(pixfmt, 200 * world, cols, 3)
+        a, b = comm.image(200, cols, pixfmt, 8), comm.image(200, cols, pixfmt, 8)
+        a.interior_tensor().copy_(full[200 * rank:200 * (rank + 1)])
+        a.apply_neighbourhood(b, fn, reach, zb.BorderMode.MIRROR)
+        want = whole_fn(zb.Image.from_tensor(full)).tensor()[200 * rank:200 * (rank + 1)]
+        torch.cuda.synchronize()
+        report(f"{name} {pixfmt.name}", bool(torch.equal(b.interior_tensor(), want)))
+        a.free()
+        b.free()
 
 # fdm on a row-sharded Rgb image
 rows = 512

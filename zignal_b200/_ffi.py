@@ -115,6 +115,8 @@ def _declare(L):
         "zb_center_columns_f64": ([dp, u32, u32, dp, i, dp, vp], i),
         "zb_svd_f64": ([dp, u32, u32, i, i, dp, dp, dp, P(u64)], i),
         "zb_svd_f32": ([fp, u32, u32, i, i, fp, fp, fp, P(u64)], i),
+        "zb_svd_dev_f64": ([dp, u32, u32, dp, dp, dp, P(u64), vp], i),
+        "zb_svd_dev_f32": ([fp, u32, u32, fp, fp, fp, P(u64), vp], i),
         "zb_fdm_create": ([P(vp), i], i),
         "zb_fdm_destroy": ([vp], i),
         "zb_fdm_set_target": ([vp, img, vp], i),

@@ -111,37 +111,50 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
         a[4] += r * r; a[5] += r * g; a[6] += r * b;
         a[7] += g * g; a[8] += g * b; a[9] += b * b;
     };
-    if (!as_luma && ((uintptr_t)img & 3u) == 0) {
-        // packed path: the 4 pixels of a group are transposed into one word per channel (byte permutes) and every moment of the
-        // group is one dot product (dp4a): 6 PRMT + 9 DP4A for 4 pixels instead of ~40 scalar operations per pixel
+    size_t tail_start = n_groups * 4;   // first pixel the scalar tail below has to take
+    if (!as_luma && ((uintptr_t)img & 15u) == 0) {
+        // packed path: 16 pixels per iteration as CH 128-bit loads; the 4 pixels of a group are transposed into one word per
+        // channel (byte permutes) and every moment of the group is one dot product (dp4a): 6 PRMT + 9 DP4A for 4 pixels
+        // instead of ~40 scalar operations per pixel
         unsigned a[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) a[i] = 0;
         int pending = 0;
-#pragma unroll 4
-        for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < n_groups; grp += stride) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + grp * CH;
-            uint32_t R, G, B;
-            if constexpr (CH == 1) {
-                R = G = B = __ldg(w);
-            } else if constexpr (CH == 3) {
-                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
-                R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);              // r0 r1 r2 . -> r0 r1 r2 r3
-                G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);              // g0 g1 g2 g3
-                B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);              // b0 b1 . . -> b0 b1 b2 b3
-            } else {
-                const uint4 q = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));   // r g b a per word (base is only 4-byte aligned)
-                const uint32_t rg01 = __byte_perm(q.x, q.y, 0x5140), rg23 = __byte_perm(q.z, q.w, 0x5140);   // r0 r1 g0 g1 | r2 r3 g2 g3
-                R = __byte_perm(rg01, rg23, 0x5410);
-                G = __byte_perm(rg01, rg23, 0x7632);
-                B = __byte_perm(__byte_perm(q.x, q.y, 0x0062), __byte_perm(q.z, q.w, 0x0062), 0x5410);
+        const size_t n16 = n_px / 16;
+        tail_start = n16 * 16;
+#pragma unroll 2
+        for (size_t sg = (size_t)blockIdx.x * blockDim.x + threadIdx.x; sg < n16; sg += stride) {
+            const uint4* q4 = reinterpret_cast<const uint4*>(img) + sg * CH;
+            uint32_t w[4 * CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const uint4 v = __ldg(q4 + i);
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            a[0] += 4;
-            a[1] = __dp4a(R, 0x01010101u, a[1]); a[2] = __dp4a(G, 0x01010101u, a[2]); a[3] = __dp4a(B, 0x01010101u, a[3]);
-            a[4] = __dp4a(R, R, a[4]); a[5] = __dp4a(R, G, a[5]); a[6] = __dp4a(R, B, a[6]);
-            a[7] = __dp4a(G, G, a[7]); a[8] = __dp4a(G, B, a[8]); a[9] = __dp4a(B, B, a[9]);
-            if (CH != 1) a[10] = __dp4a(__vsetne4((R ^ G) | (G ^ B), 0u), 0x01010101u, a[10]);   // pixels with r != g or g != b
-            if (++pending == 4096) {   // 16384 pixels: 16384 * 255^2 < 2^32, flush before the u32 sums can wrap
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const uint32_t* wd = w + g4 * CH;
+                uint32_t R, G, B;
+                if constexpr (CH == 1) {
+                    R = G = B = wd[0];
+                } else if constexpr (CH == 3) {
+                    const uint32_t w0 = wd[0], w1 = wd[1], w2 = wd[2];                       // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+                    R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);              // r0 r1 r2 . -> r0 r1 r2 r3
+                    G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);              // g0 g1 g2 g3
+                    B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);              // b0 b1 . . -> b0 b1 b2 b3
+                } else {
+                    const uint32_t rg01 = __byte_perm(wd[0], wd[1], 0x5140), rg23 = __byte_perm(wd[2], wd[3], 0x5140);   // r0 r1 g0 g1 | r2 r3 g2 g3
+                    R = __byte_perm(rg01, rg23, 0x5410);
+                    G = __byte_perm(rg01, rg23, 0x7632);
+                    B = __byte_perm(__byte_perm(wd[0], wd[1], 0x0062), __byte_perm(wd[2], wd[3], 0x0062), 0x5410);
+                }
+                a[0] += 4;
+                a[1] = __dp4a(R, 0x01010101u, a[1]); a[2] = __dp4a(G, 0x01010101u, a[2]); a[3] = __dp4a(B, 0x01010101u, a[3]);
+                a[4] = __dp4a(R, R, a[4]); a[5] = __dp4a(R, G, a[5]); a[6] = __dp4a(R, B, a[6]);
+                a[7] = __dp4a(G, G, a[7]); a[8] = __dp4a(G, B, a[8]); a[9] = __dp4a(B, B, a[9]);
+                if (CH != 1) a[10] = __dp4a(__vsetne4((R ^ G) | (G ^ B), 0u), 0x01010101u, a[10]);   // pixels with r != g or g != b
+            }
+            if (++pending == 1024) {   // 16384 pixels: 16384 * 255^2 < 2^32, flush before the u32 sums can wrap
 #pragma unroll
                 for (int i = 0; i < 11; ++i) { acc[i] += a[i]; a[i] = 0; }
                 pending = 0;
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
         unsigned a[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) a[i] = 0;
-        for (size_t px = n_groups * 4; px < n_px; ++px) {
+        for (size_t px = tail_start; px < n_px; ++px) {   // at most 15 pixels
             if constexpr (CH == 1) add_px(a, img[px], img[px], img[px]);
             else add_px(a, img[px * CH], img[px * CH + 1], img[px * CH + 2]);
         }
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const uint8_t* __restrict_
 }
 
 struct MapParams {
-    float wf[9], wa[9], bf[3], ba[3];   // f32 fast path of the colour map: weights, |weights|, 255*bias + 1/2, |that| + 1
+    float wf[9], wa[9], bf[3], ba[3];   // f32 fast path of the colour map: weights, (unused), 255*bias, safe distance from k + 1/2 per channel
     double w[9];
     double bias[3];
     double scale, offset;  // gray branch
@@ -232,14 +245,43 @@ __device__ __noinline__ uint8_t fdm_exact_channel(int r, int g, int b, int j, co
     return quantize01(rr * p->w[j] + gg * p->w[3 + j] + bb * p->w[6 + j] + p->bias[j]);
 }
 
-// A thread maps 4 consecutive pixels (4*CH bytes as CH aligned words).
+// The colour map (fdm.zig:257-271) for one pixel: three outputs x_j = 255 * (r/255 * w0j + g/255 * w1j + b/255 * w2j + bias_j),
+// rounded half away from zero and clamped.
 //
-// FP64 is the scarce resource here (64 lanes/clk/SM): the reference's 9 multiplies, 9 adds, 3 divisions and 3 roundings per pixel
-// in f64 bound the kernel at ~5x the memory time.  So every output is first evaluated in f32 together with a rigorous bound on
-// |x32 - x64| (4 roundings of 2^-24 on the sum of absolute terms, doubled for slack); when x32 is farther than that bound from
-// every rounding boundary k + 1/2, the f64 value rounds to the same integer and the f32 result IS the reference's.  Otherwise
-// (a few pixels in 10^4) the output is recomputed with the reference's exact f64 sequence.  Gray maps are 256-entry byte tables
-// built with that same f64 sequence.
+// FP64 is the scarce resource (64 lanes/clk/SM): the reference's 9 multiplies, 9 adds, 3 divisions and 3 roundings per pixel in
+// f64 bound the kernel at ~5x the memory time.  So every output is first evaluated in f32 (three FMAs on weights rounded to f32)
+// together with a RIGOROUS bound on |x32 - x64|: each of the 3 FMA roundings and each of the 4 rounded constants contributes at
+// most 2^-24 of M_j = 255 (|w0j| + |w1j| + |w2j|) + |255 bias_j|, so |x32 - x64| <= 7 * 2^-24 * M_j; the solve stores the
+// per-channel constant safe_j = 1/2 - 8 * 2^-24 * M_j.  When x32 is closer than safe_j to its nearest integer, x64 rounds to that
+// same integer and the f32 result IS the reference's.  Otherwise (a few values in 10^4) the pixel is recomputed with the
+// reference's exact f64 sequence, out of line.  No integer<->float conversion instructions (a quarter-rate pipe): bytes enter
+// through the 2^23 exponent trick (PRMT + FADD), x32 is rounded to the nearest integer by adding 1.5 * 2^23, and the result byte is
+// the low byte of that sum.  Gray maps are 256-entry byte tables built with the same f64 sequence.
+struct MapRegs {
+    float w[9], b[3], safe[3];
+};
+__device__ __forceinline__ float byte_to_float(uint32_t word, int k) {   // byte k of `word` as a float, exactly
+    const uint32_t sel = 0x7440u | (uint32_t)k;
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+}
+// returns the packed result bytes (r | g << 8 | b << 16) and sets `bad` when a channel sits too close to a rounding boundary
+__device__ __forceinline__ uint32_t map_colour(float rf, float gf, float bf, const MapRegs& m, bool& bad) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float x = fmaf(bf, m.w[6 + j], fmaf(gf, m.w[3 + j], fmaf(rf, m.w[j], m.b[j])));   // ~ 255 * res
+        const float t = __fadd_rn(x, 12582912.0f);           // round to the nearest integer (ties are inside the unsafe band)
+        const float n = __fsub_rn(t, 12582912.0f);
+        const float d = __fsub_rn(x, n);
+        bad |= !(fabsf(d) < m.safe[j]);
+        const float c = fminf(fmaxf(n, 0.0f), 255.0f);
+        const uint32_t bits = __float_as_uint(__fadd_rn(c, 8388608.0f));   // integer c in the low mantissa byte
+        out |= (bits & 0xFFu) << (8 * j);
+    }
+    return out;
+}
+
+// A thread maps 16 consecutive pixels when the image is 16-byte aligned (CH 128-bit loads and stores), else 4.
 template <int CH>
 __global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img, size_t n_px, const MapParams* __restrict__ pp) {
     __shared__ uint8_t gray_lut[256];
@@ -252,67 +294,116 @@ __global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img,
         gray_lut[threadIdx.x] = quantize01(((double)threadIdx.x / 255.0) * p.scale + p.offset);
         __syncthreads();
     }
-    // f32 copies of the colour map, pre-scaled to the 0..255 domain: x_j = r*w0j + g*w1j + b*w2j + 255*bias_j
-    float wf[9], wa[9], bf[3], ba[3];
+    MapRegs m;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { wf[i] = p.wf[i]; wa[i] = p.wa[i]; }
+    for (int i = 0; i < 9; ++i) m.w[i] = p.wf[i];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { bf[j] = p.bf[j]; ba[j] = p.ba[j]; }
-    // maps one pixel in place; returns a 3-bit mask of the channels whose f32 value sits too close to a rounding boundary
-    auto map_px = [&](uint8_t* q) -> unsigned {
+    for (int j = 0; j < 3; ++j) { m.b[j] = p.bf[j]; m.safe[j] = p.ba[j]; }
+
+    // maps the pixel whose channel bytes are r, g, b (positions inside `q`: byte offsets), in place in the byte array
+    auto map_px = [&](uint8_t* q) {
         if constexpr (CH == 1) {
             q[0] = gray_lut[q[0]];
-            return 0u;
         } else {
             if (mode == 2) {
                 const uint8_t res = gray_lut[rgb_to_gray(q[0], q[1], q[2])];
                 q[0] = res; q[1] = res; q[2] = res;
                 if (CH == 4) q[3] = 0;  // `.{ .r, .g, .b }`: alpha takes its default 0 (color.zig:405, fdm.zig:196)
-                return 0u;
+                return;
             }
-            const float rf = (float)q[0], gf = (float)q[1], bfl = (float)q[2];
-            unsigned bad = 0;
-            uint8_t out[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float y = fmaf(bfl, wf[6 + j], fmaf(gf, wf[3 + j], fmaf(rf, wf[j], bf[j])));   // ~ 255*res + 1/2
-                const float m = fmaf(bfl, wa[6 + j], fmaf(gf, wa[3 + j], fmaf(rf, wa[j], ba[j])));   // sum of |terms| (+1)
-                const float fl = floorf(y);
-                const float d = y - fl;                       // distance above the boundary below
-                const float e = m * 9.6e-7f;                  // 16 * 2^-24 * m  >=  |y32 - y64| with 2x slack
-                bad |= (d > e && d < 1.0f - e) ? 0u : (1u << j);
-                out[j] = (uint8_t)fminf(fmaxf(fl, 0.0f), 255.0f);
+            const uint32_t word = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+            bool bad = false;
+            const uint32_t o = map_colour(byte_to_float(word, 0), byte_to_float(word, 1), byte_to_float(word, 2), m, bad);
+            if (bad) {   // exact f64 recomputation of the whole pixel (all three channels read the ORIGINAL r, g, b)
+                const int r = q[0], g = q[1], b = q[2];
+                q[0] = fdm_exact_channel(r, g, b, 0, pp);
+                q[1] = fdm_exact_channel(r, g, b, 1, pp);
+                q[2] = fdm_exact_channel(r, g, b, 2, pp);
+            } else {
+                q[0] = (uint8_t)o; q[1] = (uint8_t)(o >> 8); q[2] = (uint8_t)(o >> 16);
             }
-            if (bad) {   // rare: keep the source values, the caller recomputes those channels exactly
-                return bad | 8u;
-            }
-            q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
-            return 0u;
         }
     };
-    auto fix_px = [&](uint8_t* q) {   // exact f64 recomputation of a whole pixel (all three channels read the ORIGINAL r, g, b)
-        const int r = q[0], g = q[1], b = q[2];
-        q[0] = fdm_exact_channel(r, g, b, 0, pp);
-        q[1] = fdm_exact_channel(r, g, b, 1, pp);
-        q[2] = fdm_exact_channel(r, g, b, 2, pp);
-    };
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((uintptr_t)img & 15u) == 0) {
+        const size_t n16 = n_px / 16;
+        if (tid < n16) {
+            uint4* q4 = reinterpret_cast<uint4*>(img) + tid * CH;
+            uint32_t w[4 * CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const uint4 v = q4[i];
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+            if (CH != 1 && mode == 0) {
+                // colour map on packed words: pixel k's bytes sit at byte offset k * CH of the 16 * CH-byte run
+                unsigned redo = 0;
+                uint32_t res[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int o = k * CH;                               // byte offset of r
+                    const uint32_t lo = w[o >> 2], hi = w[((o + 3) >> 2) < 4 * CH ? ((o + 3) >> 2) : (4 * CH - 1)];
+                    const uint32_t word = __funnelshift_r(lo, hi, (o & 3) * 8);   // r, g, b (, a) in bytes 0..2 (3)
+                    bool bad = false;
+                    res[k] = map_colour(byte_to_float(word, 0), byte_to_float(word, 1), byte_to_float(word, 2), m, bad);
+                    if (bad) {
+                        redo |= 1u << k;
+                        res[k] = word;                                          // keep the source bytes for the exact pass
+                    } else if (CH == 4) {
+                        res[k] |= word & 0xFF000000u;                           // alpha is untouched (fdm.zig:268-270)
+                    }
+                }
+                if (redo) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (redo & (1u << k)) {
+                            const int r = res[k] & 0xFF, g = (res[k] >> 8) & 0xFF, b = (res[k] >> 16) & 0xFF;
+                            res[k] = (res[k] & 0xFF000000u) | (uint32_t)fdm_exact_channel(r, g, b, 0, pp) | ((uint32_t)fdm_exact_channel(r, g, b, 1, pp) << 8) |
+                                     ((uint32_t)fdm_exact_channel(r, g, b, 2, pp) << 16);
+                        }
+                }
+                if constexpr (CH == 4) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) w[k] = res[k];
+                } else {
+                    // 16 x 3 bytes -> 12 words: word i holds bytes [4i, 4i + 4) of the stream r0 g0 b0 r1 ...
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const int b0 = 4 * i;                                   // stream byte of the word's byte 0
+                        const int k0 = b0 / 3, off = b0 - 3 * k0;              // pixel and channel it starts in
+                        // bytes of pixel k0 from channel `off`, then pixel k0 + 1 (and k0 + 2 when off == 2 ... covered by 3 pixels)
+                        const uint32_t a = res[k0] >> (8 * off);                // (3 - off) valid bytes
+                        const uint32_t b = k0 + 1 < 16 ? res[k0 + 1] : 0u;      // 3 valid bytes
+                        const uint32_t c = k0 + 2 < 16 ? res[k0 + 2] : 0u;
+                        uint32_t v;
+                        if (off == 0) v = (a & 0x00FFFFFFu) | (b << 24);
+                        else if (off == 1) v = (a & 0x0000FFFFu) | ((b & 0x0000FFFFu) << 16);
+                        else v = (a & 0x000000FFu) | ((b & 0x00FFFFFFu) << 8);
+                        (void)c;
+                        w[i] = v;
+                    }
+                }
+            } else {
+                uint8_t* bytes = reinterpret_cast<uint8_t*>(w);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) map_px(bytes + k * CH);
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i) q4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        } else if (tid == n16) {   // the tail (< 16 pixels), byte by byte
+            for (size_t px = n16 * 16; px < n_px; ++px) map_px(img + px * CH);
+        }
+        return;
+    }
     const size_t n_groups = n_px / 4;
-    const size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp < n_groups) {
+    if (tid < n_groups) {
         uint8_t b[4 * CH];
-        load_group<CH>(img, grp, b);
-        unsigned redo = 0;
+        load_group<CH>(img, tid, b);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) redo |= (map_px(b + q * CH) ? 1u : 0u) << q;
-        if (redo) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (redo & (1u << q)) fix_px(b + q * CH);
-        }
-        store_group<CH>(img, grp, b);
-    } else if (grp == n_groups) {   // the tail (< 4 pixels), byte by byte
-        for (size_t px = n_groups * 4; px < n_px; ++px)
-            if (map_px(img + px * CH)) fix_px(img + px * CH);
+        for (int q = 0; q < 4; ++q) map_px(b + q * CH);
+        store_group<CH>(img, tid, b);
+    } else if (tid == n_groups) {   // the tail (< 4 pixels), byte by byte
+        for (size_t px = n_groups * 4; px < n_px; ++px) map_px(img + px * CH);
     }
 }
 
@@ -416,12 +507,22 @@ ZB_HD inline int fdm_solve(const unsigned long long* m, const FdmTarget& t, int 
     return ZB_OK;
 }
 
+// the f32 constants of the map's fast path (see map_colour)
+ZB_HD inline void finish_map_params(MapParams& p) {
+    for (int i = 0; i < 9; ++i) { p.wf[i] = (float)p.w[i]; p.wa[i] = 0.0f; }
+    for (int j = 0; j < 3; ++j) {
+        p.bf[j] = (float)(255.0 * p.bias[j]);
+        const double M = 255.0 * (fabs(p.w[j]) + fabs(p.w[3 + j]) + fabs(p.w[6 + j])) + fabs(255.0 * p.bias[j]);
+        const double safe = 0.5 - 8.0 * 5.9604644775390625e-08 * M - 1e-6;   // 8 * 2^-24 * M, and x must stay below 2^22 for the rounding trick
+        p.ba[j] = (safe > 0.0 && M < 4.0e6) ? (float)safe : -1.0f;           // -1: every pixel takes the exact path
+    }
+}
+
 __global__ void fdm_solve_kernel(const unsigned long long* __restrict__ m, FdmTarget t, int pixfmt, MapParams* __restrict__ out,
                                  int* __restrict__ status) {
     MapParams p;
     const int rc = fdm_solve(m, t, pixfmt, p);
-    for (int i = 0; i < 9; ++i) { p.wf[i] = (float)p.w[i]; p.wa[i] = fabsf(p.wf[i]); }
-    for (int j = 0; j < 3; ++j) { p.bf[j] = (float)(255.0 * p.bias[j]) + 0.5f; p.ba[j] = fabsf(p.bf[j]) + 1.0f; }
+    finish_map_params(p);
     *out = p;
     *status = rc;
 }
@@ -460,11 +561,16 @@ __device__ void moments_tail(unsigned long long* sums, const SolveTail& tail) {
         *tail.ticket = 0;
         MapParams p;
         const int rc = fdm_solve(m, tail.target, tail.pixfmt, p);
-        for (int i = 0; i < 9; ++i) { p.wf[i] = (float)p.w[i]; p.wa[i] = fabsf(p.wf[i]); }
-        for (int j = 0; j < 3; ++j) { p.bf[j] = (float)(255.0 * p.bias[j]) + 0.5f; p.ba[j] = fabsf(p.bf[j]) + 1.0f; }
+        finish_map_params(p);
         *tail.out = p;
         *tail.status = rc;
     }
+}
+
+// the target's 3x3 decomposition on the host: the same fixed-size routine the device solve uses
+static uint64_t svd3_host(const double* cov, double* u, double* q, double* v) {
+    double e[3] = {0, 0, 0};
+    return svd_gr_core<double>(cov, 3, 3, ZB_SVD_SKINNY_U, false, u, 3, q, v, e);
 }
 
 // fdm.zig:92-121
@@ -478,7 +584,7 @@ int set_target_from_moments(zb_fdm* f, const uint64_t* m) {
         f->target_s[0] = cov[0];
     } else {
         double v[9];
-        if (svd_golub_reinsch<double>(cov, 3, 3, ZB_SVD_SKINNY_U, false, f->target_u, 3, f->target_s, v) != 0) return ZB_ERR_NOT_CONVERGED;
+        if (svd3_host(cov, f->target_u, f->target_s, v) != 0) return ZB_ERR_NOT_CONVERGED;
     }
     f->has_target = true;
     return ZB_OK;
@@ -544,7 +650,8 @@ int map_enqueue(zb_fdm* f, cudaStream_t s) {
     if (n_px == 0) return ZB_OK;
     MapParams* dp = (MapParams*)f->d_params;
     uint8_t* img = (uint8_t*)f->source.data;
-    const unsigned blocks = div_up(n_px / 4 + 1, 256);   // one thread per 4-pixel group, one more for the tail
+    // one thread per 16-pixel run (16-byte aligned images) or 4-pixel group, one more for the tail
+    const unsigned blocks = (((uintptr_t)img) & 15u) == 0 ? div_up(n_px / 16 + 1, 256) : div_up(n_px / 4 + 1, 256);
     switch (channels_of(f->pixfmt)) {
         case 1: fdm_map_kernel<1><<<blocks, 256, 0, s>>>(img, n_px, dp); break;
         case 3: fdm_map_kernel<3><<<blocks, 256, 0, s>>>(img, n_px, dp); break;

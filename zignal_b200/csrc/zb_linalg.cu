@@ -18,7 +18,6 @@
 
 #include "zb_internal.h"
 #include "zb_linalg.h"
-#include "zb_svd_core.h"
 
 namespace zb {
 
@@ -202,35 +201,6 @@ int center_columns(const T* x, uint32_t n, uint32_t dim, T* mean, int compute_me
 
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------
-// Golub-Reinsch SVD, host entry (body: zb_svd_core.h).  u: m x ucols row-major; q: n singular values; v: n x n.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-uint64_t svd_golub_reinsch(const T* a, uint32_t m, uint32_t n, int mode, bool with_v, T* u, uint32_t ucols, T* q, T* v) {
-    std::vector<T> e(n, (T)0);
-    return svd_gr_core<T>(a, m, n, mode, with_v, u, ucols, q, v, e.data());
-}
-
-template uint64_t svd_golub_reinsch<float>(const float*, uint32_t, uint32_t, int, bool, float*, uint32_t, float*, float*);
-template uint64_t svd_golub_reinsch<double>(const double*, uint32_t, uint32_t, int, bool, double*, uint32_t, double*, double*);
-
-template <typename T>
-static int svd_entry(const T* a, uint32_t m, uint32_t n, int mode, int with_v, T* u, T* s, T* v, uint64_t* converged) {
-    if (!a || !s) return ZB_ERR_INVALID_ARGUMENT;
-    if (m < n) return ZB_ERR_DIMENSION_MISMATCH;  // svd.zig:86
-    if (mode < ZB_SVD_NO_U || mode > ZB_SVD_FULL_U) return ZB_ERR_INVALID_ARGUMENT;
-    if (mode != ZB_SVD_NO_U && !u) return ZB_ERR_INVALID_ARGUMENT;
-    if (with_v && !v) return ZB_ERR_INVALID_ARGUMENT;
-    const uint32_t ucols = mode == ZB_SVD_FULL_U ? m : n;
-    std::vector<T> ubuf((size_t)m * ucols, (T)0), vbuf(with_v ? (size_t)n * n : 1, (T)0);
-    for (uint32_t i = 0; i < n; ++i) s[i] = 0;
-    const uint64_t failed = svd_golub_reinsch<T>(a, m, n, mode, with_v != 0, ubuf.data(), ucols, s, vbuf.data());
-    if (mode != ZB_SVD_NO_U) std::copy(ubuf.begin(), ubuf.end(), u);
-    if (with_v) std::copy(vbuf.begin(), vbuf.end(), v);
-    if (converged) *converged = failed;
-    return ZB_OK;
-}
-
 }  // namespace zb
 
 using namespace zb;
@@ -250,12 +220,6 @@ int zb_center_columns_f32(const float* x, uint32_t n, uint32_t dim, float* mean,
 }
 int zb_center_columns_f64(const double* x, uint32_t n, uint32_t dim, double* mean, int compute_mean, double* centered, zb_stream s) {
     return center_columns<double>(x, n, dim, mean, compute_mean, centered, (cudaStream_t)s);
-}
-int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged) {
-    return svd_entry<double>(a, m, n, mode, with_v, u, s, v, converged);
-}
-int zb_svd_f32(const float* a, uint32_t m, uint32_t n, int mode, int with_v, float* u, float* s, float* v, uint64_t* converged) {
-    return svd_entry<float>(a, m, n, mode, with_v, u, s, v, converged);
 }
 
 }  // extern "C"

@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <list>
+#include <mutex>
 #include <vector>
 
 #include "zb_host_stage.h"
@@ -434,6 +436,89 @@ int launch_generic(const zb_image* src, zb_image* dst, int method, float mb, flo
     });
 }
 
+// Everything the plane resizers derive from (src shape, dst shape, method), cached per device.
+struct ResizePlan {
+    uint32_t src_rows, src_cols, dst_rows, dst_cols;
+    int method, device;
+    std::vector<TapEntry> xt, yt;
+    TapEntry* dxt = nullptr;   // device copies (one allocation; lives as long as the cache entry)
+    TapEntry* dyt = nullptr;
+    bool uniform_ok = false;   // every row / column has the same cubic weights and the products fit the integer fast path
+    bool cols_4to1 = false;    // idx(c) = 4c + o for every column
+    UniformCubic u;
+};
+
+int resize_plan(uint32_t src_rows, uint32_t src_cols, uint32_t dst_rows, uint32_t dst_cols, int method, const ResizePlan** out) {
+    static std::mutex mu;
+    static std::list<ResizePlan> cache;   // most recently used first; list nodes stay put, so returned pointers remain valid
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto it = cache.begin(); it != cache.end(); ++it)
+        if (it->device == dev && it->method == method && it->src_rows == src_rows && it->src_cols == src_cols && it->dst_rows == dst_rows &&
+            it->dst_cols == dst_cols) {
+            cache.splice(cache.begin(), cache, it);
+            *out = &cache.front();
+            return ZB_OK;
+        }
+    ResizePlan pl;
+    pl.src_rows = src_rows; pl.src_cols = src_cols; pl.dst_rows = dst_rows; pl.dst_cols = dst_cols;
+    pl.method = method; pl.device = dev;
+    build_table(pl.xt, src_cols, dst_cols, method);
+    build_table(pl.yt, src_rows, dst_rows, method);
+    const std::vector<TapEntry>&xt = pl.xt, &yt = pl.yt;
+    memset(&pl.u, 0, sizeof(pl.u));
+    if (method == ZB_INTERP_BICUBIC || method == ZB_INTERP_CATMULL_ROM || method == ZB_INTERP_MITCHELL) {
+        bool uniform = true;
+        for (size_t c = 1; c < xt.size() && uniform; ++c) uniform = memcmp(xt[c].w, xt[0].w, 4 * sizeof(int)) == 0;
+        for (size_t r = 1; r < yt.size() && uniform; ++r) uniform = memcmp(yt[r].w, yt[0].w, 4 * sizeof(int)) == 0;
+        UniformCubic& u = pl.u;
+        u.weight_sum = 0;
+        for (int ky = 0; ky < 4; ++ky)
+            for (int kx = 0; kx < 4; ++kx) {
+                u.w[ky * 4 + kx] = (xt[0].w[kx] * yt[0].w[ky]) / 256;   // @divTrunc(wx * wy, SCALE), channel_ops.zig:262
+                u.weight_sum += u.w[ky * 4 + kx];
+            }
+        long long abs_sum = 0;
+        for (int i = 0; i < 16; ++i) abs_sum += std::llabs((long long)u.w[i]);
+        if (uniform && u.weight_sum > 0 && 255 * abs_sum < (1 << 24)) {
+            pl.uniform_ok = true;
+            u.rcp = 1.0f / (float)u.weight_sum;
+            u.dp4a_ok = 1;
+            for (int i = 0; i < 16; ++i) u.dp4a_ok &= (u.w[i] >= -128 && u.w[i] <= 127) ? 1 : 0;
+            for (int ky = 0; ky < 4; ++ky) {
+                uint32_t pk = 0;
+                for (int kx = 0; kx < 4; ++kx) pk |= ((uint32_t)(u.w[ky * 4 + kx] & 0xFF)) << (8 * kx);
+                u.packed[ky] = (int)pk;
+            }
+            bool r4 = true;
+            const int o = xt[0].idx[0];
+            for (size_t c = 0; c < xt.size() && r4; ++c)
+                for (int k = 0; k < 4; ++k) r4 = r4 && xt[c].idx[k] == (int)(4 * c) + o + k;
+            pl.cols_4to1 = r4;
+        }
+    }
+    // one device allocation for both tables; a blocking upload once per plan (any stream may use the plan afterwards)
+    const size_t nx = xt.size(), ny = yt.size();
+    TapEntry* d = nullptr;
+    ZB_CUDA(cudaMalloc(&d, (nx + ny) * sizeof(TapEntry)));
+    if (cudaMemcpy(d, xt.data(), nx * sizeof(TapEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d + nx, yt.data(), ny * sizeof(TapEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return set_cuda_error(cudaGetLastError(), "tap table upload", __FILE__, __LINE__);
+    }
+    pl.dxt = d;
+    pl.dyt = d + nx;
+    if (cache.size() >= 32) {   // evict the least recently used plan; its table may still be read by queued kernels
+        cudaDeviceSynchronize();
+        cudaFree(cache.back().dxt);
+        cache.pop_back();
+    }
+    cache.push_front(std::move(pl));
+    *out = &cache.front();
+    return ZB_OK;
+}
+
 }  // namespace
 
 int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, float mb, float mc, cudaStream_t s) {
@@ -450,37 +535,16 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
         return ZB_OK;
     }
     if (pixfmt == ZB_PIX_RGB8 || pixfmt == ZB_PIX_RGBA8) {  // meta.isRgb(T), :111
-        std::vector<TapEntry> xt, yt;
-        build_table(xt, src->cols, dst->cols, method);
-        build_table(yt, src->rows, dst->rows, method);
-        Scratch tab;
-        if ((rc = tab.alloc((xt.size() + yt.size()) * sizeof(TapEntry), s))) return rc;
-        TapEntry* dxt = tab.as<TapEntry>();
-        TapEntry* dyt = dxt + xt.size();
-        ZB_CUDA(cudaMemcpyAsync(dxt, xt.data(), xt.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, s));
-        ZB_CUDA(cudaMemcpyAsync(dyt, yt.data(), yt.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, s));
+        // tap tables and everything derived from them depend only on (src shape, dst shape, method): built once per device,
+        // kept in device memory (the per-call rebuild + two pageable uploads cost more than the 4:1 kernel itself)
+        const ResizePlan* plan = nullptr;
+        if ((rc = resize_plan(src->rows, src->cols, dst->rows, dst->cols, method, &plan))) return rc;
+        const std::vector<TapEntry>& xt = plan->xt;
+        const TapEntry* dxt = plan->dxt;
+        const TapEntry* dyt = plan->dyt;
         if (method == ZB_INTERP_BICUBIC || method == ZB_INTERP_CATMULL_ROM || method == ZB_INTERP_MITCHELL) {
-            bool uniform = true;
-            for (size_t c = 1; c < xt.size() && uniform; ++c) uniform = memcmp(xt[c].w, xt[0].w, 4 * sizeof(int)) == 0;
-            for (size_t r = 1; r < yt.size() && uniform; ++r) uniform = memcmp(yt[r].w, yt[0].w, 4 * sizeof(int)) == 0;
-            UniformCubic u;
-            u.weight_sum = 0;
-            for (int ky = 0; ky < 4; ++ky)
-                for (int kx = 0; kx < 4; ++kx) {
-                    u.w[ky * 4 + kx] = (xt[0].w[kx] * yt[0].w[ky]) / 256;   // @divTrunc(wx * wy, SCALE), channel_ops.zig:262
-                    u.weight_sum += u.w[ky * 4 + kx];
-                }
-            long long abs_sum = 0;
-            for (int i = 0; i < 16; ++i) abs_sum += std::llabs((long long)u.w[i]);
-            if (uniform && u.weight_sum > 0 && 255 * abs_sum < (1 << 24)) {
-                u.rcp = 1.0f / (float)u.weight_sum;
-                u.dp4a_ok = 1;
-                for (int i = 0; i < 16; ++i) u.dp4a_ok &= (u.w[i] >= -128 && u.w[i] <= 127) ? 1 : 0;
-                for (int ky = 0; ky < 4; ++ky) {
-                    uint32_t pk = 0;
-                    for (int kx = 0; kx < 4; ++kx) pk |= ((uint32_t)(u.w[ky * 4 + kx] & 0xFF)) << (8 * kx);
-                    u.packed[ky] = (int)pk;
-                }
+            const UniformCubic& u = plan->u;
+            if (plan->uniform_ok) {
                 dim3 grid(div_up(dst->cols, 256), dst->rows);
                 const int ch = pixfmt == ZB_PIX_RGB8 ? 3 : 4;
                 const size_t sb = (size_t)src->stride * ch, db = (size_t)dst->stride * ch;
@@ -489,9 +553,7 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
                 const size_t valid_b = (size_t)src->cols * ch;
                 bool r4 = u.dp4a_ok && ((uintptr_t)src->data & 15u) == 0 && sb % 16 == 0 && valid_b % 16 == 0;
                 const int o = xt[0].idx[0];
-                r4 = r4 && o >= 0 && ((size_t)o * ch) % 16 == 0;
-                for (size_t c = 0; c < xt.size() && r4; ++c)
-                    for (int k = 0; k < 4; ++k) r4 = r4 && xt[c].idx[k] == (int)(4 * c) + o + k;
+                r4 = r4 && plan->cols_4to1 && o >= 0 && ((size_t)o * ch) % 16 == 0;
                 if (r4) {
                     dim3 g4(div_up(dst->cols, ch == 3 ? 1024 : 512), dst->rows);
                     if (ch == 3)

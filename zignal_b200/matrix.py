@@ -1,6 +1,7 @@
 """Host-side mirror of zignal's Matrix(T) operations on the hot path: `gemm` (reference
-src/matrix/Matrix.zig:696-822) runs on the device through the C ABI, `svd` (Matrix.zig:1570,
-svd.zig:80-496) on the host (it is sequential and small on this path)."""
+src/matrix/Matrix.zig:696-822) runs on the device through the C ABI; `svd` (Matrix.zig:1570, svd.zig:80-496) and `eigh`
+(matrix/eigen.zig:34) are parallel-ordering Jacobi methods (csrc/zb_jacobi.cu: a persistent cooperative kernel for 24 columns
+and more, the same algorithm on the host below that)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -8,6 +9,11 @@ import ctypes as C
 import numpy as np
 
 from ._ffi import ZignalError, check, lib
+
+
+def _torch():
+    import torch
+    return torch
 
 
 def _ptr(t, ctype):
@@ -83,8 +89,28 @@ def svd(a: np.ndarray, mode: str = "full_u", with_v: bool = False):
     return u, s, v, conv.value
 
 
+def svd_device(a, with_u: bool = True, with_v: bool = False):
+    """The same decomposition for a CUDA tensor (m x n, m >= n, f32 / f64) that stays on the device (zb_svd_dev_*):
+    -> (u: m x n or None, s: n descending, v: n x n or None, converged) as CUDA tensors."""
+    torch = _torch()
+    assert a.is_cuda and a.is_contiguous() and a.dim() == 2
+    m, n = a.shape
+    if m < n:
+        raise ZignalError(1, "DimensionMismatch")
+    u = torch.empty((m, n), dtype=a.dtype, device=a.device) if with_u else None
+    s = torch.empty(n, dtype=a.dtype, device=a.device)
+    v = torch.empty((n, n), dtype=a.dtype, device=a.device) if with_v else None
+    conv = C.c_uint64(0)
+    ct = C.c_double if a.dtype == torch.float64 else C.c_float
+    fn = lib().zb_svd_dev_f64 if a.dtype == torch.float64 else lib().zb_svd_dev_f32
+    with torch.cuda.device(a.device):
+        check(fn(_ptr(a, ct), m, n, _ptr(u, ct) if u is not None else None, _ptr(s, ct), _ptr(v, ct) if v is not None else None,
+                 C.byref(conv), torch.cuda.current_stream(a.device).cuda_stream))
+    return u, s, v, conv.value
+
+
 def eigh(a: np.ndarray):
-    """Matrix.eigh(allocator) (matrix/eigen.zig:34-136) -> (values ascending, vectors with eigenvectors as columns).  Host routine."""
+    """Matrix.eigh(allocator) (matrix/eigen.zig:34-136) -> (values ascending, vectors with eigenvectors as columns)."""
     a = np.ascontiguousarray(a)
     if a.ndim != 2:
         raise ZignalError(18, "NotSquare")

@@ -1,6 +1,7 @@
 """Host-side mirror of zignal's Pca(T) (reference src/pca.zig:54-427).  The dense step -- the scaled
 covariance X^T X / (n-1) (or Gram X X^T / (n-1)) and the batch projection -- runs on the GPU through
-zb_gemm; the small SVD of the dim x dim (or n x n) matrix runs on the host through zb_svd."""
+zb_gemm, and the SVD of the dim x dim (or n x n) matrix follows on the device (zb_svd_dev: one-sided Jacobi in a persistent
+cooperative kernel) -- the covariance never leaves the GPU."""
 from __future__ import annotations
 
 import numpy as np
@@ -36,10 +37,11 @@ class Pca:
         scale = 1.0 / float(n - 1)
         self.mean = mean.cpu().numpy()
         if n <= dim:  # Gram path, pca.zig:380-425
-            g = matrix.gemm_device(centered, centered, False, True, scale, 0.0, None).cpu().numpy()
-            u, s, _, conv = matrix.svd(g, "skinny_u", False)
+            g = matrix.gemm_device(centered, centered, False, True, scale, 0.0, None)
+            ud, sd, _, conv = matrix.svd_device(g, True, False)
             if conv != 0:
                 raise ZignalError(4, "SvdFailed")
+            u, s = ud.cpu().numpy(), sd.cpu().numpy()
             comps = np.zeros((dim, k), self.dtype)
             cen = centered.cpu().numpy()
             for i in range(k):
@@ -47,11 +49,11 @@ class Pca:
                     comps[:, i] = (cen.T @ u[:, i]) / np.sqrt(s[i] * self.dtype.type(n - 1))
             self.components, self.eigenvalues = comps, s[:k].copy()
         else:  # covariance path, pca.zig:331-362
-            cov = matrix.gemm_device(centered, centered, True, False, scale, 0.0, None).cpu().numpy()
-            u, s, _, conv = matrix.svd(cov, "skinny_u", False)
+            cov = matrix.gemm_device(centered, centered, True, False, scale, 0.0, None)
+            ud, sd, _, conv = matrix.svd_device(cov, True, False)
             if conv != 0:
                 raise ZignalError(4, "SvdFailed")
-            self.components, self.eigenvalues = np.ascontiguousarray(u[:, :k]), s[:k].copy()
+            self.components, self.eigenvalues = np.ascontiguousarray(ud[:, :k].cpu().numpy()), sd[:k].cpu().numpy().copy()
         self.num_components = k
 
     def transform(self, data: np.ndarray) -> np.ndarray:  # pca.zig:291-312

@@ -6,9 +6,9 @@ Workload (BASELINE.json configs[1]): 15x15 separable Gaussian blur (sigma = 2.25
 
   N = 1   one zb_gaussian_blur-equivalent call on the device-resident image.
   N > 1   one process per GPU, everything through the C ABI's zb_shard_* entry points: the image is a stack of row blocks, one
-          per rank, and a step is ONE kernel launch per rank -- the fused convolution kernel TMA-loads the 7 edge rows of its row
-          neighbours straight from their memory over NVLink (CUDA IPC mappings) and synchronises with them through flags; there is
-          no separate exchange.  Two partitionings are timed in the same run:
+          per rank, and a step is ONE kernel launch per rank -- the fused convolution kernel copies the 7 edge rows of its row
+          neighbours from their memory over NVLink (CUDA IPC mappings) in its own prologue and synchronises with them through
+          flags; there is no separate exchange.  Two partitionings are timed in the same run:
             weak   (the headline `value`, "scaling": "weak"): 8192 rows per GPU, the image is (N*8192) x 8192;
             strong (`extra.strong`): THE 8192 x 8192 image split into 8192/N rows per GPU.
           After the timed region every rank checks its block of the result against a single-GPU blur of (its block + the true
@@ -241,7 +241,7 @@ def main():
     assert taps.size == 15
 
     def make_blocks(rows):
-        src, dst = comm.image(rows, COLS, zb.PixFmt.RGBAF32, 0), comm.image(rows, COLS, zb.PixFmt.RGBAF32, 0)
+        src, dst = comm.image(rows, COLS, zb.PixFmt.RGBAF32, 8), comm.image(rows, COLS, zb.PixFmt.RGBAF32, 8)   # 8 halo rows: the kernel's landing zone for the neighbours' 7
         gen = torch.Generator(device=dev).manual_seed(2 + rank)
         src.interior_tensor().copy_(torch.rand(rows, COLS, 4, device=dev, dtype=torch.float32, generator=gen))
         return src, dst
@@ -458,7 +458,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "image": [ROWS * world, COLS] if (world == 1 or args.scaling == "weak") else [ROWS, COLS],
                        "pixel": "RGBA f32 interleaved (16 B)", "taps": 15, "border": "mirror",
-                       "parallelism": f"row-block x{world}" + (" (zb_shard_conv_separable: neighbours' 7 edge rows TMA-loaded over NVLink inside the kernel, "
+                       "parallelism": f"row-block x{world}" + (" (zb_shard_conv_separable: neighbours' 7 edge rows fetched over NVLink inside the kernel, "
                                                                 f"peer_access={comm.peer_access})" if world > 1 else ""),
                        "l2": "input 1 GiB per GPU >> 126 MB L2 (no flush needed)", "kernel": kernel_name},
             "e2e": e2e, "gpu_launches": int(launches),

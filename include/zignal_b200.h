@@ -307,9 +307,10 @@ int zb_fdm_status(zb_fdm* f, zb_stream s);
  * any other neighbourhood filter, fdm.update (fdm.zig:141-273) and batches of rotate / resize.
  *
  * Plumbing: NCCL (dlopen'ed at run time) bootstraps the communicator and exchanges CUDA IPC handles; the data
- * path is NVLink peer memory.  The RGBA f32 convolution kernel TMA-loads the `half` edge rows of the row
- * neighbours straight from their memory -- one launch per step, no separate exchange -- and carries the whole
- * synchronisation in a pair of flags per neighbour; every other filter uses zb_shard_halo_exchange (one pull
+ * path is NVLink peer memory.  The RGBA f32 convolution kernel copies the `half` edge rows of the row
+ * neighbours from their memory into its own halo rows in a prologue -- one launch per step, no separate exchange
+ * -- and carries the whole synchronisation in a pair of flags per neighbour (blocks need halo_cap >= 8 for this
+ * kernel); every other filter uses zb_shard_halo_exchange (one pull
  * kernel over NVLink; NCCL send/recv when IPC mappings are unavailable) followed by its ordinary entry point
  * on the extended block.  All ranks must issue the same sequence of zb_shard_* calls (SPMD).
  * ---------------------------------------------------------------------------------------------- */

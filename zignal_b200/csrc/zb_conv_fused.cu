@@ -62,16 +62,22 @@ struct FusedParams {
     int fix_rows;    // 1 if out-of-range rows need patching (border != zero)
     int fix_left;    // 1 if x < 0 needs patching
     int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
+    int tma_row_off; // row of the tensor map that holds image row 0 (sharded blocks: the map starts at the first halo row)
 };
 
-// Sharded launch (zb_shard_conv_separable): this rank holds one row block of a taller image.  The 8-row chunks that lie
-// above row 0 / below the last row are not border pixels but the neighbours' edge rows: the producer fetches them with
-// TMA straight from the neighbours' memory (IPC mappings, NVLink) through tensor maps of THEIR blocks.
+// Sharded launch (zb_shard_conv_separable): this rank holds one row block of a taller image, stored with `halo_cap` (>= CHUNK)
+// spare rows above and below it.  The rows beyond the block are not border pixels but the neighbours' edge rows.  The kernel
+// fetches them itself: in a prologue every CTA copies a slice of the 2 x half neighbour rows from the neighbours' memory (IPC
+// mappings over NVLink; plain 128-bit loads, many in flight per thread) into the block's own halo rows, after which the ordinary
+// TMA pipeline reads them like any other row.  (A TMA load straight from peer memory was measured first: 34 KB per chunk arrived in
+// ~45 us -- the TMA unit keeps too few requests in flight for NVLink's latency -- which cost the whole step 47 us.)  The bands next
+// to a neighbour are processed LAST, so nothing ever waits for the copy; the kernel also carries the whole synchronisation
+// (ready / done flags, zb_shard.h).
 struct ShardParams {
-    const float4* up_src;      // row 0 of the upper neighbour's block (null: global top edge, border mode applies)
-    const float4* down_src;    // row 0 of the lower neighbour's block (null: global bottom edge)
+    const float4* up_rows;     // the upper neighbour's last `half` rows (null: global top edge, border mode applies)
+    const float4* down_rows;   // the lower neighbour's first `half` rows (null: global bottom edge)
     unsigned long long up_pitch_px, down_pitch_px;
-    int up_rows;
+    int half;
     ShardLink link;
 };
 
@@ -111,12 +117,10 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const int rr = idx / per_row, e = idx - rr * per_row;
             const int xx = e < nleft ? e : r0 + (e - nleft);
             const int y = y0 + rr, x = xs0 + xx;
-            const float4* rowp = p.src + (size_t)y * p.src_pitch_px;
+            const float4* rowp = p.src + (long long)y * (long long)p.src_pitch_px;
             if (y < 0 || y >= p.rows) {
-                if constexpr (SHARD) {   // a neighbour's row (its pixels arrived by TMA like any other row's)
-                    if (y < 0 && sp->up_src) rowp = sp->up_src + (size_t)(sp->up_rows + y) * sp->up_pitch_px;
-                    else if (y >= p.rows && sp->down_src) rowp = sp->down_src + (size_t)(y - p.rows) * sp->down_pitch_px;
-                    else continue;
+                if constexpr (SHARD) {   // a neighbour's row: it sits in this block's halo rows (the prologue copied it)
+                    if (!((y < 0 && sp->up_rows) || (y >= p.rows && sp->down_rows))) continue;
                 } else {
                     continue;                                                   // handled by the row pass below
                 }
@@ -138,7 +142,7 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const int y = y0 + rr, x = xs0 + xx;
             if (y >= 0 && y < p.rows) continue;
             if constexpr (SHARD) {
-                if ((y < 0 && sp->up_src) || (y >= p.rows && sp->down_src)) continue;   // neighbour rows: not border pixels
+                if ((y < 0 && sp->up_rows) || (y >= p.rows && sp->down_rows)) continue;   // neighbour rows: not border pixels
             }
             const int ry = resolve_index(y, p.rows, p.border);
             const int rx = resolve_index(x, p.cols, p.border);
@@ -198,8 +202,7 @@ __device__ __forceinline__ void v_pass(uint32_t v_col, const FusedParams& p, flo
 
 // F2: use the packed fma.rn.f32x2 (FFMA2) -- two lanes per issued instruction, same IEEE result as FFMA.
 template <int HALF, bool EXACT, int STAGES, bool F2, bool SHARD>
-__device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, const CUtensorMap* tmap_up, const CUtensorMap* tmap_down,
-                                                       const FusedParams& p, const ShardParams* sp) {
+__device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, const FusedParams& p, const ShardParams* sp) {
     static_assert(!(EXACT && F2), "exact mode is scalar");
     constexpr int K = 2 * HALF + 1;
     constexpr int NLOAD = CHUNK + 2 * HALF;
@@ -216,30 +219,24 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
     uint32_t pcount = 0;
     auto produce = [&]() {
         if (pu >= n_units) return;
-        const int band = pu / p.n_strips, strip = pu - band * p.n_strips;
+        int band = pu / p.n_strips;
+        const int strip = pu - band * p.n_strips;
+        if constexpr (SHARD) band = band + 1 == p.n_bands ? 0 : band + 1;   // the band that reads the upper halo goes last
         const int ra = p.row0 + band * p.band_rows;
         const int rb = min(ra + p.band_rows, p.row1);
         const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
         const uint32_t st = pcount % STAGES;
-        const CUtensorMap* tm = &tmap;
-        int y = ra - CHUNK + CHUNK * pi;
+        const int y = ra - CHUNK + CHUNK * pi;
         if constexpr (SHARD) {
-            // chunks never straddle the block (rows, band_rows and row0 are multiples of CHUNK): a chunk is the neighbour's or mine
-            if (y < 0 && sp->up_src) {
-                shard_wait_ge(&sp->link.self->ready_from[0], sp->link.epoch, sp->link.self);
+            // a chunk that touches the halo rows needs the prologue copies of ALL CTAs (normally long finished by now)
+            if ((y < 0 && sp->up_rows) || (y + CHUNK > p.rows && sp->down_rows)) {
+                shard_wait_ge(&sp->link.self->halo_landed, sp->link.epoch, sp->link.self);
                 asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above orders the async-proxy read below
-                tm = tmap_up;
-                y += sp->up_rows;
-            } else if (y >= p.rows && sp->down_src) {
-                shard_wait_ge(&sp->link.self->ready_from[1], sp->link.epoch, sp->link.self);
-                asm volatile("fence.proxy.async;" ::: "memory");
-                tm = tmap_down;
-                y -= p.rows;
             }
         }
         fence_proxy_async();
         mbar_arrive_expect_tx(bar0 + 8 * st, STAGE_BYTES);
-        tma_load_3d(smem0 + st * STAGE_BYTES, tm, 0, strip * (TW / 8) - 1, y, bar0 + 8 * st);
+        tma_load_3d(smem0 + st * STAGE_BYTES, &tmap, 0, strip * (TW / 8) - 1, y + p.tma_row_off, bar0 + 8 * st);
         ++pcount;
         if (++pi == n_in) { pi = 0; pu += gridDim.x; }
     };
@@ -249,16 +246,63 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
         for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
         fence_barrier_init();
         if constexpr (SHARD) {
-            // this kernel is stream-ordered after whatever produced my source block: tell the neighbours it is complete
+            // this kernel is stream-ordered after whatever produced my source block: tell the neighbours it is complete,
+            // then wait until theirs are
             if (blockIdx.x == 0) {
                 if (sp->link.up) st_release_sys(&sp->link.up->ready_from[1], sp->link.epoch);
                 if (sp->link.down) st_release_sys(&sp->link.down->ready_from[0], sp->link.epoch);
             }
+            if (sp->up_rows) shard_wait_ge(&sp->link.self->ready_from[0], sp->link.epoch, sp->link.self);
+            if (sp->down_rows) shard_wait_ge(&sp->link.self->ready_from[1], sp->link.epoch, sp->link.self);
         }
     }
     __syncthreads();
     if (tid == 0)
-        for (int i = 0; i < STAGES; ++i) produce();
+        for (int i = 0; i < STAGES; ++i) produce();   // the first bands do not touch the halo: the pipeline fills while the copy runs
+    if constexpr (SHARD) {
+        // ---- prologue: this CTA's slice of the neighbours' edge rows -> my halo rows (plain loads over NVLink, all issued before
+        // the first use so the round trips overlap) ----
+        const int per_side = sp->half * p.cols;                      // pixels
+        const int total = (sp->up_rows ? per_side : 0) + (sp->down_rows ? per_side : 0);
+        constexpr int BATCH = 4;
+        for (int base = blockIdx.x * NTHREADS * BATCH; base < total; base += gridDim.x * NTHREADS * BATCH) {
+            float4 v[BATCH];
+            float4* dstp[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                int e = base + k * NTHREADS + tid;
+                dstp[k] = nullptr;
+                if (e < total) {
+                    const bool upper = sp->up_rows && e < per_side;
+                    if (!upper && sp->up_rows) e -= per_side;
+                    const int r = e / p.cols, x = e - r * p.cols;
+                    if (upper) {
+                        v[k] = *(sp->up_rows + (size_t)r * sp->up_pitch_px + x);
+                        dstp[k] = const_cast<float4*>(p.src) + (long long)(r - sp->half) * (long long)p.src_pitch_px + x;
+                    } else {
+                        v[k] = *(sp->down_rows + (size_t)r * sp->down_pitch_px + x);
+                        dstp[k] = const_cast<float4*>(p.src) + (long long)(p.rows + r) * (long long)p.src_pitch_px + x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (dstp[k]) *dstp[k] = v[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ShardCtrl* me = sp->link.self;
+            __threadfence();
+            if (atomicAdd(&me->halo_reads[0], 1u) == gridDim.x - 1u) {   // every CTA's slice has landed
+                me->halo_reads[0] = 0;
+                __threadfence();
+                st_release_sys(&me->halo_landed, sp->link.epoch);
+                // the neighbours' rows have been read: they may overwrite their source again
+                if (sp->up_rows) st_release_sys(&sp->link.up->done_from[1], sp->link.epoch);
+                if (sp->down_rows) st_release_sys(&sp->link.down->done_from[0], sp->link.epoch);
+            }
+        }
+    }
 
     // H-pass role: lane -> pixel group (8 consecutive pixels), warp -> row of the chunk
     const int ht = tid & 31, hr = tid >> 5;
@@ -271,7 +315,9 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
     uint32_t ccount = 0;  // chunks consumed by this CTA
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
+        int band = unit / p.n_strips;
+        const int strip = unit - band * p.n_strips;
+        if constexpr (SHARD) band = band + 1 == p.n_bands ? 0 : band + 1;
         const int x0 = strip * TW;
         const int ra = p.row0 + band * p.band_rows;
         const int rb = min(ra + p.band_rows, p.row1);
@@ -285,10 +331,8 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             while (!mbar_try_wait(bar0 + 8 * st, (ccount / STAGES) & 1u)) {}
             const int y0 = ra - CHUNK + CHUNK * i;
             bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
-            int peer_side = -1;   // this chunk came from the up (0) / down (1) neighbour
-            if constexpr (SHARD) {
-                if (y0 < 0 && sp->up_src) { peer_side = 0; fix_r = false; }
-                else if (y0 >= p.rows && sp->down_src) { peer_side = 1; fix_r = false; }
+            if constexpr (SHARD) {   // rows beyond the block on a neighbour side are real rows (already in the halo), not border pixels
+                if ((y0 < 0 && sp->up_rows) || (y0 + CHUNK > p.rows && sp->down_rows)) fix_r = false;
             }
             const bool fix_x = (p.fix_left && g0 < 0) || (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
             if (fix_r || fix_x) {
@@ -340,19 +384,6 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             }
             __syncthreads();  // ring slot complete; stage `st` is free again
 
-            if constexpr (SHARD) {
-                // all reads of the neighbour's rows for this unit are done (TMA landed, column patches loaded): once every strip
-                // of that side has said so, tell the neighbour it may overwrite its source again
-                if (peer_side >= 0 && tid == 0) {
-                    ShardCtrl* me = sp->link.self;
-                    __threadfence();
-                    if (atomicAdd(&me->halo_reads[peer_side], 1u) == (unsigned)p.n_strips - 1u) {
-                        me->halo_reads[peer_side] = 0;
-                        ShardCtrl* nb = peer_side == 0 ? sp->link.up : sp->link.down;
-                        st_release_sys(&nb->done_from[peer_side == 0 ? 1 : 0], sp->link.epoch);
-                    }
-                }
-            }
             if (tid == 0) produce();  // refill the stage just drained (the chunk STAGES ahead, possibly of the next unit)
 
             // ---------------- V(i-2): ring -> global rows [ra+8c, ra+8c+8) ----------------
@@ -389,15 +420,14 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
 template <int HALF, bool EXACT, int STAGES, bool F2>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fused_sep_rgbaf32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p) {
-    fused_sep_rgbaf32_body<HALF, EXACT, STAGES, F2, false>(tmap, nullptr, nullptr, p, nullptr);
+    fused_sep_rgbaf32_body<HALF, EXACT, STAGES, F2, false>(tmap, p, nullptr);
 }
 
 template <int HALF, bool EXACT, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
-fused_sep_rgbaf32_shard_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_up,
-                               const __grid_constant__ CUtensorMap tmap_down, const __grid_constant__ FusedParams p,
+fused_sep_rgbaf32_shard_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FusedParams p,
                                const __grid_constant__ ShardParams sp) {
-    fused_sep_rgbaf32_body<HALF, EXACT, STAGES, false, true>(tmap, &tmap_up, &tmap_down, p, &sp);
+    fused_sep_rgbaf32_body<HALF, EXACT, STAGES, false, true>(tmap, p, &sp);
 }
 
 template <int HALF, bool EXACT, int STAGES, bool F2>
@@ -697,67 +727,72 @@ int conv_separable_fused_rgbaf32(const zb_image* src, zb_image* dst, const float
 }
 
 template <int HALF>
-static int launch_shard(const CUtensorMap& tmap, const CUtensorMap& tup, const CUtensorMap& tdown, const FusedParams& p, const ShardParams& sp,
+static int launch_shard(const CUtensorMap& tmap, const FusedParams& p, const ShardParams& sp,
                         int grid, bool exact, cudaStream_t s) {
     // the same pipeline depth as the single-GPU kernel (2 stages measured faster than 3 at 15 taps: 0.435 vs 0.462 ms)
     if (exact) {
         auto k = fused_sep_rgbaf32_shard_kernel<HALF, true, 2>;
         ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2)));
-        k<<<grid, NTHREADS, smem_bytes(2), s>>>(tmap, tup, tdown, p, sp);
+        k<<<grid, NTHREADS, smem_bytes(2), s>>>(tmap, p, sp);
     } else if (g_tune_stages.load() == 3) {
         auto k = fused_sep_rgbaf32_shard_kernel<HALF, false, 3>;
         ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(3)));
-        k<<<grid, NTHREADS, smem_bytes(3), s>>>(tmap, tup, tdown, p, sp);
+        k<<<grid, NTHREADS, smem_bytes(3), s>>>(tmap, p, sp);
     } else {
         auto k = fused_sep_rgbaf32_shard_kernel<HALF, false, 2>;
         ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2)));
-        k<<<grid, NTHREADS, smem_bytes(2), s>>>(tmap, tup, tdown, p, sp);
+        k<<<grid, NTHREADS, smem_bytes(2), s>>>(tmap, p, sp);
     }
     ZB_LAUNCHED();
     return ZB_OK;
 }
 
-// One launch per step: the convolution of this rank's row block of a taller image.  The neighbours' edge rows are TMA-loaded
-// from their memory inside the kernel, which also carries the whole synchronisation (ready / done flags, zb_shard.h).
+// One launch per step: the convolution of this rank's row block of a taller image.  src must own `halo_cap` >= 8 rows of the same
+// stride above and below the block; the kernel's prologue copies the neighbours' `half` edge rows into them over NVLink.
 int conv_separable_fused_rgbaf32_shard(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                                       bool exact, const PeerBlock& up, const PeerBlock& down, const ShardLink& link, cudaStream_t s) {
-    if (src->rows % CHUNK != 0) return ZB_ERR_UNSUPPORTED;   // chunks must not straddle the block
-    if ((up.data && (up.rows < (uint32_t)CHUNK || ((uintptr_t)up.data & 15u))) ||
-        (down.data && (down.rows < (uint32_t)CHUNK || ((uintptr_t)down.data & 15u))))
-        return ZB_ERR_UNSUPPORTED;
+                                       bool exact, const PeerBlock& up, const PeerBlock& down, uint32_t halo_cap, const ShardLink& link,
+                                       cudaStream_t s) {
+    if (src->rows % CHUNK != 0 || halo_cap < (uint32_t)CHUNK) return ZB_ERR_UNSUPPORTED;   // chunks must not straddle the block
     FusedParams p;
-    CUtensorMap tmap, tup, tdown;
+    CUtensorMap tmap;
     EncodeTiledFn encode;
     int grid = 0, half = 0;
     int rc = fused_prepare(src, dst, kx, nx, ky, ny, border, 0, -1, p, tmap, grid, half, encode);
     if (rc) return rc;
     if (grid == 0) return ZB_ERR_UNSUPPORTED;
     if (p.band_rows % CHUNK != 0) return ZB_ERR_UNSUPPORTED;
-    tup = tmap;
-    tdown = tmap;
-    if (up.data && (rc = encode_block_map(encode, tup, const_cast<void*>(up.data), p.ngroups, (int)up.rows, up.stride))) return rc;
-    if (down.data && (rc = encode_block_map(encode, tdown, const_cast<void*>(down.data), p.ngroups, (int)down.rows, down.stride))) return rc;
+    const uint32_t hv = (uint32_t)(ny / 2);   // rows the vertical pass reaches into a neighbour
+    if ((up.data && (up.rows < hv || ((uintptr_t)up.data & 15u))) || (down.data && (down.rows < hv || ((uintptr_t)down.data & 15u))))
+        return ZB_ERR_UNSUPPORTED;
+    // the tensor map spans the block AND its halo rows; the image's row 0 is the map's row halo_cap
+    void* ext = (char*)src->data - (size_t)halo_cap * src->stride * 16;
+    if ((rc = encode_block_map(encode, tmap, ext, p.ngroups, (int)(src->rows + 2 * halo_cap), src->stride))) return rc;
+    p.tma_row_off = (int)halo_cap;
+    p.fix_rows = 1;   // beyond a GLOBAL edge the halo rows hold no image data: every border mode (zero included) patches them
     ShardParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.up_src = (const float4*)up.data;
-    sp.down_src = (const float4*)down.data;
-    sp.up_pitch_px = up.stride;
-    sp.down_pitch_px = down.stride;
-    sp.up_rows = (int)up.rows;
+    sp.half = (int)hv;
+    if (up.data && hv) {
+        sp.up_rows = (const float4*)up.data + (size_t)(up.rows - hv) * up.stride;
+        sp.up_pitch_px = up.stride;
+    }
+    if (down.data && hv) {
+        sp.down_rows = (const float4*)down.data;
+        sp.down_pitch_px = down.stride;
+    }
     sp.link = link;
-    if (!up.data) sp.link.up = nullptr;
-    if (!down.data) sp.link.down = nullptr;
-    // a neighbour side never takes the border path: rows beyond the block are real rows there
+    if (!sp.up_rows) sp.link.up = nullptr;
+    if (!sp.down_rows) sp.link.down = nullptr;
     t_last_kernel = exact ? "fused_sep_rgbaf32_shard_exact" : "fused_sep_rgbaf32_shard";
     switch (half) {
-        case 1: return launch_shard<1>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 2: return launch_shard<2>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 3: return launch_shard<3>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 4: return launch_shard<4>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 5: return launch_shard<5>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 6: return launch_shard<6>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 7: return launch_shard<7>(tmap, tup, tdown, p, sp, grid, exact, s);
-        case 8: return launch_shard<8>(tmap, tup, tdown, p, sp, grid, exact, s);
+        case 1: return launch_shard<1>(tmap, p, sp, grid, exact, s);
+        case 2: return launch_shard<2>(tmap, p, sp, grid, exact, s);
+        case 3: return launch_shard<3>(tmap, p, sp, grid, exact, s);
+        case 4: return launch_shard<4>(tmap, p, sp, grid, exact, s);
+        case 5: return launch_shard<5>(tmap, p, sp, grid, exact, s);
+        case 6: return launch_shard<6>(tmap, p, sp, grid, exact, s);
+        case 7: return launch_shard<7>(tmap, p, sp, grid, exact, s);
+        case 8: return launch_shard<8>(tmap, p, sp, grid, exact, s);
     }
     return ZB_ERR_UNSUPPORTED;
 }

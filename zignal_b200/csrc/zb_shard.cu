@@ -596,13 +596,14 @@ int zb_shard_conv_separable(zb_shard_comm* c, const zb_shard_image* src, zb_shar
         bool all_fused = true;
         for (int r = 0; r < c->world; ++r)
             all_fused &= src->rows[r] % 8 == 0 && src->rows[r] >= 16 && (((uintptr_t)src->data[r] | (uintptr_t)dst->data[r]) & 15u) == 0;
+        all_fused &= src->halo_cap >= 8;   // the kernel's TMA chunks are 8 rows: the halo rows it copies into must exist
         all_fused &= src->cols >= 16 && nx / 2 <= 8 && ny / 2 <= 8 && (nx / 2 >= 1 || ny / 2 >= 1);
         for (int i = 0; i < nx; ++i) all_fused &= !(fabsf(kx[i]) < 1e-10f);
         for (int i = 0; i < ny; ++i) all_fused &= !(fabsf(ky[i]) < 1e-10f);
         if (all_fused) {
             ShardLink link;
             shard_link(c, border, true, &link, nullptr, nullptr);
-            int rc = conv_separable_fused_rgbaf32_shard(&sblk, &dblk, kx, nx, ky, ny, border, g_exact_f32.load() != 0, pu, pd, link, s);
+            int rc = conv_separable_fused_rgbaf32_shard(&sblk, &dblk, kx, nx, ky, ny, border, g_exact_f32.load() != 0, pu, pd, src->halo_cap, link, s);
             if (rc != ZB_ERR_UNSUPPORTED) return rc;
             --c->epoch;   // nothing was launched
             return ZB_ERR_DEVICE_FAILURE;   // the ranks would diverge: report instead of silently taking another path

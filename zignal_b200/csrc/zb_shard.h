@@ -19,7 +19,8 @@ struct ShardCtrl {
     unsigned long long ready_from[2];
     unsigned long long done_from[2];
     unsigned long long gather[2][ZB_SHARD_MAX_WORLD][16];
-    unsigned int halo_reads[2];   // local: CTAs that have consumed their peer chunks on side d in the running op
+    unsigned long long halo_landed;   // local: op number whose neighbour rows have all arrived in my halo rows
+    unsigned int halo_reads[2];   // local: [0] CTAs of the running kernel whose share of the halo copy is done
     unsigned int exit_ticket;     // local: CTAs that have left the running kernel
     unsigned int error;           // local: set when a wait timed out (a peer never arrived)
     unsigned int gather_ticket;   // local: blocks of the running statistics kernel that have added their partial sums
@@ -103,12 +104,13 @@ int shard_rank(const zb_shard_comm* c);
 int shard_allreduce(zb_shard_comm* c, void* buf, size_t count, int dtype, cudaStream_t s);
 
 // zb_conv_fused.cu: the fused RGBA f32 convolution of a row block whose edge rows come from the neighbours' memory
-// (TMA loads over NVLink).  up / down: block geometry of the neighbours (null data = global edge).
+// (copied over NVLink into the block's halo rows by the kernel's own prologue).  up / down: block geometry of the neighbours (null data = global edge).
 struct PeerBlock {
     const void* data;   // row 0 of the neighbour's block
     uint32_t rows;
     uint64_t stride;
 };
 int conv_separable_fused_rgbaf32_shard(const zb_image* src, zb_image* dst, const float* kx, int nx, const float* ky, int ny, int border,
-                                       bool exact, const PeerBlock& up, const PeerBlock& down, const ShardLink& link, cudaStream_t s);
+                                       bool exact, const PeerBlock& up, const PeerBlock& down, uint32_t halo_cap, const ShardLink& link,
+                                       cudaStream_t s);
 }  // namespace zb

@@ -85,17 +85,38 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
             return;
         }
     }
+    // Rgba(u8), bilinear, frames below 2^21 pixels a side (config 4): an interior sample costs ONE float->int conversion per axis.
+    // i = floor(512 * s) is exact (512 s is an exact product) and holds both floor(s) = i >> 9 and the reference's weight
+    // @round(256 * frac) = ((i & 511) + 1) >> 1 (interpolation.zig:349-352; see frac_q8); offsets are 32-bit.  Samples that touch
+    // the image edge take the general sampler below.
+    constexpr bool kFastRgba8 = sizeof(CT) == 1 && N == 4 && METHOD == ZB_INTERP_BILINEAR;
+    const bool fast_ok = kFastRgba8 && img.rows < (1 << 21) && img.cols < (1 << 21) && (unsigned long long)img.rows * img.stride < (1ull << 29);
+    const float yf0 = (float)r0;
 #pragma unroll
     for (int j = 0; j < ROT_RPT; ++j) {
         if (r0 + j >= dst_rows) break;
-        const float y = (float)(r0 + j);
+        const float y = kFastRgba8 ? yf0 + (float)j : (float)(r0 + j);   // exact either way
         const float dy = y - p.rcy;
         const float rotated_dx = cos_dx - p.sin_a * dy;
         const float rotated_dy = sin_dx + p.cos_a * dy;
         const float src_x = rotated_dx + p.cx;
         const float src_y = rotated_dy + p.cy;
         Pix<CT, N> val;
-        if (!interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+        bool done = false;
+        if constexpr (kFastRgba8) {
+            if (fast_ok && fabsf(src_x) < 2097152.0f && fabsf(src_y) < 2097152.0f) {
+                const int ix = __float2int_rd(src_x * 512.0f), iy = __float2int_rd(src_y * 512.0f);
+                const int left = ix >> 9, top = iy >> 9;
+                if ((unsigned)left < (unsigned)(img.cols - 1) && (unsigned)top < (unsigned)(img.rows - 1)) {   // all four neighbours inside
+                    const unsigned fx = (unsigned)((ix & 511) + 1) >> 1, fy = (unsigned)((iy & 511) + 1) >> 1;
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(img.data) + (unsigned)top * (unsigned)img.stride + (unsigned)left;
+                    const uint32_t* q2 = q + (unsigned)img.stride;
+                    val.u = bilerp_rgba8(__ldg(q), __ldg(q + 1), __ldg(q2), __ldg(q2 + 1), fx, fy);
+                    done = true;
+                }
+            }
+        }
+        if (!done && !interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
         store_px<CT, N>(out, 0, val);
         out += dst_stride * N;
     }

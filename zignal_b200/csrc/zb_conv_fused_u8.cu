@@ -51,7 +51,7 @@ struct U8Params {
     int kx[MAXK];
     int ky[MAXK];
     float kxf[MAXK];  // the same Q8 taps as floats (FMATH variant)
-    float kyf[MAXK];
+    float kyf[MAXK];  // ky_q8 / 65536: the vertical sums come out as acc / 65536 (exact), ready for round_clamp_byte
     const uint32_t* src;
     uint32_t* dst;
     unsigned long long src_pitch_px, dst_pitch_px;
@@ -117,6 +117,21 @@ __device__ __forceinline__ void mac4f_px(float4& acc, uint32_t w, float k) {
     acc.y = fmaf((float)((w >> 8) & 0xffu), k, acc.y);
     acc.z = fmaf((float)((w >> 16) & 0xffu), k, acc.z);
     acc.w = fmaf((float)(w >> 24), k, acc.w);
+}
+// Byte k of `w` as a float without an I2F (the conversion pipe runs at a quarter of the FMA rate and the horizontal pass needs
+// ~11 of them per output pixel): PRMT drops the byte into the mantissa of 2^23, one FADD removes the 2^23.  Exact.
+__device__ __forceinline__ float byte_f32(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k)) - 8388608.0f;
+}
+// divClampU8(65536, acc) (convolution.zig:18-22) on u = acc / 65536 held exactly in f32 (the vertical taps carry the 2^-16):
+// round half away from zero, clamp to [0, 255], and return the integer in the low byte -- no F2I.  u + 1.5 * 2^23 rounds to the
+// nearest integer (ties to even); the one case where that differs from half-away for u >= 0 is u = k + 1/2 with k even.
+__device__ __forceinline__ uint32_t round_clamp_byte(float u) {
+    const float t = __fadd_rn(u, 12582912.0f);
+    float r = __fsub_rn(t, 12582912.0f);
+    if (__fsub_rn(u, r) == 0.5f) r = __fadd_rn(r, 1.0f);
+    r = fminf(fmaxf(r, 0.0f), 255.0f);
+    return __float_as_uint(__fadd_rn(r, 8388608.0f)) & 0xFFu;
 }
 __device__ __forceinline__ void mac4f(float4& acc, const float4& v, float k) {
     acc.x = fmaf(v.x, k, acc.x);
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < NLOAD; ++j) {
                         const uint32_t px = w[8 - HALF + j];
-                        const float4 pf = make_float4((float)(px & 0xffu), (float)((px >> 8) & 0xffu), (float)((px >> 16) & 0xffu), (float)(px >> 24));
+                        const float4 pf = make_float4(byte_f32(px, 0), byte_f32(px, 1), byte_f32(px, 2), byte_f32(px, 3));
 #pragma unroll
                         for (int o = 0; o < 8; ++o) {
                             const int ti = j - o;
@@ -241,8 +256,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
             // ---------------- V(i-2) ----------------
             if (i >= 2) {
                 const int c = i - 2;
-                int4 acc[8];
                 const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
+                const int x = x0 + vx;
+                const int yb = ra + CHUNK * c;
+                uint32_t* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
                 if constexpr (FMATH) {
                     float4 facc[8];
 #pragma unroll
@@ -255,12 +272,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
 #pragma unroll
                         for (int o = 0; o < 8; ++o) {
                             const int ti = j - o;
-                            if (ti >= 0 && ti < K) mac4f(facc[o], v, p.kyf[ti]);
+                            if (ti >= 0 && ti < K) mac4f(facc[o], v, p.kyf[ti]);   // kyf = ky_q8 * 2^-16: the sums are acc / 65536, still exact
                         }
                     }
+                    if (x < p.cols) {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) acc[o] = make_int4((int)facc[o].x, (int)facc[o].y, (int)facc[o].z, (int)facc[o].w);  // exact integers
+                        for (int o = 0; o < 8; ++o) {
+                            if (yb + o < rb) {
+                                const uint32_t px = round_clamp_byte(facc[o].x) | (round_clamp_byte(facc[o].y) << 8) | (round_clamp_byte(facc[o].z) << 16) |
+                                                    (round_clamp_byte(facc[o].w) << 24);
+                                __stcs(out + (size_t)o * p.dst_pitch_px, px);
+                            }
+                        }
+                    }
                 } else {
+                    int4 acc[8];
 #pragma unroll
                     for (int o = 0; o < 8; ++o) acc[o] = make_int4(0, 0, 0, 0);
 #pragma unroll
@@ -274,17 +300,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
                             if (ti >= 0 && ti < K) mac4v(acc[o], v, p.ky[ti]);
                         }
                     }
-                }
-                const int x = x0 + vx;
-                if (x < p.cols) {
-                    const int yb = ra + CHUNK * c;
-                    uint32_t* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+                    if (x < p.cols) {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        if (yb + o < rb) {
-                            const uint32_t px = div_clamp_65536(acc[o].x) | (div_clamp_65536(acc[o].y) << 8) | (div_clamp_65536(acc[o].z) << 16) |
-                                                (div_clamp_65536(acc[o].w) << 24);
-                            __stcs(out + (size_t)o * p.dst_pitch_px, px);
+                        for (int o = 0; o < 8; ++o) {
+                            if (yb + o < rb) {
+                                const uint32_t px = div_clamp_65536(acc[o].x) | (div_clamp_65536(acc[o].y) << 8) | (div_clamp_65536(acc[o].z) << 16) |
+                                                    (div_clamp_65536(acc[o].w) << 24);
+                                __stcs(out + (size_t)o * p.dst_pitch_px, px);
+                            }
                         }
                     }
                 }
@@ -320,7 +343,7 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     for (int i = 0; i < ny; ++i) { const int q = (int)roundf(ky[i] * 256.0f); p.ky[i + (half - half_y)] = q; say += llabs((long long)q); }
     if (sax * 255 * say + 32768 >= 2147483647LL) return ZB_ERR_UNSUPPORTED;  // i32 accumulators must be provably safe
     const bool fmath = (sax * 255 * say <= (1LL << 24)) && g_tune_u8_fmath.load() != 0;  // f32 is exact up to 2^24
-    for (int i = 0; i < MAXK; ++i) { p.kxf[i] = (float)p.kx[i]; p.kyf[i] = (float)p.ky[i]; }
+    for (int i = 0; i < MAXK; ++i) { p.kxf[i] = (float)p.kx[i]; p.kyf[i] = (float)p.ky[i] * (1.0f / 65536.0f); }   // exact power-of-two scaling
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return ZB_ERR_UNSUPPORTED;
     DeviceInfo di;

@@ -381,6 +381,29 @@ def main():
                 ms = time_steps(torch, dist, world, dev, lambda: big.resize(small, zb.Interpolation.BICUBIC), 50, 5)
                 extra["c3_bicubic_16384_to_4096_rgb8"] = {"ms": ms, "algorithmic_bytes": 855638016, "frac_of_hbm_peak": 855638016 / (ms * 1e-3) / 1e9 / peak_x}
                 del x, big, small
+                # PCA (the "SVD step" config): Pca.fit's device core on n = 1,048,576 x dim 256 f32 -- column means + centring,
+                # X^T X / (n - 1) on the tcgen05 tensor cores (3xTF32), one-sided Jacobi SVD of the 256 x 256 covariance
+                from zignal_b200 import matrix
+                g = torch.Generator(device=dev).manual_seed(7)
+                X = torch.randn(1 << 20, 256, device=dev, generator=g)
+                mean = torch.empty(256, device=dev)
+                cen = torch.empty_like(X)
+
+                def gram():
+                    return matrix.gemm_device(cen, cen, True, False, 1.0 / (X.shape[0] - 1), 0.0, None)
+                matrix.center_columns(X, mean, True, cen)
+                ms_gemm = time_steps(torch, dist, world, dev, gram, 20, 3)
+                cov = gram()
+                ms_svd = time_steps(torch, dist, world, dev, lambda: matrix.svd_device(cov, True, False), 3, 1)
+
+                def fit():
+                    matrix.center_columns(X, mean, True, cen)
+                    matrix.svd_device(gram(), True, False)
+                ms_fit = time_steps(torch, dist, world, dev, fit, 3, 1)
+                extra["pca_fit_1048576x256_f32"] = {"ms": ms_fit, "gemm_xtx_ms": ms_gemm, "svd_256x256_ms": ms_svd,
+                                                    "gemm_tflops_fp32_accurate": 2.0 * X.shape[0] * 256 * 256 / (ms_gemm * 1e-3) / 1e12,
+                                                    "kernel": L.zb_last_kernel().decode()}
+                del X, cen, cov
             # C4: rotate 45 deg bilinear .zero, 1920x1080 Rgba frames; 1024 frames split over the ranks (128 per step call)
             n_total = 1024
             lo, hi_ = comm.split(n_total)

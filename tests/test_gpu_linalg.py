@@ -20,7 +20,7 @@ def zb():
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape", [(24, 24), (40, 33), (64, 64), (300, 47), (256, 256)])
+@pytest.mark.parametrize("shape", [(24, 24), (40, 33), (64, 64), (300, 47), (256, 256), (3000, 40)])
 @pytest.mark.parametrize("mode", ["no_u", "skinny_u", "full_u"])
 def test_svd_device_kernel_vs_oracle(zb, dtype, shape, mode):
     if mode == "full_u" and shape[0] > 100:

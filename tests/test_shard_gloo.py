@@ -254,3 +254,38 @@ def test_conv_plan_invariants_for_every_rank_up_to_eight_gpus():
                         if not needs:
                             assert not reads_up_halo and not reads_down_halo, (world, rank, border, rows, halo, half, steps)
                     assert all(not needs for _, _, needs in steps) or up is not None or down is not None
+
+
+def test_c_abi_batch_split_matches_the_python_model():
+    """zb_shard_split (pure host arithmetic behind the C ABI) == shard.split_batch for every rank of 1..8-GPU runs."""
+    import ctypes as C
+
+    from zignal_b200 import _ffi, shard
+    L = _ffi.lib()
+    for world in range(1, 9):
+        for n in (0, 1, 7, 128, 1024, 1000003):
+            covered = 0
+            for rank in range(world):
+                lo, hi = C.c_uint32(), C.c_uint32()
+                assert L.zb_shard_split(n, rank, world, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == shard.split_batch(n, rank, world)
+                assert lo.value == covered
+                covered = hi.value
+            assert covered == n
+    lo, hi = C.c_uint32(), C.c_uint32()
+    assert L.zb_shard_split(4, 3, 2, C.byref(lo), C.byref(hi)) != 0          # rank outside the world
+
+
+def test_shard_entry_points_reject_bad_arguments_without_a_gpu():
+    import ctypes as C
+
+    from zignal_b200 import _ffi
+    L = _ffi.lib()
+    h = C.c_void_p()
+    assert L.zb_shard_comm_create(C.byref(h), 0, 0, None) == 5                 # world < 1: InvalidArgument
+    assert L.zb_shard_comm_create(C.byref(h), 2, 2, None) == 5                 # rank outside the world
+    assert L.zb_shard_comm_create(C.byref(h), 0, 2, None) == 5                 # world > 1 needs the unique id
+    assert L.zb_shard_conv_separable(None, None, None, None, 0, None, 0, 2, None) == 5
+    assert L.zb_shard_halo_exchange(None, None, 1, 2, None) == 5
+    assert L.zb_shard_fdm_update(None, None, None) == 5
+    assert L.zb_shard_tune_path(7) == 5

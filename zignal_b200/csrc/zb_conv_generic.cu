@@ -28,10 +28,10 @@ __global__ void __launch_bounds__(kThreads) sep_h_kernel(const SrcT* __restrict_
     KT* taps = reinterpret_cast<KT*>(smem_raw);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) taps[i] = taps_g[i];
     __syncthreads();
-    const int r = blockIdx.y;
+    const int r = ZB_GRID_ROW();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // element within the row
     const int w = cols * CH;
-    if (e >= w) return;
+    if (e >= w || r >= rows) return;
     const int c = e / CH, k = e - c * CH;
     const int half = nx / 2;
     const SrcT* row = src + (size_t)r * src_row_el;
@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(kThreads) sep_v_kernel(const TmpT* __restrict_
     KT* taps = reinterpret_cast<KT*>(smem_raw);
     for (int i = threadIdx.x; i < ny; i += blockDim.x) taps[i] = taps_g[i];
     __syncthreads();
-    const int r = blockIdx.y;
+    const int r = ZB_GRID_ROW();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = cols * CH;
-    if (e >= w) return;
+    if (e >= w || r >= rows) return;
     const int half = ny / 2;
     const bool interior = (rows > 2 * half) && r >= half && r < rows - half;
     AccT acc = 0;
@@ -197,7 +197,7 @@ static int launch_sep(const zb_image* src, zb_image* dst, const KT* d_kx, int nx
                       cudaStream_t s) {
     const int rows = (int)src->rows, cols = (int)src->cols;
     const int w = cols * CH;
-    dim3 grid(div_up(w, kThreads), rows);
+    const dim3 grid = row_grid(div_up(w, kThreads), (size_t)rows);
     sep_h_kernel<PixT, TmpT, AccH, KT, CH><<<grid, kThreads, nx * sizeof(KT), s>>>((const PixT*)src->data, (size_t)src->stride * CH,
                                                                                    (TmpT*)tmp, rows, cols, d_kx, nx, border);
     ZB_LAUNCHED();

@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ s
                                                       int rows, int cols) {
     using S = Fmt<SF>;
     using D = Fmt<DF>;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= cols) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = ZB_GRID_ROW();
+    if (c >= cols || r >= rows) return;
     const typename S::CT* sp = (const typename S::CT*)src + ((size_t)r * src_stride + c) * S::N;
     typename D::CT* dp = (typename D::CT*)dst + ((size_t)r * dst_stride + c) * D::N;
     constexpr bool s_float = sizeof(typename S::CT) == 4, d_float = sizeof(typename D::CT) == 4;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ s
 
 template <int SF, int DF>
 int launch(const zb_image* src, zb_image* dst, cudaStream_t s) {
-    dim3 grid(div_up(src->cols, 256), src->rows);
+    const dim3 grid = row_grid(div_up(src->cols, 256), src->rows);
     convert_kernel<SF, DF><<<grid, 256, 0, s>>>(src->data, src->stride, dst->data, dst->stride, (int)src->rows, (int)src->cols);
     ZB_LAUNCHED();
     return ZB_OK;

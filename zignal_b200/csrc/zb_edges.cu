@@ -18,8 +18,8 @@ namespace {
 template <int CH, bool IS_FLOAT>
 __global__ void __launch_bounds__(256) to_gray_f32_kernel(const void* __restrict__ src, size_t src_stride, float* __restrict__ gray, int rows,
                                                           int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= cols) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = ZB_GRID_ROW();
+    if (c >= cols || r >= rows) return;
     float v;
     if constexpr (IS_FLOAT) {
         v = ((const float*)src)[(size_t)r * src_stride + c];
@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) to_gray_f32_kernel(const void* __restrict
 
 __global__ void __launch_bounds__(256) sobel_magnitude_kernel(const float* __restrict__ gx, const float* __restrict__ gy, uint8_t* __restrict__ dst,
                                                               size_t dst_stride, int rows, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= cols) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = ZB_GRID_ROW();
+    if (c >= cols || r >= rows) return;
     const float a = gx[(size_t)r * cols + c], b = gy[(size_t)r * cols + c];
     const float magnitude = __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));   // edges.zig:65
     const float scaled = __fdiv_rn(magnitude, 4.0f);                                        // :68
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) sobel_fused_kernel(const void* __restrict
 // as(f32, convertColor(u8, v)) for a float scalar: round(clamp(v, 0, 1) * 255) evaluated in f64 (color.zig:114-118).
 __global__ void __launch_bounds__(256) canny_quantize_f32_kernel(const float* __restrict__ src, size_t src_stride, float* __restrict__ gray,
                                                                  int rows, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= cols) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = ZB_GRID_ROW();
+    if (c >= cols || r >= rows) return;
     double d = (double)src[(size_t)r * src_stride + c];
     d = d < 0.0 ? 0.0 : (d > 1.0 ? 1.0 : d);
     gray[(size_t)r * cols + c] = (float)(uint8_t)round(d * 255.0);
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(1024) canny_hysteresis_kernel(uint8_t* img, si
 
 // Candidates that were never reached stay 0 in the reference's output.
 __global__ void __launch_bounds__(256) canny_finalize_kernel(uint8_t* __restrict__ img, size_t stride, int rows, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= cols) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = ZB_GRID_ROW();
+    if (c >= cols || r >= rows) return;
     uint8_t* p = img + (size_t)r * stride + c;
     if (*p == kWeak) *p = 0;
 }
@@ -215,7 +215,7 @@ extern "C" int zb_canny(const zb_image* src, zb_image* dst, int pixfmt, float si
     float* blurred = sigma == 0 ? gray : mag + n;                      // :241-242 (sigma == 0: no blur)
     int* promoted = (int*)((char*)buf.p + planes * plane);
 
-    dim3 grid(div_up(cols, 256), rows);
+    const dim3 grid = row_grid(div_up(cols, 256), (size_t)rows);
     switch (pixfmt) {                                                  // :229-236
         case ZB_PIX_F32: canny_quantize_f32_kernel<<<grid, 256, 0, s>>>((const float*)src->data, src->stride, gray, rows, cols); break;
         case ZB_PIX_U8: to_gray_f32_kernel<1, false><<<grid, 256, 0, s>>>(src->data, src->stride, gray, rows, cols); break;
@@ -287,7 +287,7 @@ extern "C" int zb_sobel(const zb_image* src, zb_image* dst, int pixfmt, zb_strea
     float* gray = buf.as<float>();
     float* gx = gray + (size_t)rows * cols;
     float* gy = gx + (size_t)rows * cols;
-    dim3 grid(div_up(cols, 256), rows);
+    const dim3 grid = row_grid(div_up(cols, 256), (size_t)rows);
     switch (pixfmt) {
         case ZB_PIX_F32: to_gray_f32_kernel<1, true><<<grid, 256, 0, s>>>(src->data, src->stride, gray, rows, cols); break;
         case ZB_PIX_U8: to_gray_f32_kernel<1, false><<<grid, 256, 0, s>>>(src->data, src->stride, gray, rows, cols); break;

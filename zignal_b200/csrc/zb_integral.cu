@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(256) sat_col_pass(float* __restrict__ sat, int
 template <typename PixT, int CH, bool SHARPEN>
 __global__ void __launch_bounds__(256) sat_eval(const float* __restrict__ sat, const PixT* __restrict__ src, size_t src_row_el,
                                                 PixT* __restrict__ dst, size_t dst_row_el, int rows, int cols, int radius) {
-    const int r = blockIdx.y;
+    const int r = ZB_GRID_ROW();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= cols * CH) return;
+    if (e >= cols * CH || r >= rows) return;
     const int c = e / CH, k = e - c * CH;
     const float* plane = sat + (size_t)k * rows * cols;
     const int r1 = max(r - radius, 0), r2 = min(r + radius, rows - 1);  // r -| radius ; @min(r + radius, rows - 1)
@@ -123,7 +123,7 @@ int box_or_sharpen(const zb_image* src, zb_image* dst, int radius, cudaStream_t 
     int rc = sat.alloc((size_t)rows * cols * CH * sizeof(float), s);
     if (rc) return rc;
     if ((rc = build_sat<PixT, CH>(src, sat.as<float>(), s))) return rc;
-    dim3 grid(div_up((size_t)cols * CH, 256), rows);
+    const dim3 grid = row_grid(div_up((size_t)cols * CH, 256), (size_t)rows);
     sat_eval<PixT, CH, SHARPEN><<<grid, 256, 0, s>>>(sat.as<float>(), (const PixT*)src->data, (size_t)src->stride * CH,
                                                      (PixT*)dst->data, (size_t)dst->stride * CH, rows, cols, radius);
     ZB_LAUNCHED();

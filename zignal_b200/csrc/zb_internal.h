@@ -86,4 +86,15 @@ static inline bool images_overlap(const zb_image* a, const zb_image* b, size_t p
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// One grid row per image row without the 65,535 limit of gridDim.y: rows are spread over (y, z); kernels read the row with
+// ZB_GRID_ROW() and return when it is >= rows (the last z-slice may be partly empty).
+#ifdef __CUDACC__
+#define ZB_GRID_ROW() ((int)(blockIdx.y + blockIdx.z * gridDim.y))
+static inline dim3 row_grid(unsigned x_blocks, size_t rows) {
+    const size_t gz = (rows + 65534) / 65535;
+    const size_t gy = gz ? (rows + gz - 1) / gz : 0;
+    return dim3(x_blocks, (unsigned)gy, (unsigned)(gz ? gz : 1));
+}
+#endif
+
 }  // namespace zb

@@ -164,6 +164,63 @@ __global__ void __launch_bounds__(NT) jacobi_svd_kernel(T* __restrict__ Gt, T* _
     if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
 }
 
+// The same sweep with one WARP per column pair (short columns: the three dot products are 5 shuffle steps, no block barrier, and
+// a quarter of the CTAs take part in the grid barrier, which is what a round costs at this size).
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) jacobi_svd_warp_kernel(T* __restrict__ Gt, T* __restrict__ Vt, int m, int n, int with_v, double tol,
+                                                             double abs_floor, unsigned int* barrier_counter, unsigned int* rotations,
+                                                             int* sweeps_done) {
+    GridBarrier bar{barrier_counter, 0};
+    const int np = n + (n & 1);
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (NT / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (NT / 32);
+    int sweep = 0;
+    for (; sweep < kMaxSweeps; ++sweep) {
+        for (int r = 0; r < np - 1; ++r) {
+            for (int k = warp_global; k < np / 2; k += n_warps) {
+                int p, q;
+                tournament_pair(np, r, k, p, q);
+                if (q >= n) continue;
+                T* gp = Gt + (size_t)p * m;
+                T* gq = Gt + (size_t)q * m;
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = lane; i < m; i += 32) {
+                    const double x = (double)__ldcg(gp + i), y = (double)__ldcg(gq + i);
+                    alpha += x * x;
+                    beta += y * y;
+                    gamma += x * y;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {   // xor butterfly: every lane ends with the same totals
+                    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+                    beta += __shfl_xor_sync(0xffffffffu, beta, o);
+                    gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+                }
+                T c, s;
+                if (!hestenes_rotation<T>(alpha, beta, gamma, tol, abs_floor, c, s)) continue;
+                if (lane == 0) atomicAdd(&rotations[sweep], 1u);
+                for (int i = lane; i < m; i += 32) {
+                    const T x = __ldcg(gp + i), y = __ldcg(gq + i);
+                    gp[i] = c * x - s * y;
+                    gq[i] = s * x + c * y;
+                }
+                if (with_v) {
+                    T* vp = Vt + (size_t)p * n;
+                    T* vq = Vt + (size_t)q * n;
+                    for (int i = lane; i < n; i += 32) {
+                        const T x = __ldcg(vp + i), y = __ldcg(vq + i);
+                        vp[i] = c * x - s * y;
+                        vq[i] = s * x + c * y;
+                    }
+                }
+            }
+            bar.sync();
+        }
+        if (*(volatile unsigned int*)&rotations[sweep] == 0) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
+}
+
 // A: n x n symmetric, row-major (both triangles kept up to date); Vt rows = eigenvector columns; cs: n/2 rotations of the round
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) jacobi_eigh_kernel(T* __restrict__ A, T* __restrict__ Vt, int n, double tiny, T* __restrict__ cs,
@@ -367,14 +424,18 @@ int svd_jacobi_device(T* dGt, T* dVt, int m, int n, bool with_v, double abs_floo
         ZB_LAUNCHED();
     }
     int grid = 1;
-    if ((rc = cooperative_grid(jacobi_svd_kernel<T, NT>, NT, (n + 1) / 2, &grid))) return rc;
+    const bool warp_pairs = m <= 2048;   // short columns: a warp per pair, four pairs per CTA
+    const int pairs = (n + 1) / 2;
+    if (warp_pairs) rc = cooperative_grid(jacobi_svd_warp_kernel<T, NT>, NT, (pairs + NT / 32 - 1) / (NT / 32), &grid);
+    else rc = cooperative_grid(jacobi_svd_kernel<T, NT>, NT, pairs, &grid);
+    if (rc) return rc;
     int wv = with_v ? 1 : 0;
     double tol = (double)std::numeric_limits<T>::epsilon();
     unsigned int* bc = w.barrier();
     unsigned int* rots = w.rotations();
     int* sw = w.sweeps();
     void* args[] = {&dGt, &dVt, &m, &n, &wv, &tol, &abs_floor, &bc, &rots, &sw};
-    ZB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_svd_kernel<T, NT>, dim3(grid), dim3(NT), args, 0, s));
+    ZB_CUDA(cudaLaunchCooperativeKernel(warp_pairs ? (void*)jacobi_svd_warp_kernel<T, NT> : (void*)jacobi_svd_kernel<T, NT>, dim3(grid), dim3(NT), args, 0, s));
     ZB_LAUNCHED();
     ZB_CUDA(cudaMemcpyAsync(sweeps, sw, sizeof(int), cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));

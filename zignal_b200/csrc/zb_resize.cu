@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256) resize_plane_kernel(const uint8_t* __rest
                                                            size_t dst_row_b, int dst_rows, int dst_cols,
                                                            const TapEntry* __restrict__ xt, const TapEntry* __restrict__ yt) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= dst_cols) return;
+    const int r = ZB_GRID_ROW();
+    if (c >= dst_cols || r >= dst_rows) return;
     const TapEntry ex = xt[c];
     const TapEntry ey = yt[r];
     uint8_t* out = dst + (size_t)r * dst_row_b + (size_t)c * CH;
@@ -208,12 +208,12 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, int b, int c) {
 
 template <int CH>
 __global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t* __restrict__ src, size_t src_row_b, size_t src_bytes,
-                                                                   uint8_t* __restrict__ dst, size_t dst_row_b, int dst_cols,
+                                                                   uint8_t* __restrict__ dst, size_t dst_row_b, int dst_rows, int dst_cols,
                                                                    const TapEntry* __restrict__ xt, const TapEntry* __restrict__ yt,
                                                                    const __grid_constant__ UniformCubic u) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= dst_cols) return;
+    const int r = ZB_GRID_ROW();
+    if (c >= dst_cols || r >= dst_rows) return;
     const int4 ix = __ldg(reinterpret_cast<const int4*>(&xt[c]));   // idx[0..3] lead the entry
     const int4 iy = __ldg(reinterpret_cast<const int4*>(&yt[r]));
     const int iyv[4] = {iy.x, iy.y, iy.z, iy.w};
@@ -304,16 +304,16 @@ __global__ void __launch_bounds__(256) resize_cubic_uniform_kernel(const uint8_t
 // 4*4*CH bytes back with 128-bit loads (48-byte lane stride: conflict-free).  Taps run on dp4a as above.
 template <int CH>
 __global__ void __launch_bounds__(CH == 3 ? 256 : 128) resize_cubic_r4_kernel(const uint8_t* __restrict__ src, size_t src_row_b, uint8_t* __restrict__ dst,
-                                                              size_t dst_row_b, int dst_cols, int col_off, size_t src_valid_b, const TapEntry* __restrict__ yt,
+                                                              size_t dst_row_b, int dst_rows, int dst_cols, int col_off, size_t src_valid_b, const TapEntry* __restrict__ yt,
                                                               const __grid_constant__ UniformCubic u) {
     constexpr int NW = CH;                 // 16-byte chunks per lane per tap row (4 outputs * 4 taps * CH bytes = 16 * CH)
     constexpr int ROW_BYTES = 32 * NW * 16;
     constexpr int WPB = CH == 3 ? 8 : 4;   // warps per block: 48 KB (Rgb) / 32 KB (Rgba) of strips
     __shared__ __align__(16) uint8_t strip[WPB][4][ROW_BYTES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.y;
+    const int r = ZB_GRID_ROW();
     const int c_base = (blockIdx.x * WPB + warp) * 128;
-    if (c_base >= dst_cols) return;
+    if (c_base >= dst_cols || r >= dst_rows) return;
     const int4 iy = __ldg(reinterpret_cast<const int4*>(&yt[r]));
     const int iyv[4] = {iy.x, iy.y, iy.z, iy.w};
     const size_t run0 = ((size_t)4 * c_base + col_off) * CH;      // first byte of the run inside a source row (multiple of 16)
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(CH == 3 ? 256 : 128) resize_cubic_r4_kernel(co
 
 template <int CH>
 int launch_plane(const zb_image* src, zb_image* dst, int method, const TapEntry* xt, const TapEntry* yt, cudaStream_t s) {
-    dim3 grid(div_up(dst->cols, 256), dst->rows);
+    const dim3 grid = row_grid(div_up(dst->cols, 256), dst->rows);
     const uint8_t* sp = (const uint8_t*)src->data;
     uint8_t* dp = (uint8_t*)dst->data;
     const size_t sb = (size_t)src->stride * CH, db = (size_t)dst->stride * CH;
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(SrcView img, CT* __
                                                              int dst_cols, float scale_x, float scale_y, float mb, float mc,
                                                              const float* __restrict__ lut) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= dst_cols) return;
+    const int r = ZB_GRID_ROW();
+    if (c >= dst_cols || r >= dst_rows) return;
     const float src_y = ((float)r + 0.5f) * scale_y - 0.5f;
     const float src_x = ((float)c + 0.5f) * scale_x - 0.5f;
     Pix<CT, N> val;
@@ -427,7 +427,7 @@ int launch_generic(const zb_image* src, zb_image* dst, int method, float mb, flo
     SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
     const float scale_x = (float)src->cols / (float)dst->cols;
     const float scale_y = (float)src->rows / (float)dst->rows;
-    dim3 grid(div_up(dst->cols, 256), dst->rows);
+    const dim3 grid = row_grid(div_up(dst->cols, 256), dst->rows);
     return dispatch_method(method, [&](auto m) -> int {
         resize_generic_kernel<CT, N, decltype(m)::value><<<grid, 256, 0, s>>>(v, (CT*)dst->data, (size_t)dst->stride, (int)dst->rows,
                                                                               (int)dst->cols, scale_x, scale_y, mb, mc, lut);
@@ -545,7 +545,7 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
         if (method == ZB_INTERP_BICUBIC || method == ZB_INTERP_CATMULL_ROM || method == ZB_INTERP_MITCHELL) {
             const UniformCubic& u = plan->u;
             if (plan->uniform_ok) {
-                dim3 grid(div_up(dst->cols, 256), dst->rows);
+                const dim3 grid = row_grid(div_up(dst->cols, 256), dst->rows);
                 const int ch = pixfmt == ZB_PIX_RGB8 ? 3 : 4;
                 const size_t sb = (size_t)src->stride * ch, db = (size_t)dst->stride * ch;
                 const size_t src_bytes = (size_t)(src->rows - 1) * sb + (size_t)src->cols * ch;
@@ -555,21 +555,21 @@ int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, 
                 const int o = xt[0].idx[0];
                 r4 = r4 && plan->cols_4to1 && o >= 0 && ((size_t)o * ch) % 16 == 0;
                 if (r4) {
-                    dim3 g4(div_up(dst->cols, ch == 3 ? 1024 : 512), dst->rows);
+                    const dim3 g4 = row_grid(div_up(dst->cols, ch == 3 ? 1024 : 512), dst->rows);
                     if (ch == 3)
-                        resize_cubic_r4_kernel<3><<<g4, 256, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->cols, o, valid_b, dyt, u);
+                        resize_cubic_r4_kernel<3><<<g4, 256, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->rows, (int)dst->cols, o, valid_b, dyt, u);
                     else
-                        resize_cubic_r4_kernel<4><<<g4, 128, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->cols, o, valid_b, dyt, u);
+                        resize_cubic_r4_kernel<4><<<g4, 128, 0, s>>>((const uint8_t*)src->data, sb, (uint8_t*)dst->data, db, (int)dst->rows, (int)dst->cols, o, valid_b, dyt, u);
                     ZB_LAUNCHED();
                     t_last_kernel = "resize_cubic_r4_u8";
                     return ZB_OK;
                 }
                 if (ch == 3)
                     resize_cubic_uniform_kernel<3><<<grid, 256, 0, s>>>((const uint8_t*)src->data, sb, src_bytes, (uint8_t*)dst->data, db,
-                                                                        (int)dst->cols, dxt, dyt, u);
+                                                                        (int)dst->rows, (int)dst->cols, dxt, dyt, u);
                 else
                     resize_cubic_uniform_kernel<4><<<grid, 256, 0, s>>>((const uint8_t*)src->data, sb, src_bytes, (uint8_t*)dst->data, db,
-                                                                        (int)dst->cols, dxt, dyt, u);
+                                                                        (int)dst->rows, (int)dst->cols, dxt, dyt, u);
                 ZB_LAUNCHED();
                 t_last_kernel = "resize_cubic_uniform_u8";
                 return ZB_OK;

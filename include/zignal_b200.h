@@ -193,7 +193,8 @@ int zb_canny(const zb_image* src, zb_image* dst_u8, int pixfmt, float sigma, flo
  *   Image.midpointBlur(out, radius, border)                  mode ZB_ORDER_MIDPOINT (param ignored)
  *   Image.alphaTrimmedMeanBlur(out, radius, trim, border)    mode ZB_ORDER_ALPHA_TRIMMED, param = trim fraction in [0, 0.5)
  * radius 0 copies; src may alias dst.  Errors in the reference's order: DimensionMismatch, (empty image: ok), InvalidTrim, (radius 0:
- * copy), InvalidPercentile, Unsupported (pixel type; also radius > 31 in this build). */
+ * copy), InvalidPercentile, Unsupported (pixel type; also a window that no longer fits one SM's shared memory: radius beyond ~100 for
+ * Rgba, ~220 for gray). */
 enum { ZB_ORDER_PERCENTILE = 0, ZB_ORDER_MIDPOINT = 1, ZB_ORDER_ALPHA_TRIMMED = 2 };
 int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uint32_t radius, int mode, double param, int border, zb_stream s);
 

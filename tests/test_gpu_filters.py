@@ -242,6 +242,10 @@ def test_order_statistic_large(zb):
     small = np.ascontiguousarray(img[:64, :96])
     dsm = zb.Image.from_numpy(small)
     assert np.array_equal(dsm.percentile_blur(31, 0.37, zb.BorderMode.MIRROR).to_numpy(), zo.order_blur(small, 31, "percentile", 0.37, "mirror"))
+    # radius > 31: the window tile opts in to the SM's full shared memory (the reference has no radius limit)
+    assert np.array_equal(dsm.median_blur(40).to_numpy(), zo.order_blur(small, 40, "percentile", 0.5, "mirror"))
+    rgba = rand_image(rng, (48, 64, 4), np.uint8)
+    assert np.array_equal(zb.Image.from_numpy(rgba).max_blur(60, zb.BorderMode.REPLICATE).to_numpy(), zo.order_blur(rgba, 60, "percentile", 1.0, "replicate"))
     with pytest.raises(zb.ZignalError) as ei:
-        dsm.median_blur(32)
+        dsm.median_blur(400)                                                       # beyond one SM's shared memory
     assert ei.value.name == "Unsupported"

@@ -21,7 +21,7 @@ namespace zb {
 namespace {
 
 constexpr int kTileW = 32, kTileH = 8;
-constexpr int kMaxRadius = 31;
+constexpr int kMaxRadius = 31;   // up to here the tile fits the default 48 KB of shared memory; larger radii opt in to the SM's full carve-out
 
 enum { MODE_PERCENTILE = 0, MODE_MIDPOINT = 1, MODE_ALPHA = 2 };
 
@@ -119,13 +119,21 @@ __global__ void __launch_bounds__(kTileW* kTileH) order_kernel(const OrderParams
     }
 }
 
+template <int CH, int MODE, int RADIUS>
+int launch_kernel(const OrderParams& p, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    if (smem > 48 * 1024) ZB_CUDA(cudaFuncSetAttribute(order_kernel<CH, MODE, RADIUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    order_kernel<CH, MODE, RADIUS><<<grid, block, smem, s>>>(p);
+    return ZB_OK;
+}
 template <int CH, int RADIUS>
 int launch_radius(const OrderParams& p, int mode, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    int rc;
     switch (mode) {
-        case MODE_PERCENTILE: order_kernel<CH, MODE_PERCENTILE, RADIUS><<<grid, block, smem, s>>>(p); break;
-        case MODE_MIDPOINT: order_kernel<CH, MODE_MIDPOINT, RADIUS><<<grid, block, smem, s>>>(p); break;
-        default: order_kernel<CH, MODE_ALPHA, RADIUS><<<grid, block, smem, s>>>(p); break;
+        case MODE_PERCENTILE: rc = launch_kernel<CH, MODE_PERCENTILE, RADIUS>(p, grid, block, smem, s); break;
+        case MODE_MIDPOINT: rc = launch_kernel<CH, MODE_MIDPOINT, RADIUS>(p, grid, block, smem, s); break;
+        default: rc = launch_kernel<CH, MODE_ALPHA, RADIUS>(p, grid, block, smem, s); break;
     }
+    if (rc) return rc;
     ZB_LAUNCHED();
     return ZB_OK;
 }
@@ -134,6 +142,10 @@ template <int CH>
 int launch_mode(const OrderParams& p, int mode, cudaStream_t s) {
     const int tw = kTileW + 2 * p.radius, th = kTileH + 2 * p.radius;
     const size_t smem = (size_t)th * ((tw * CH + 3) & ~3);
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (smem > di.smem_optin) return ZB_ERR_UNSUPPORTED;   // radius beyond ~100 (Rgba) / ~220 (gray): the window no longer fits one SM
     dim3 grid(div_up(p.cols, kTileW), div_up(p.rows, kTileH)), block(kTileW, kTileH);
     switch (g_force_generic.load() ? 0 : p.radius) {     // zb_set_force_generic: the any-radius kernel, as the cross-check of the unrolled ones
         case 1: return launch_radius<CH, 1>(p, mode, grid, block, smem, s);
@@ -160,7 +172,7 @@ extern "C" int zb_order_blur(const zb_image* src, zb_image* dst, int pixfmt, uin
     if (radius == 0) return zb_copy(src, dst, pixfmt, stream);                                   // :43-46 image.copy(out)
     if (mode == ZB_ORDER_PERCENTILE && !(param >= 0.0 && param <= 1.0)) return ZB_ERR_INVALID_PERCENTILE;   // :48-50 (NaN trips the reference's assert)
     if (pixfmt != ZB_PIX_U8 && pixfmt != ZB_PIX_RGB8 && pixfmt != ZB_PIX_RGBA8) return ZB_ERR_UNSUPPORTED;  // :66,74 UnsupportedPixelType
-    if (radius > (uint32_t)kMaxRadius) return ZB_ERR_UNSUPPORTED;
+    if (radius > 4096) return ZB_ERR_UNSUPPORTED;   // (the shared-memory check in launch_mode is the real limit)
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;

@@ -121,7 +121,6 @@ extern "C" int zb_convert(const zb_image* src, int src_pixfmt, zb_image* dst, in
     if (src->rows != dst->rows || src->cols != dst->cols) return ZB_ERR_DIMENSION_MISMATCH;      // image.zig:397
     if (src_pixfmt == dst_pixfmt) return zb_copy(src, dst, src_pixfmt, stream);                  // :398-399
     if (src->rows == 0 || src->cols == 0) return ZB_OK;
-    if (src->rows > 65535) return ZB_ERR_UNSUPPORTED;
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;

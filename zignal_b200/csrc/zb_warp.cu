@@ -55,6 +55,14 @@ struct RotParams {
 // coordinate is bit-identical to the per-pixel formula).  Warp patch: 8 columns x (4 x RPT) rows; CTA tile: 32 x (8 x RPT).
 constexpr int ROT_RPT = 8;   // measured on config 4: 8 rows per thread 1.66 ms / 128 frames, 4 rows 1.74 ms, 1 row 2.33 ms
 
+// The general sampler, out of line: the Rgba8 bilinear fast path of rotate_kernel calls it only for samples that touch the image
+// edge, and keeping eight inlined copies of it out of the unrolled row loop keeps that loop inside the instruction cache.
+template <typename CT, int N, int METHOD, int BORDER_T>
+__device__ __noinline__ void sample_general(const SrcView& img, float src_x, float src_y, const RotParams& p, const float* __restrict__ lut,
+                                            Pix<CT, N>& val) {
+    if (!interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+}
+
 template <typename CT, int N, int METHOD, int BORDER_T>
 __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long long src_image_pitch, CT* __restrict__ dst, size_t dst_stride,
                                                      unsigned long long dst_image_pitch, int dst_rows, int dst_cols, RotParams p,
@@ -116,7 +124,11 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
                 }
             }
         }
-        if (!done && !interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+        if constexpr (kFastRgba8) {
+            if (!done) sample_general<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p, lut, val);
+        } else {
+            if (!interpolate<CT, N, METHOD, BORDER_T>(img, src_x, src_y, p.mb, p.mc, p.border, lut, val)) val = zero_px<CT, N>();
+        }
         store_px<CT, N>(out, 0, val);
         out += dst_stride * N;
     }

@@ -231,8 +231,8 @@ int zb_extract(const zb_image* src, zb_image* dst, int pixfmt, float rect_l, flo
                float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int border, zb_stream s);
 
 /* Image.insert(source, rect, angle, method, .none)   transforms.zig:293-376, the complement of extract: `source` (same pixel type as
- * `self`) is resampled into the rotated rectangle of `self`; pixels outside the rectangle are not touched.  Alpha blending
- * (Blending != .none) and mixed pixel types are not on this path. */
+ * `self`) is resampled into the rotated rectangle of `self`; pixels outside the rectangle are not touched.  (Blend modes:
+ * zb_insert_blend; a source of another pixel type: zb_insert_from.) */
 int zb_insert(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
               float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, zb_stream s);
 /* Image.insert(source, rect, angle, method, blend_mode) with a Blending mode (blending.zig:8-22, enum order): Rgba(u8) samples are
@@ -242,6 +242,12 @@ enum { ZB_BLEND_NONE = 0, ZB_BLEND_NORMAL, ZB_BLEND_MULTIPLY, ZB_BLEND_SCREEN, Z
        ZB_BLEND_COLOR_DODGE, ZB_BLEND_COLOR_BURN, ZB_BLEND_DARKEN, ZB_BLEND_LIGHTEN, ZB_BLEND_DIFFERENCE, ZB_BLEND_EXCLUSION };
 int zb_insert_blend(zb_image* self, const zb_image* source, int pixfmt, float rect_l, float rect_t, float rect_r, float rect_b, float angle,
                     float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int blend_mode, zb_stream s);
+/* Image.insert(source: anytype, ...) with a source of ANOTHER pixel type (transforms.zig:293, image.zig:67-95): samples are taken in the
+ * source's type and converted per pixel with convertColor(DestType, sample); an Rgba(u8) source with a blend mode composites through
+ * Rgba(u8): dest = convertColor(DestType, blend(convertColor(Rgba, dest), sample)).  Equal pixel types forward to zb_insert_blend. */
+int zb_insert_from(zb_image* self, int self_pixfmt, const zb_image* source, int source_pixfmt, float rect_l, float rect_t, float rect_r,
+                   float rect_b, float angle, float cos_a, float sin_a, int method, float mitchell_b, float mitchell_c, int blend_mode,
+                   zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Linear algebra behind fdm / pca

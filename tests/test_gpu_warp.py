@@ -251,3 +251,58 @@ def test_insert_blend_modes(zb):
         import ctypes as C
         check(zb.lib().zb_insert_blend(d._zb(), d._zb(), int(d.pixfmt), C.c_float(0), C.c_float(0), C.c_float(1), C.c_float(1), C.c_float(0),
                                        C.c_float(1), C.c_float(0), 0, C.c_float(0), C.c_float(0), 13, None))
+
+
+def _oracle_insert_mixed(dest, source, rect, angle, method, blend):
+    """Image.insert with a source of another pixel type, composed from oracle pieces exactly as the reference composes it
+    (transforms.zig:293-376 + image.zig:67-95 assignPixel): the SAMPLE every destination pixel receives is what the same-type insert
+    of the source's type writes (two passes over differently filled canvases tell written pixels from untouched ones), then
+    assignPixel: an Rgba(u8) sample with a blend mode composites through Rgba(u8), anything else is convertColor(DestType, sample)."""
+    sfmt, dfmt = zo.pixfmt_of(source), zo.pixfmt_of(dest)
+    shape = dest.shape[:2] + tuple(source.shape[2:])
+    lo = np.zeros(shape, source.dtype)
+    hi = np.full(shape, 255 if source.dtype == np.uint8 else 1.0, source.dtype)
+    s0 = zo.insert(lo, source, rect, angle, method)
+    s1 = zo.insert(hi, source, rect, angle, method)
+    same = (s0 == s1)
+    written = same if same.ndim == 2 else same.all(axis=2)
+    if sfmt == zo.PIX_RGBA8 and blend != "none":
+        base = dest if dfmt == zo.PIX_RGBA8 else zo.convert(dest, zo.PIX_RGBA8)
+        comp = base.copy()
+        for r, c in zip(*np.nonzero(written)):
+            comp[r, c] = zo.blend_rgba8(tuple(int(v) for v in base[r, c]), tuple(int(v) for v in s0[r, c]), blend)
+        conv = comp if dfmt == zo.PIX_RGBA8 else zo.convert(comp, dfmt)
+    else:
+        conv = zo.convert(s0, dfmt)
+    out = dest.copy()
+    out[written] = conv[written]
+    return out
+
+
+_MIX = {"u8": ((24, 30), np.uint8), "f32": ((24, 30), np.float32), "rgb8": ((24, 30, 3), np.uint8), "rgba8": ((24, 30, 4), np.uint8),
+        "rgbaf32": ((24, 30, 4), np.float32)}
+
+
+@pytest.mark.parametrize("src_kind", list(_MIX))
+@pytest.mark.parametrize("dst_kind", list(_MIX))
+def test_insert_source_of_another_pixel_type(zb, src_kind, dst_kind):
+    """Image.insert(source: anytype, ...) (transforms.zig:293): all 20 mixed pairs, rotated + scaled rectangle and the copy fast path,
+    bilinear and bicubic; an Rgba(u8) source also under blend modes.  Bit-exact against the oracle composition."""
+    if src_kind == dst_kind:
+        pytest.skip("same pixel type: test_insert_* above")
+    rng = np.random.default_rng(hash((src_kind, dst_kind)) % 2**32)
+    dshape, ddt = _MIX[dst_kind]
+    dest = rand_image(rng, (40, 52) + tuple(dshape[2:]), ddt)
+    source = rand_image(rng, *_MIX[src_kind])
+    cases = [((6.0, 5.0, 41.0, 33.0), 0.35, "bilinear", "none"), ((10.0, 8.0, 40.0, 32.0), 0.0, "nearest", "none"),      # the second is the copy path
+             ((3.5, 2.0, 30.0, 38.0), -1.1, "bicubic", "none")]
+    if src_kind == "rgba8":
+        cases += [((6.0, 5.0, 41.0, 33.0), 0.35, "bilinear", "normal"), ((2.0, 4.0, 44.0, 30.0), 2.0, "bilinear", "multiply"),
+                  ((10.0, 8.0, 40.0, 32.0), 0.0, "nearest", "screen")]
+    for rect, angle, method, blend in cases:
+        d = zb.Image.from_numpy(dest)
+        d.insert(zb.Image.from_numpy(source), rect, angle, method_enum(zb, method), blend=zb.Blending[blend.upper()])
+        want = _oracle_insert_mixed(dest, source, rect, angle, method, blend)
+        got = d.to_numpy()
+        assert zb.lib().zb_last_kernel().decode() == "insert_mixed"
+        assert np.array_equal(got, want), (rect, angle, method, blend, int(np.count_nonzero(got != want)))

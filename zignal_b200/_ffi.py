@@ -94,6 +94,7 @@ def _declare(L):
         "zb_order_blur": ([img, img, i, u32, i, C.c_double, i, vp], i),
         "zb_insert": ([img, img, i, f, f, f, f, f, f, f, i, f, f, vp], i),
         "zb_insert_blend": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
+        "zb_insert_from": ([img, i, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
         "zb_extract": ([img, img, i, f, f, f, f, f, f, f, i, f, f, i, vp], i),
         "zb_set_border_zero": ([img, i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp], i),
         "zb_conv_separable": ([img, img, i, fp, i, fp, i, i, vp], i),

@@ -397,10 +397,10 @@ class Image:
         composited under a blend mode (blending.zig:26-156); other pixel types are assigned (image.zig:67-95)."""
         a32 = np.float32(angle)
         cos_a, sin_a = np.cos(a32, dtype=np.float32), np.sin(a32, dtype=np.float32)
-        self._peer(source, what="source")
+        self._peer(source, fmt=source.pixfmt, what="source")          # `source: anytype`: any pixel type, same device
         d, s = self._zb(), source._zb()
-        self._run(lib().zb_insert_blend, d, s, int(self.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]), C.c_float(rect[3]),
-                                    C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(blend))
+        self._run(lib().zb_insert_from, d, int(self.pixfmt), s, int(source.pixfmt), C.c_float(rect[0]), C.c_float(rect[1]), C.c_float(rect[2]),
+                  C.c_float(rect[3]), C.c_float(a32), C.c_float(cos_a), C.c_float(sin_a), int(method), C.c_float(b), C.c_float(c), int(blend))
         return self
 
     def crop(self, rect) -> "Image":

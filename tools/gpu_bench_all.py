@@ -93,8 +93,8 @@ f = FeatureDistributionMatching(PixFmt.RGB8)
 si, ti = Image.from_tensor(src), Image.from_tensor(tgt)
 f.set_target(ti)
 f.set_source(si)
-rec("C5 fdm.update 4096^2 Rgb u8 (stats + 3x3 SVD on host + map)", time_it(lambda: f.update(), n=10, warm=2), 150994944, 4096 * 4096,
-    "includes one D2H of 88 B and host SVD between the two kernels")
+rec("C5 fdm.update 4096^2 Rgb u8 (statistics + in-kernel 3x3 solve, map)", time_it(lambda: f.update(), n=20, warm=3), 150994944, 4096 * 4096,
+    "two launches, nothing leaves the device")
 rec("C5 fdm.match (target stats too)", time_it(lambda: f.match(si, ti), n=10, warm=2), 150994944 + 50331648, 4096 * 4096)
 f.deinit()
 del src, tgt
@@ -105,6 +105,35 @@ flops = 2.0 * X.shape[0] * 256 * 256
 r = {"config": "PCA GEMM X^T X, n=1048576 x dim=256 f32 (tcgen05 3xTF32, fp32-accurate)", "ms": ms, "TFLOP_per_s": flops / (ms * 1e-3) / 1e12,
      "kernel": L.zb_last_kernel().decode(), "algorithmic_bytes": 1048576 * 256 * 4, "GB_per_s": 1048576 * 256 * 4 / (ms * 1e-3) / 1e9,
      "note": "useful fp32-accurate flops; 2.25x that is issued as TF32 MMAs (3 products on the upper-triangle tiles); shared-memory operand bandwidth bound"}
+out.append(r)
+print(json.dumps(r), flush=True)
+# the SVD step of Pca.fit: 256 x 256 covariance, one-sided Jacobi on the device; and the end-to-end core of Pca.fit
+mean = torch.empty(256, device="cuda")
+cen = torch.empty_like(X)
+matrix.center_columns(X, mean, True, cen)
+cov = matrix.gemm_device(cen, cen, True, False, 1.0 / (X.shape[0] - 1), 0.0, None)
+ms_svd = time_it(lambda: matrix.svd_device(cov, True, False), n=3, warm=1)
+r = {"config": "SVD 256x256 f32 (one-sided Jacobi, persistent cooperative kernel; PCA covariance)", "ms": ms_svd, "kernel": L.zb_last_kernel().decode(),
+     "note": "latency-bound: 255 rounds x ~8 sweeps, one grid barrier per round"}
+out.append(r)
+print(json.dumps(r), flush=True)
+
+
+def fit():
+    matrix.center_columns(X, mean, True, cen)
+    matrix.svd_device(matrix.gemm_device(cen, cen, True, False, 1.0 / (X.shape[0] - 1), 0.0, None), True, False)
+
+
+r = {"config": "Pca.fit device core (column means + centring + X^T X + SVD), n=1048576 x dim=256 f32", "ms": time_it(fit, n=3, warm=1),
+     "kernel": L.zb_last_kernel().decode()}
+out.append(r)
+print(json.dumps(r), flush=True)
+a64 = np.random.default_rng(0).standard_normal((200, 200))
+a64 = (a64 + a64.T) / 2
+import time
+t0 = time.perf_counter()
+matrix.eigh(a64)
+r = {"config": "Matrix.eigh 200x200 f64 (two-sided Jacobi, host pointers in and out)", "ms": (time.perf_counter() - t0) * 1e3, "kernel": L.zb_last_kernel().decode()}
 out.append(r)
 print(json.dumps(r), flush=True)
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)

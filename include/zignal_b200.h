@@ -395,6 +395,8 @@ int zb_set_force_generic(int on);
 int zb_tune(const char* key, int value);
 /* Name of the kernel variant the last zb_conv_separable call selected on this thread. */
 const char* zb_last_kernel(void);
+/* Jacobi sweeps the last zb_svd_* / zb_eigh_* call on this thread needed (60 = the limit: not converged). */
+int zb_last_sweeps(void);
 
 #ifdef __cplusplus
 }

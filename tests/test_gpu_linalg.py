@@ -29,6 +29,7 @@ def test_svd_device_kernel_vs_oracle(zb, dtype, shape, mode):
     a = (rng.standard_normal(shape) @ np.diag(np.logspace(0, -3, shape[1]))).astype(dtype)    # graded spectrum
     u, s, v, conv = _svd_prod(a, mode, True)
     assert conv == 0 and zb.lib().zb_last_kernel().decode() == "jacobi_svd_onesided"
+    assert zb.lib().zb_last_sweeps() <= 20, zb.lib().zb_last_sweeps()          # quadratic convergence, not the sweep limit
     _check_svd_against_oracle(a, u, s, v, mode)
 
 
@@ -71,6 +72,7 @@ def test_eigh_device_kernel_vs_oracle(zb, dtype, n):
     a = ((a + a.T) * dtype(0.5)).astype(dtype)
     vals, vecs = zb.matrix.eigh(a)
     assert zb.lib().zb_last_kernel().decode() == "jacobi_eigh_twosided"
+    assert zb.lib().zb_last_sweeps() <= 20, zb.lib().zb_last_sweeps()
     ovals, ovecs = zo.eigh(a)
     eps = np.finfo(dtype).eps
     norm = float(np.linalg.norm(a.astype(np.float64), 2))

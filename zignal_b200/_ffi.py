@@ -65,6 +65,7 @@ def _declare(L):
         "zb_status_name": ([i], C.c_char_p),
         "zb_last_error": ([], C.c_char_p),
         "zb_last_kernel": ([], C.c_char_p),
+        "zb_last_sweeps": ([], i),
         "zb_device_count": ([P(i)], i),
         "zb_set_device": ([i], i),
         "zb_get_device": ([P(i)], i),

@@ -257,8 +257,12 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
         }
     }
     __syncthreads();
-    if (tid == 0)
-        for (int i = 0; i < STAGES; ++i) produce();   // the first bands do not touch the halo: the pipeline fills while the copy runs
+    // With three or more bands the first chunks of every CTA touch no halo row, so the pipeline fills while the copy below runs.
+    // With fewer, a first chunk may need the halo, and waiting for `halo_landed` before this CTA has contributed its own slice
+    // would deadlock: fill the pipeline after the prologue instead.
+    const bool fill_first = !SHARD || p.n_bands >= 3;
+    if (tid == 0 && fill_first)
+        for (int i = 0; i < STAGES; ++i) produce();
     if constexpr (SHARD) {
         // ---- prologue: this CTA's slice of the neighbours' edge rows -> my halo rows (plain loads over NVLink, all issued before
         // the first use so the round trips overlap) ----
@@ -289,6 +293,7 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             for (int k = 0; k < BATCH; ++k)
                 if (dstp[k]) *dstp[k] = v[k];
         }
+        asm volatile("fence.proxy.async;" ::: "memory");   // these generic-proxy stores are read by TMA (async proxy) later on
         __syncthreads();
         if (tid == 0) {
             ShardCtrl* me = sp->link.self;
@@ -301,6 +306,8 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
                 if (sp->up_rows) st_release_sys(&sp->link.up->done_from[1], sp->link.epoch);
                 if (sp->down_rows) st_release_sys(&sp->link.down->done_from[0], sp->link.epoch);
             }
+            if (!fill_first)
+                for (int i = 0; i < STAGES; ++i) produce();
         }
     }
 

@@ -36,6 +36,7 @@ namespace {
 
 constexpr uint32_t kDeviceMinN = 24;   // below this the host runs the same algorithm
 constexpr int kMaxSweeps = 60;
+thread_local int t_last_sweeps = 0;    // sweeps the last decomposition on this thread needed (zb_last_sweeps)
 
 // ---- shared rotation math ----------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -315,11 +316,18 @@ __global__ void __launch_bounds__(256) identity_kernel(T* __restrict__ v, int n)
     v[t] = (t / n == t % n) ? (T)1 : (T)0;
 }
 
+// Two columns stored in T count as orthogonal when |a_p . a_q| <= sqrt(m) eps |a_p| |a_q|: that is the size of the rounding noise
+// their m stored products carry (the criterion of LAPACK's xGESVJ); asking for less only rotates noise until the sweep limit.
+template <typename T>
+double jacobi_tol(int m) {
+    return std::sqrt((double)(m > 1 ? m : 1)) * (double)std::numeric_limits<T>::epsilon();
+}
+
 // ---- host twins of the same algorithm (tiny matrices) --------------------------------------------------------------
 template <typename T>
 int svd_jacobi_host(std::vector<T>& Gt, std::vector<T>& Vt, int m, int n, bool with_v, double abs_floor) {
     const int np = n + (n & 1);
-    const double tol = (double)std::numeric_limits<T>::epsilon();
+    const double tol = jacobi_tol<T>(m);
     int sweep = 0;
     for (; sweep < kMaxSweeps; ++sweep) {
         unsigned rot = 0;
@@ -430,7 +438,7 @@ int svd_jacobi_device(T* dGt, T* dVt, int m, int n, bool with_v, double abs_floo
     else rc = cooperative_grid(jacobi_svd_kernel<T, NT>, NT, pairs, &grid);
     if (rc) return rc;
     int wv = with_v ? 1 : 0;
-    double tol = (double)std::numeric_limits<T>::epsilon();
+    double tol = jacobi_tol<T>(m);
     unsigned int* bc = w.barrier();
     unsigned int* rots = w.rotations();
     int* sw = w.sweeps();
@@ -508,6 +516,7 @@ int svd_entry(const T* a, uint32_t m, uint32_t n, int mode, int with_v, T* u, T*
         if (with_v) ZB_CUDA(cudaMemcpyAsync(Vt.data(), dv.p, Vt.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
         ZB_CUDA(cudaStreamSynchronize(st));
     }
+    t_last_sweeps = sweeps;
     if (sweeps >= kMaxSweeps && converged) *converged = 1;   // svd.zig:79: index of the value that failed (any non-zero = failure)
     // singular values, descending order (svd.zig:463-496)
     std::vector<double> sig(n);
@@ -570,6 +579,7 @@ int svd_device_entry(const T* d_a, uint32_t m, uint32_t n, T* d_u, T* d_s, T* d_
     const double eps_t = (double)std::numeric_limits<T>::epsilon();
     int sweeps = 0;
     if ((rc = svd_jacobi_device<T>(dg.as<T>(), dv.as<T>(), (int)m, (int)n, d_v != nullptr, (double)n * eps_t * eps_t * frob2, &sweeps, st))) return rc;
+    t_last_sweeps = sweeps;
     if (sweeps >= kMaxSweeps && converged) *converged = 1;
     column_norms_kernel<T><<<n, 128, 0, st>>>(dg.as<T>(), (int)m, (int)n, dn.as<double>());
     ZB_LAUNCHED();
@@ -622,10 +632,12 @@ int eigh_entry(const T* a, uint32_t rows, uint32_t cols, T* values, T* vectors) 
             A[(size_t)i * n + j] = x;
             frob += (double)x * (double)x;
         }
-    const double tiny = std::sqrt(frob) * (double)eps * (double)eps;
+    // the reference stops when the off-diagonal Frobenius norm^2 <= |A|_F^2 eps^2 (eigen.zig:64-72); an entry below eps |A|_F / n can
+    // no longer lift it above that, and rotating it would only feed rounding noise back in
+    const double tiny = std::sqrt(frob) * (double)eps / (double)n;
     for (uint32_t i = 0; i < n; ++i) Vt[(size_t)i * n + i] = 1;
     if (n < kDeviceMinN) {
-        eigh_jacobi_host<T>(A, Vt, (int)n, tiny);
+        t_last_sweeps = eigh_jacobi_host<T>(A, Vt, (int)n, tiny);
     } else {
         constexpr int NT = 128;
         DeviceInfo di;
@@ -657,6 +669,7 @@ int eigh_entry(const T* a, uint32_t rows, uint32_t cols, T* values, T* vectors) 
         ZB_LAUNCHED();
         ZB_CUDA(cudaMemcpyAsync(A.data(), da.p, nn * sizeof(T), cudaMemcpyDeviceToHost, st));
         ZB_CUDA(cudaMemcpyAsync(Vt.data(), dv.p, nn * sizeof(T), cudaMemcpyDeviceToHost, st));
+        ZB_CUDA(cudaMemcpyAsync(&t_last_sweeps, sw, sizeof(int), cudaMemcpyDeviceToHost, st));
         ZB_CUDA(cudaStreamSynchronize(st));
         t_last_kernel = "jacobi_eigh_twosided";
     }
@@ -677,6 +690,8 @@ int eigh_entry(const T* a, uint32_t rows, uint32_t cols, T* values, T* vectors) 
 using namespace zb;
 
 extern "C" {
+
+int zb_last_sweeps(void) { return t_last_sweeps; }
 
 int zb_svd_f64(const double* a, uint32_t m, uint32_t n, int mode, int with_v, double* u, double* s, double* v, uint64_t* converged) {
     return svd_entry<double>(a, m, n, mode, with_v, u, s, v, converged);

@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(256) rotate_kernel(SrcView img, unsigned long 
             if (fast_ok && fabsf(src_x) < 2097152.0f && fabsf(src_y) < 2097152.0f) {
                 const int ix = __float2int_rd(src_x * 512.0f), iy = __float2int_rd(src_y * 512.0f);
                 const int left = ix >> 9, top = iy >> 9;
-                if ((unsigned)left < (unsigned)(img.cols - 1) && (unsigned)top < (unsigned)(img.rows - 1)) {   // all four neighbours inside
+                if (BORDER_T == ZB_BORDER_ZERO && (left < -1 || left >= img.cols || top < -1 || top >= img.rows)) {
+                    val.u = 0u;   // all four neighbours outside: .zero makes the sample 0 (the margin lanes of a partly covered strip)
+                    done = true;
+                } else if ((unsigned)left < (unsigned)(img.cols - 1) && (unsigned)top < (unsigned)(img.rows - 1)) {   // all four neighbours inside
                     const unsigned fx = (unsigned)((ix & 511) + 1) >> 1, fy = (unsigned)((iy & 511) + 1) >> 1;
                     const uint32_t* q = reinterpret_cast<const uint32_t*>(img.data) + (unsigned)top * (unsigned)img.stride + (unsigned)left;
                     const uint32_t* q2 = q + (unsigned)img.stride;

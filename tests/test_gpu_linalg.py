@@ -76,10 +76,11 @@ def test_eigh_device_kernel_vs_oracle(zb, dtype, n):
     ovals, ovecs = zo.eigh(a)
     eps = np.finfo(dtype).eps
     norm = float(np.linalg.norm(a.astype(np.float64), 2))
-    assert np.max(np.abs(vals.astype(np.float64) - ovals.astype(np.float64))) <= 64 * eps * norm
+    # two Jacobi variants in the same precision: each is backward stable to O(n eps |A|), so that is how far apart they may be
+    assert np.max(np.abs(vals.astype(np.float64) - ovals.astype(np.float64))) <= 8 * n * eps * norm
     v64 = vecs.astype(np.float64)
-    assert np.allclose(v64.T @ v64, np.eye(n), atol=400 * eps * np.sqrt(n))
-    assert np.allclose(v64 @ np.diag(vals.astype(np.float64)) @ v64.T, a, atol=400 * eps * norm)
+    assert np.allclose(v64.T @ v64, np.eye(n), atol=8 * n * eps)
+    assert np.allclose(v64 @ np.diag(vals.astype(np.float64)) @ v64.T, a, atol=8 * n * eps * norm)
     assert np.all(np.diff(vals) >= 0)
     for i in range(n):
         gap = min(abs(ovals[i] - ovals[j]) for j in range(n) if j != i)

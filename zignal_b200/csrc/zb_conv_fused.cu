@@ -257,10 +257,15 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
         }
     }
     __syncthreads();
-    // With three or more bands the first chunks of every CTA touch no halo row, so the pipeline fills while the copy below runs.
-    // With fewer, a first chunk may need the halo, and waiting for `halo_landed` before this CTA has contributed its own slice
-    // would deadlock: fill the pipeline after the prologue instead.
-    const bool fill_first = !SHARD || p.n_bands >= 3;
+    // Normally the first chunks of a CTA touch no halo row (the halo bands come last), so the pipeline fills while the copy below
+    // runs.  On a small block a CTA's first unit can be a halo band: waiting for `halo_landed` before this CTA has contributed its
+    // own slice would deadlock, so such a CTA fills its pipeline after the prologue instead.
+    bool fill_first = true;
+    if constexpr (SHARD) {
+        int b0 = blockIdx.x / p.n_strips;   // the band of this CTA's first unit (a unit has >= 10 chunks: only it matters here)
+        b0 = b0 + 1 == p.n_bands ? 0 : b0 + 1;
+        fill_first = blockIdx.x < n_units && !((b0 == 0 && sp->up_rows) || (b0 == p.n_bands - 1 && sp->down_rows));
+    }
     if (tid == 0 && fill_first)
         for (int i = 0; i < STAGES; ++i) produce();
     if constexpr (SHARD) {

@@ -52,6 +52,8 @@ struct U8Params {
     int ky[MAXK];
     float kxf[MAXK];  // the same Q8 taps as floats (FMATH variant)
     float kyf[MAXK];  // ky_q8 / 65536: the vertical sums come out as acc / 65536 (exact), ready for round_clamp_byte
+    unsigned kx4[5];  // DP variant: horizontal taps packed four bytes per word (tap 4q + b in byte b), zero beyond the kernel
+    unsigned ky4[5];  // DP variant: vertical taps likewise; dp2a.lo reads bytes 0,1 (taps 4q, 4q+1), dp2a.hi bytes 2,3
     const uint32_t* src;
     uint32_t* dst;
     unsigned long long src_pitch_px, dst_pitch_px;
@@ -317,6 +319,211 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
     }
 }
 
+
+// ================================================================================================
+// DP variant: the same single-pass structure on the integer dot-product instructions.
+// When every Q8 tap is a byte (0 .. 255: every kernel with non-negative taps -- Gaussian, box, motion blur) and the horizontal
+// sums fit 16 bits (255 * sum(kx) <= 65535), the reference's integer arithmetic maps onto
+//   horizontal  dp4a: the 4 pixels of a group are byte-transposed into one word per channel, a window of 4 consecutive
+//               bytes at any offset is one funnel shift, and 4 taps are ONE instruction (15 taps: 4 dp4a instead of 15 FMAs);
+//   vertical    dp2a: the horizontal sums of two consecutive rows share a register (lo / hi 16 bits) and 2 taps are one
+//               instruction (15 taps: 8 dp2a); the pair registers for odd rows are one PRMT from the even ones.
+// The ring holds u16 sums (8 B per pixel instead of 16), so two CTAs fit an SM.  Integer sums are order-independent: the results
+// are the reference's bits, like the FFMA / IMAD variants (which remain for kernels with negative or larger taps).
+// ================================================================================================
+constexpr int DP_RING_ROW_BYTES = TW * 8;                       // 2048
+constexpr int DP_RING_BYTES = RING_ROWS * DP_RING_ROW_BYTES;     // 49152
+constexpr int DP_SMEM_BYTES = NSTAGE * STAGE_BYTES + DP_RING_BYTES + 64 + 1024;
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+// 16-byte chunk c of a ring row (2 pixels) lives at chunk c ^ ((c >> 3) & 3): the horizontal pass writes 4 consecutive chunks per
+// lane (64-byte lane stride), which without the swizzle would hit two bank groups from eight lanes
+__device__ __forceinline__ uint32_t dp_chunk(uint32_t c) { return c ^ ((c >> 3) & 3u); }
+
+template <int HALF>
+__global__ void __launch_bounds__(NTHREADS, 2) fused_sep_rgba8_dp_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ U8Params p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int NLOAD = CHUNK + 2 * HALF;   // rows a vertical window block reads
+    constexpr int NW = (K + 3) / 4;           // tap words of the horizontal pass
+    constexpr int NP = HALF + 1;              // tap pairs of the vertical pass
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = smem0 + NSTAGE * STAGE_BYTES;
+    const uint32_t bar0 = ring + DP_RING_BYTES;
+    const int tid = threadIdx.x;
+    const int n_units = p.n_strips * p.n_bands;
+
+    int pu = blockIdx.x, pi = 0;
+    uint32_t pcount = 0;
+    auto produce = [&]() {
+        if (pu >= n_units) return;
+        const int band = pu / p.n_strips, strip = pu - band * p.n_strips;
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
+        const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
+        const uint32_t st = pcount % NSTAGE;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar0 + 8 * st, STAGE_BYTES);
+        tma_load_2d(smem0 + st * STAGE_BYTES, &tmap, strip * TW - PAD, ra - CHUNK + CHUNK * pi, bar0 + 8 * st);
+        tma_load_2d(smem0 + st * STAGE_BYTES + BLOCK_BYTES, &tmap, strip * TW - PAD + BW, ra - CHUNK + CHUNK * pi, bar0 + 8 * st);
+        ++pcount;
+        if (++pi == n_in) { pi = 0; pu += gridDim.x; }
+    };
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(bar0 + 8 * i, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < NSTAGE; ++i) produce();
+
+    const int ht = tid & 31, hr = tid >> 5;
+    const int vx = tid;
+    const uint32_t v_off = dp_chunk((uint32_t)vx >> 1) * 16u + ((uint32_t)vx & 1u) * 8u;
+    uint32_t ccount = 0;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int band = unit / p.n_strips, strip = unit - band * p.n_strips;
+        const int x0 = strip * TW;
+        const int ra = p.row0 + band * p.band_rows;
+        const int rb = min(ra + p.band_rows, p.row1);
+        const int n_out = (rb - ra + CHUNK - 1) / CHUNK;
+        const int n_in = n_out + 2;
+        const int xs0 = x0 - PAD;
+
+        for (int i = 0; i < n_in; ++i, ++ccount) {
+            const uint32_t st = ccount % NSTAGE;
+            const uint32_t stage = smem0 + st * STAGE_BYTES;
+            while (!mbar_try_wait(bar0 + 8 * st, (ccount / NSTAGE) & 1u)) {}
+            const int y0 = ra - CHUNK + CHUNK * i;
+            const bool fix_r = p.fix && (y0 < 0 || y0 + CHUNK > p.rows);
+            const bool fix_x = p.fix && (xs0 < 0 || xs0 + SW > p.cols);
+            if (fix_r || fix_x) {
+                fixup_stage_u8(stage, y0, xs0, fix_x, fix_r, p);
+                __syncthreads();
+            }
+            // ---------------- H(i): 8 outputs of row hr, pixels [8 ht, 8 ht + 8) ----------------
+            {
+                uint32_t w[24];   // pixels [8 ht - 8, 8 ht + 16) of the strip
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int4 v = lds128_i(stage_px(stage, hr, PAD - 8 + 8 * ht + 4 * q));
+                    w[4 * q + 0] = (uint32_t)v.x; w[4 * q + 1] = (uint32_t)v.y; w[4 * q + 2] = (uint32_t)v.z; w[4 * q + 3] = (uint32_t)v.w;
+                }
+                // byte transpose: P[c][g] = channel c of pixels 4g .. 4g + 3; P[c][6] = 0 pads the 17-tap window
+                uint32_t P[4][7];
+#pragma unroll
+                for (int g = 0; g < 6; ++g) {
+                    const uint32_t rg01 = __byte_perm(w[4 * g], w[4 * g + 1], 0x5140), rg23 = __byte_perm(w[4 * g + 2], w[4 * g + 3], 0x5140);
+                    const uint32_t ba01 = __byte_perm(w[4 * g], w[4 * g + 1], 0x7362), ba23 = __byte_perm(w[4 * g + 2], w[4 * g + 3], 0x7362);
+                    P[0][g] = __byte_perm(rg01, rg23, 0x5410);
+                    P[1][g] = __byte_perm(rg01, rg23, 0x7632);
+                    P[2][g] = __byte_perm(ba01, ba23, 0x5410);
+                    P[3][g] = __byte_perm(ba01, ba23, 0x7632);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) P[c][6] = 0u;
+                uint32_t hsum[4][8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int start = 8 - HALF + o;   // byte of P[c] where output o's window begins
+                        const int sh = start & 3, j0 = start >> 2;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int q = 0; q < NW; ++q) {
+                            const uint32_t win = sh == 0 ? P[c][j0 + q] : __funnelshift_r(P[c][j0 + q], P[c][j0 + q + 1], 8 * sh);
+                            acc = __dp4a(win, p.kx4[q], acc);
+                        }
+                        hsum[c][o] = acc;   // <= 255 * sum(kx) <= 65535
+                    }
+                }
+                // 2 pixels per 16-byte chunk: (c0 | c1 << 16, c2 | c3 << 16) per pixel
+                const uint32_t rrow = ring + (uint32_t)(((i % 3) * CHUNK + hr) * DP_RING_ROW_BYTES);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int4 v;
+                    v.x = (int)__byte_perm(hsum[0][2 * q], hsum[1][2 * q], 0x5410);
+                    v.y = (int)__byte_perm(hsum[2][2 * q], hsum[3][2 * q], 0x5410);
+                    v.z = (int)__byte_perm(hsum[0][2 * q + 1], hsum[1][2 * q + 1], 0x5410);
+                    v.w = (int)__byte_perm(hsum[2][2 * q + 1], hsum[3][2 * q + 1], 0x5410);
+                    sts128_i(rrow + dp_chunk((uint32_t)(4 * ht + q)) * 16u, v);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) produce();
+            // ---------------- V(i-2): 8 output rows of pixel column vx ----------------
+            if (i >= 2) {
+                const int c = i - 2;
+                const uint32_t cbase = (uint32_t)((c % 3) * CHUNK);
+                uint32_t w01[NLOAD], w23[NLOAD];   // (c0 | c1 << 16), (c2 | c3 << 16) of window rows 0 .. NLOAD - 1
+#pragma unroll
+                for (int j = 0; j < NLOAD; ++j) {
+                    uint32_t sr = cbase + (uint32_t)(8 - HALF + j);
+                    if (sr >= RING_ROWS) sr -= RING_ROWS;
+                    const uint2 v = lds64(ring + sr * (uint32_t)DP_RING_ROW_BYTES + v_off);
+                    w01[j] = v.x;
+                    w23[j] = v.y;
+                }
+                uint32_t outpx[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) outpx[o] = 0u;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    // pair registers: E[m] = (row 2m, row 2m + 1), O[m] = (row 2m + 1, row 2m + 2) of this channel
+                    const uint32_t sel = (ch & 1) ? 0x7632u : 0x5410u;
+                    uint32_t E[HALF + 4], O[HALF + 4];
+#pragma unroll
+                    for (int m = 0; m < HALF + 4; ++m) {
+                        constexpr int last = NLOAD - 1;
+                        const int r0 = 2 * m, r1 = 2 * m + 1, r2 = (2 * m + 2) > last ? last : (2 * m + 2);   // a row beyond the window only meets a zero tap
+                        const uint32_t a0 = ch < 2 ? w01[r0] : w23[r0], a1 = ch < 2 ? w01[r1] : w23[r1], a2 = ch < 2 ? w01[r2] : w23[r2];
+                        E[m] = __byte_perm(a0, a1, sel);
+                        O[m] = __byte_perm(a1, a2, sel);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int t = 0; t < NP; ++t) {
+                            const uint32_t pr = (o & 1) ? O[(o - 1) / 2 + t] : E[o / 2 + t];   // rows (o + 2t, o + 2t + 1)
+                            acc = (t & 1) ? __dp2a_hi(pr, p.ky4[t >> 1], acc) : __dp2a_lo(pr, p.ky4[t >> 1], acc);
+                        }
+                        // divClampU8(65536) for acc >= 0: trunc((acc + 32768) / 65536), at most 255.99.. -> clamp
+                        const uint32_t q = min((acc + 32768u) >> 16, 255u);
+                        outpx[o] |= q << (8 * ch);
+                    }
+                }
+                const int x = x0 + vx;
+                if (x < p.cols) {
+                    const int yb = ra + CHUNK * c;
+                    uint32_t* out = p.dst + (size_t)yb * p.dst_pitch_px + x;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o)
+                        if (yb + o < rb) __stcs(out + (size_t)o * p.dst_pitch_px, outpx[o]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int HALF>
+int launch_u8_dp(const CUtensorMap& tmap, const U8Params& p, int n_units, int sm_count, cudaStream_t s) {
+    auto k = fused_sep_rgba8_dp_kernel<HALF>;
+    ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES));
+    const int grid = n_units < 2 * sm_count ? n_units : 2 * sm_count;   // two persistent CTAs per SM
+    k<<<grid, NTHREADS, DP_SMEM_BYTES, s>>>(tmap, p);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
 template <int HALF>
 int launch_u8(const CUtensorMap& tmap, const U8Params& p, int grid, bool fmath, cudaStream_t s) {
     auto k = fmath ? fused_sep_rgba8_kernel<HALF, true> : fused_sep_rgba8_kernel<HALF, false>;
@@ -386,6 +593,29 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
     }
     const int n_units = p.n_strips * p.n_bands;
     const int grid = n_units < di.sm_count ? n_units : di.sm_count;
+    // DP variant: every tap a byte (non-negative), horizontal sums within 16 bits
+    bool dp = g_tune_u8_dp.load() != 0 && sax * 255 <= 65535;
+    for (int i = 0; i < MAXK && dp; ++i) dp = p.kx[i] >= 0 && p.kx[i] <= 255 && p.ky[i] >= 0 && p.ky[i] <= 255;
+    if (dp) {
+        for (int q = 0; q < 5; ++q) {
+            p.kx4[q] = p.ky4[q] = 0;
+            for (int b = 0; b < 4; ++b) {
+                const int t = 4 * q + b;
+                if (t < MAXK) { p.kx4[q] |= (unsigned)p.kx[t] << (8 * b); p.ky4[q] |= (unsigned)p.ky[t] << (8 * b); }
+            }
+        }
+        t_last_kernel = "fused_sep_rgba8_dp";
+        switch (half) {
+            case 1: return launch_u8_dp<1>(tmap, p, n_units, di.sm_count, s);
+            case 2: return launch_u8_dp<2>(tmap, p, n_units, di.sm_count, s);
+            case 3: return launch_u8_dp<3>(tmap, p, n_units, di.sm_count, s);
+            case 4: return launch_u8_dp<4>(tmap, p, n_units, di.sm_count, s);
+            case 5: return launch_u8_dp<5>(tmap, p, n_units, di.sm_count, s);
+            case 6: return launch_u8_dp<6>(tmap, p, n_units, di.sm_count, s);
+            case 7: return launch_u8_dp<7>(tmap, p, n_units, di.sm_count, s);
+            case 8: return launch_u8_dp<8>(tmap, p, n_units, di.sm_count, s);
+        }
+    }
     t_last_kernel = fmath ? "fused_sep_rgba8_f" : "fused_sep_rgba8";
     switch (half) {
         case 1: return launch_u8<1>(tmap, p, grid, fmath, s);

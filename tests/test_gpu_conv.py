@@ -21,6 +21,13 @@ def zb():
     zb.lib().zb_set_force_generic(0)
 
 
+def _dp_eligible(kx, ky):
+    """The dp4a / dp2a variant of the Rgba8 kernel takes kernels whose Q8 taps are bytes and whose horizontal sums fit 16 bits."""
+    qx = np.round(np.asarray(kx, np.float32) * np.float32(256)).astype(np.int64)
+    qy = np.round(np.asarray(ky, np.float32) * np.float32(256)).astype(np.int64)
+    return bool(qx.min() >= 0 and qx.max() <= 255 and qy.min() >= 0 and qy.max() <= 255 and int(qx.sum()) * 255 <= 65535)
+
+
 def _taps(rng, n):
     k = (rng.random(n) + 0.05).astype(np.float32)
     return (k / k.sum()).astype(np.float32)
@@ -109,12 +116,17 @@ def test_fused_rgba8_bit_exact(zb, rows, cols, border):
         img = rand_image(rng, (rows, cols, 4), np.uint8)
         for k in (_taps(rng, 2 * half + 1), (rng.standard_normal(2 * half + 1) * 0.4).astype(np.float32)):  # positive and signed taps
             want = zo.conv_separable(img, k, k, border)
-            for fmath in (1, 0):  # exact-integer pipeline on FFMA (when provably exact) and on IMAD
+            # three pipelines, one result: dp4a / dp2a (byte taps only), exact integers on FFMA (when provably exact), IMAD
+            for dp, fmath in ((1, 1), (0, 1), (0, 0)):
+                L.zb_tune(b"conv.u8_dp", dp)
                 L.zb_tune(b"conv.u8_fmath", fmath)
                 got = zb.Image.from_numpy(img).convolve_separable(k, k, border_enum(zb, border)).to_numpy()
-                assert L.zb_last_kernel().decode().startswith("fused_sep_rgba8"), L.zb_last_kernel().decode()
-                assert np.array_equal(got, want), (half, fmath, L.zb_last_kernel().decode())
+                name = L.zb_last_kernel().decode()
+                assert name.startswith("fused_sep_rgba8"), name
+                assert (name == "fused_sep_rgba8_dp") == bool(dp and _dp_eligible(k, k)), (name, dp)
+                assert np.array_equal(got, want), (half, dp, fmath, name)
     L.zb_tune(b"conv.u8_fmath", 1)
+    L.zb_tune(b"conv.u8_dp", 1)
 
 
 def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
@@ -128,7 +140,7 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     ov = out_big.view(zb.Rectangle(3, 2, 287, 187))
     kx, ky = _taps(rng, 6), _taps(rng, 15)
     v.convolve_separable(kx, ky, zb.BorderMode.MIRROR, out=ov)
-    assert L.zb_last_kernel().decode() == "fused_sep_rgba8_f"
+    assert L.zb_last_kernel().decode() == ("fused_sep_rgba8_dp" if _dp_eligible(kx, ky) else "fused_sep_rgba8_f")
     full = out_big.to_numpy()
     assert np.array_equal(full[2:187, 3:287], zo.conv_separable(crop, kx, ky, "mirror"))
     mask = np.ones(full.shape[:2], bool)
@@ -145,7 +157,8 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     assert np.array_equal(got, zo.conv_separable(img, huge, huge, "mirror"))
     for sigma in (0.5, 1.0, 2.25):
         got = big.gaussian_blur(sigma).to_numpy()
-        assert L.zb_last_kernel().decode() == "fused_sep_rgba8_f"
+        g = zb.gaussian_taps(sigma)
+        assert L.zb_last_kernel().decode() == ("fused_sep_rgba8_dp" if _dp_eligible(g, g) else "fused_sep_rgba8_f")
         assert np.array_equal(got, zo.gaussian_blur(img, sigma)), sigma
 
 

@@ -4,6 +4,8 @@ tag=${1:-r02c}
 o=gpurun_out; mkdir -p $o
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 600 $TR --nproc-per-node 2 --master-port 29511 tools/gpu_shard_check.py > $o/${tag}_shard_check_n2.log 2>&1; echo "shard check rc=$?"; grep -E "MISMATCH|shard check|Error|error" $o/${tag}_shard_check_n2.log | head
+timeout 300 $TR --nproc-per-node 2 --master-port 29513 tools/gpu_shard_diag.py 8192 > $o/${tag}_shard_diag.log 2>&1; grep "rank" $o/${tag}_shard_diag.log
+timeout 300 $TR --nproc-per-node 2 --master-port 29514 tools/gpu_shard_diag.py 4096 >> $o/${tag}_shard_diag.log 2>&1; grep "rank" $o/${tag}_shard_diag.log | tail -2
 timeout 1500 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 $o/${tag}_pytest_gpu.log
 timeout 600 python bench.py --steps 100 > $o/${tag}_bench_n1.json 2> $o/${tag}_bench_n1.err; echo "bench n1 rc=$?"; cut -c1-200 $o/${tag}_bench_n1.json; tail -3 $o/${tag}_bench_n1.err
 timeout 600 $TR --nproc-per-node 2 --master-port 29512 bench.py --gpus 2 --steps 100 > $o/${tag}_bench_n2.json 2> $o/${tag}_bench_n2.err; echo "bench n2 rc=$?"; cut -c1-200 $o/${tag}_bench_n2.json; tail -3 $o/${tag}_bench_n2.err

@@ -53,6 +53,9 @@ def test_gaussian_taps_match_oracle_bit_for_bit():
     assert zb.gaussian_taps(0.0).size == 0
     n = C.c_int()
     assert zb.lib().zb_gaussian_taps(C.c_float(-1.0), None, 0, C.byref(n)) == 2  # InvalidSigma
+    for bad in (float("inf"), float("nan")):     # image.zig:973 would panic on the usize cast; an error code here, no huge allocation
+        assert zb.lib().zb_gaussian_taps(C.c_float(bad), None, 0, C.byref(n)) == 2, bad
+    assert zb.lib().zb_gaussian_taps(C.c_float(1e30), None, 0, C.byref(n)) != 0
 
 
 def test_rotate_bounds_match_oracle():

@@ -59,6 +59,10 @@ int conv_separable_dispatch(const zb_image* src, zb_image* dst, int pixfmt, cons
 
 // image.zig:972-990
 int gaussian_taps_host(float sigma, std::vector<float>& taps) {
+    // image.zig:973 casts ceil(3 sigma) to usize: a NaN / infinite sigma is a panic there, an error code here; a radius beyond 2^24
+    // could not be allocated either (and no kernel of this build takes it)
+    if (!std::isfinite(sigma)) return ZB_ERR_INVALID_SIGMA;
+    if (3.0f * sigma > 16777216.0f) return ZB_ERR_UNSUPPORTED;
     const size_t radius = (size_t)std::ceil(3.0f * sigma);
     const size_t n = 2 * radius + 1;
     taps.resize(n);
@@ -188,7 +192,7 @@ int zb_gaussian_taps(float sigma, float* taps, int cap, int* n) {
     if (sigma == 0) { *n = 0; return ZB_OK; }
     if (!(sigma > 0)) return ZB_ERR_INVALID_SIGMA;
     std::vector<float> t;
-    gaussian_taps_host(sigma, t);
+    if (int rc = gaussian_taps_host(sigma, t)) return rc;
     *n = (int)t.size();
     if (!taps || cap < (int)t.size()) return ZB_ERR_INVALID_ARGUMENT;
     memcpy(taps, t.data(), t.size() * sizeof(float));
@@ -226,7 +230,7 @@ int zb_gaussian_blur(const zb_image* src, zb_image* dst, int pixfmt, float sigma
     if (sigma == 0) return zb_copy(src, dst, pixfmt, s);   // image.zig:966
     if (!(sigma > 0)) return ZB_ERR_INVALID_SIGMA;         // image.zig:970
     std::vector<float> taps;
-    gaussian_taps_host(sigma, taps);
+    if ((rc = gaussian_taps_host(sigma, taps))) return rc;
     return conv_separable_dispatch(src, dst, pixfmt, taps.data(), (int)taps.size(), taps.data(), (int)taps.size(), ZB_BORDER_MIRROR,
                                    (cudaStream_t)s);     // image.zig:993
 }
@@ -259,7 +263,7 @@ int zb_host_gaussian_blur(const zb_image* src, zb_image* dst, int pixfmt, float 
     if (!(sigma >= 0)) return ZB_ERR_INVALID_SIGMA;
     if (sigma > 0) {
         std::vector<float> taps;
-        gaussian_taps_host(sigma, taps);
+        if ((rc = gaussian_taps_host(sigma, taps))) return rc;
         rc = host_conv_separable_pipelined(src, dst, pixfmt, taps.data(), (int)taps.size(), taps.data(), (int)taps.size(), ZB_BORDER_MIRROR);
         if (rc != ZB_ERR_UNSUPPORTED) return rc;
     }

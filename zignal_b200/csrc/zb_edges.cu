@@ -227,7 +227,7 @@ extern "C" int zb_canny(const zb_image* src, zb_image* dst, int pixfmt, float si
         iy{gy, src->rows, src->cols, src->cols};
     if (sigma != 0) {                                                  // blurGaussian, :663-687
         std::vector<float> taps;
-        gaussian_taps_host(sigma, taps);
+        if ((rc = gaussian_taps_host(sigma, taps))) return rc;
         if ((int)taps.size() > kMaxTaps) return ZB_ERR_UNSUPPORTED;
         if ((rc = conv_separable_generic(&g, &b, ZB_PIX_F32, taps.data(), (int)taps.size(), taps.data(), (int)taps.size(), ZB_BORDER_REPLICATE, s)))
             return rc;

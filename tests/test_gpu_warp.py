@@ -97,6 +97,74 @@ def test_rotate_batch_and_config4_shape(zb):
         assert np.array_equal(y[i].cpu().numpy(), want), i
 
 
+def _last_kernel(zb):
+    return zb.lib().zb_last_kernel().decode()
+
+
+@pytest.mark.parametrize("shape", [(64, 100), (37, 52), (130, 260), (5, 8), (1, 4), (200, 64)])
+def test_rotate_tile_kernel_vs_oracle(zb, shape):
+    """Rgba(u8) / bilinear / .zero with a 16-byte aligned row pitch takes the shared-memory tile kernel (zb_rotate_tile.cu: TMA
+    source tiles, zero fill as the border, magic-number floor + weight): bit-exact against the oracle for angles in every
+    quadrant, near-orthogonal angles, tiny and odd shapes, destinations larger and smaller than rotateBounds."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, shape + (4,), dtype=np.uint8)
+    dev = zb.Image.from_numpy(img)
+    for angle in (np.pi / 4, 0.3, -1.1, 2.5, 1e-3, np.pi / 2 + 2e-3, -np.pi / 4, 3.0, 4.0, 5.5, 0.7853):
+        cs = _cs(angle)
+        got = dev.rotate(np.float32(angle), zb.Interpolation.BILINEAR, zb.BorderMode.ZERO, cos_sin=cs).to_numpy()
+        assert _last_kernel(zb) == "rotate_tile_rgba8"
+        want = zo.rotate(img, np.float32(angle), "bilinear", "zero", cos_sin=cs)
+        assert np.array_equal(got, want), angle
+    for out_shape in ((shape[0] + 70, shape[1] + 3), (max(1, shape[0] // 2), max(1, shape[1] - 1)), (129, 65)):
+        fill = rng.integers(0, 256, out_shape + (4,), dtype=np.uint8)
+        out = zb.Image.from_numpy(fill)
+        dev.rotate_into(out, np.float32(0.9))
+        assert _last_kernel(zb) == "rotate_tile_rgba8"
+        assert np.array_equal(out.to_numpy(), zo.rotate_into(img, fill.copy(), np.float32(0.9))), out_shape
+
+
+def test_rotate_tile_kernel_views_and_gather_cross_check(zb):
+    """A view with a row pitch larger than its width (still 16-byte aligned) stays on the tile kernel and reads nothing outside the
+    view (TMA fills beyond the view's columns with zeros even though the parent has pixels there); a 1080p frame at several angles
+    is bit-identical between the tile kernel and the gather kernel (zb_tune rotate.tile 0)."""
+    import torch
+    rng = np.random.default_rng(77)
+    parent = rng.integers(1, 256, (90, 128, 4), dtype=np.uint8)
+    pdev = zb.Image.from_numpy(parent)
+    v = pdev.view(zb.Rectangle(8, 5, 8 + 60, 5 + 70)) if hasattr(zb, "Rectangle") else None
+    if v is not None:
+        sub = parent[5:75, 8:68].copy()
+        got = v.rotate(np.float32(0.6), cos_sin=_cs(0.6)).to_numpy()
+        assert _last_kernel(zb) == "rotate_tile_rgba8"
+        assert np.array_equal(got, zo.rotate(sub, np.float32(0.6), "bilinear", "zero", cos_sin=_cs(0.6)))
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randint(0, 256, (1080, 1920, 4), device="cuda", dtype=torch.uint8, generator=gen)
+    dev = zb.Image.from_tensor(x)
+    for angle in (np.pi / 4, 0.1, -2.0, 1.5607):
+        cs = _cs(angle)
+        a = dev.rotate(np.float32(angle), cos_sin=cs)
+        assert _last_kernel(zb) == "rotate_tile_rgba8"
+        try:
+            zb._ffi.check(zb.lib().zb_tune(b"rotate.tile", 0))
+            b = dev.rotate(np.float32(angle), cos_sin=cs)
+            assert _last_kernel(zb) == "rotate_gather"
+        finally:
+            zb._ffi.check(zb.lib().zb_tune(b"rotate.tile", 1))
+        assert torch.equal(a._t, b._t), angle
+    # destinations whose last tile row / column is 1..3 pixels
+    for orows, ocols in ((1089, 1921), (1027, 2050)):
+        out = zb.Image.init(orows, ocols, dev.pixfmt)
+        dev.rotate_into(out, np.float32(0.4), cos_sin=_cs(0.4))
+        assert _last_kernel(zb) == "rotate_tile_rgba8"
+        zb._ffi.check(zb.lib().zb_tune(b"rotate.tile", 0))
+        try:
+            ref = zb.Image.init(orows, ocols, dev.pixfmt)
+            dev.rotate_into(ref, np.float32(0.4), cos_sin=_cs(0.4))
+        finally:
+            zb._ffi.check(zb.lib().zb_tune(b"rotate.tile", 1))
+        assert torch.equal(out._t, ref._t), (orows, ocols)
+
+
 class _Xf:
     def __init__(self, kind, m):
         self.kind, self.m = kind, np.asarray(m, np.float32)

@@ -44,12 +44,6 @@ static int rotate_class(float angle) {
 __device__ __forceinline__ int patch_col(unsigned t) { return (int)(((t >> 5) & 3u) * 8u + (t & 7u)); }
 __device__ __forceinline__ int patch_row(unsigned t) { return (int)((t >> 7) * 4u + ((t >> 3) & 3u)); }
 
-struct RotParams {
-    float cos_a, sin_a, cx, cy, rcx, rcy;
-    int method, border;
-    float mb, mc;
-};
-
 // A thread produces RPT consecutive rows of one destination column: the per-pixel index / pointer set-up and the column terms
 // cos*dx, sin*dx are paid once per RPT pixels (each product is still the reference's own rounded f32 product, so every source
 // coordinate is bit-identical to the per-pixel formula).  Warp patch: 8 columns x (4 x RPT) rows; CTA tile: 32 x (8 x RPT).
@@ -231,6 +225,12 @@ int rotate_typed(const zb_image* src, unsigned long long spitch, zb_image* dst, 
     p.rcx = p.cx + offset_x;
     p.rcy = p.cy + offset_y;
     p.method = method; p.border = border; p.mb = mb; p.mc = mc;
+    if constexpr (sizeof(CT) == 1 && N == 4) {   // Rgba(u8), bilinear, .zero (config 4): shared-memory source tiles, zb_rotate_tile.cu
+        if (g_tune_rotate_tile.load()) {
+            const int rc = rotate_tile_rgba8(src, spitch, dst, dpitch, n, p, s);
+            if (rc != ZB_ERR_UNSUPPORTED) return rc;
+        }
+    }
     SrcView v{src->data, (int)src->rows, (int)src->cols, src->stride};
     t_last_kernel = "rotate_gather";
     return dispatch_method(method, [&](auto m) -> int {

@@ -1,6 +1,7 @@
 // zb_warp.h -- internal declarations shared by zb_resize.cu / zb_warp.cu.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "zb_internal.h"
@@ -9,6 +10,17 @@ namespace zb {
 // Device copy of the reference's 1025-entry Lanczos3 LUT (interpolation.zig:256-267), built once per device on the host.
 int lanczos_lut_device(const float** out, cudaStream_t s);
 int resize_dispatch(const zb_image* src, zb_image* dst, int pixfmt, int method, float mb, float mc, cudaStream_t s);
+
+// Image.rotateInto (transforms.zig:189-211): the geometry of one call, shared by the gather kernel (zb_warp.cu) and the tile kernel
+// for Rgba(u8) / bilinear / .zero (zb_rotate_tile.cu; returns ZB_ERR_UNSUPPORTED when it does not apply).
+struct RotParams {
+    float cos_a, sin_a, cx, cy, rcx, rcy;
+    int method, border;
+    float mb, mc;
+};
+int rotate_tile_rgba8(const zb_image* src, unsigned long long spitch, zb_image* dst, unsigned long long dpitch, uint32_t n, const RotParams& rp,
+                      cudaStream_t s);
+extern std::atomic<int> g_tune_rotate_tile;   // zb_tune("rotate_tile", 0) forces the gather kernel (tests cross-check the two)
 
 // Image.insert (transforms.zig:293-376): the geometry of one call, shared by the same-type kernel (zb_warp.cu) and the mixed-type
 // kernel (zb_insert_mixed.cu).

@@ -364,6 +364,10 @@ int zb_shard_fdm_set_target(zb_shard_comm* c, zb_fdm* f, const zb_image* target_
 int zb_shard_fdm_update(zb_shard_comm* c, zb_fdm* f, zb_stream s);
 /* Testing aid: 0 = automatic, 1 = force the NCCL send/recv halo exchange, 2 = force the peer pull kernel for every format. */
 int zb_shard_tune_path(int path);
+/* Introspection: %globaltimer stamps (ns) of this rank's last zb_shard_conv_separable kernel on the fused path -- [0] first CTA
+ * started, [1] both neighbours' sources seen complete, [2] all neighbour rows copied into the halo, [3] last CTA finished its
+ * rows, [4] both neighbours seen done reading this block's edge rows.  Waits for the stream. */
+int zb_shard_debug_times(zb_shard_comm* c, uint64_t* out8, zb_stream s);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-pointer twins (H2D + op + D2H inside the call; returns when dst is valid on the host).

@@ -55,6 +55,12 @@ def sharded():
 
 a, ha = loop(single)
 b, hb = loop(sharded)
+alt = {}
+for name, path in (("pull kernel + plain kernel", 2), ("NCCL exchange + plain kernel", 1)):   # the other two paths, back to back
+    zb._ffi.check(zb.lib().zb_shard_tune_path(path))
+    alt[name] = loop(sharded)[0]
+zb._ffi.check(zb.lib().zb_shard_tune_path(0))
+print(f"rank {rank}: " + " | ".join(f"{k} {v:.4f} ms" for k, v in alt.items()), flush=True)
 per = []
 for _ in range(30):
     if world > 1:
@@ -68,6 +74,13 @@ for _ in range(30):
     per.append(e0.elapsed_time(e1))
 per.sort()
 comm.status()
+# where inside the kernel the time goes: stamps of the last launch (one at a time, ranks released together by the barrier)
+import ctypes as C  # noqa: E402
+stamps = (C.c_uint64 * 8)()
+zb._ffi.check(zb.lib().zb_shard_debug_times(comm._h, stamps, zb.image.current_stream()))
+t = [int(x) for x in stamps]
+print(f"rank {rank}: kernel stamps (us after the first CTA started): neighbours ready {(t[1] - t[0]) / 1e3:.1f} | halo copied {(t[2] - t[0]) / 1e3:.1f} | "
+      f"last CTA done {(t[3] - t[0]) / 1e3:.1f} | neighbours done reading {(t[4] - t[0]) / 1e3:.1f}", flush=True)
 print(f"rank {rank}: single-GPU kernel on shard memory {a:.4f} ms (host {ha:.4f}) | sharded back-to-back {b:.4f} ms (host {hb:.4f}) | "
       f"sharded one at a time median {per[len(per) // 2]:.4f} min {per[0]:.4f} | kernel {zb.lib().zb_last_kernel().decode()}", flush=True)
 comm.destroy()

@@ -102,7 +102,7 @@ __device__ __forceinline__ void mac4(float4& acc, const float4& v, float k) {
 // of the edge strips.  Out-of-range rows (image top / bottom only) are fetched from global memory.
 template <int NT, bool SHARD = false>
 __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool fix_x, bool fix_rows, const FusedParams& p,
-                                         const ShardParams* sp = nullptr) {
+                                         int nb_lo = 0, int nb_hi = 0) {   // SHARD: rows in [nb_lo, 0) / [rows, nb_hi) are neighbour rows
     const int xlimit = p.ngroups * 8;
     auto stage_addr = [&](int rr, int xx) {
         const uint32_t line = (uint32_t)(rr * G + (xx >> 3));
@@ -120,7 +120,7 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const float4* rowp = p.src + (long long)y * (long long)p.src_pitch_px;
             if (y < 0 || y >= p.rows) {
                 if constexpr (SHARD) {   // a neighbour's row: it sits in this block's halo rows (the prologue copied it)
-                    if (!((y < 0 && sp->up_rows) || (y >= p.rows && sp->down_rows))) continue;
+                    if (y < nb_lo || y >= nb_hi) continue;
                 } else {
                     continue;                                                   // handled by the row pass below
                 }
@@ -142,7 +142,7 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
             const int y = y0 + rr, x = xs0 + xx;
             if (y >= 0 && y < p.rows) continue;
             if constexpr (SHARD) {
-                if ((y < 0 && sp->up_rows) || (y >= p.rows && sp->down_rows)) continue;   // neighbour rows: not border pixels
+                if (y >= nb_lo && y < nb_hi) continue;   // neighbour rows: not border pixels
             }
             const int ry = resolve_index(y, p.rows, p.border);
             const int rx = resolve_index(x, p.cols, p.border);
@@ -200,9 +200,13 @@ __device__ __forceinline__ void v_pass(uint32_t v_col, const FusedParams& p, flo
     }
 }
 
+// The heavy part of the kernel: this CTA's units k_begin <= k < k_end (unit = blockIdx.x + k * gridDim.x), TMA pipeline filled at
+// entry and drained at exit; `count0` = chunks this CTA has consumed before (stage index and mbarrier parity carry on from there).
+// Returns the updated count.  nbr (SHARD): bit 0 = the rows above the block are the upper neighbour's (already in the halo rows),
+// bit 1 = the rows below are the lower neighbour's.
 // F2: use the packed fma.rn.f32x2 (FFMA2) -- two lanes per issued instruction, same IEEE result as FFMA.
 template <int HALF, bool EXACT, int STAGES, bool F2, bool SHARD>
-__device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, const FusedParams& p, const ShardParams* sp) {
+__device__ __forceinline__ uint32_t fused_units(const CUtensorMap& tmap, const FusedParams& p, unsigned nbr, int k_begin, int k_end, uint32_t count0) {
     static_assert(!(EXACT && F2), "exact mode is scalar");
     constexpr int K = 2 * HALF + 1;
     constexpr int NLOAD = CHUNK + 2 * HALF;
@@ -212,109 +216,34 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
     const uint32_t bar0 = ring + RING_BYTES;
 
     const int tid = threadIdx.x;
-    const int n_units = p.n_strips * p.n_bands;
+    const long long u_first = (long long)blockIdx.x + (long long)k_begin * gridDim.x;
+    const long long u_last = (long long)blockIdx.x + (long long)k_end * gridDim.x;
+    const int n_units = (int)min((long long)p.n_strips * p.n_bands, u_last);
+    if (u_first >= n_units) return count0;
+    // does a chunk of rows [y, y + CHUNK) read neighbour rows?
+    auto touches_neighbour = [&](int y) { return ((nbr & 1u) && y < 0) || ((nbr & 2u) && y + CHUNK > p.rows); };
 
     // ---- producer (thread 0): a cursor over this CTA's (unit, chunk) sequence, STAGES chunks ahead ----
-    int pu = blockIdx.x, pi = 0;
-    uint32_t pcount = 0;
+    int pu = (int)u_first, pi = 0;
+    uint32_t pcount = count0;
     auto produce = [&]() {
         if (pu >= n_units) return;
         int band = pu / p.n_strips;
         const int strip = pu - band * p.n_strips;
-        if constexpr (SHARD) band = band + 1 == p.n_bands ? 0 : band + 1;   // the band that reads the upper halo goes last
+        if constexpr (SHARD) band = band + 1 == p.n_bands ? 0 : band + 1;   // the bands next to a neighbour go last
         const int ra = p.row0 + band * p.band_rows;
         const int rb = min(ra + p.band_rows, p.row1);
         const int n_in = (rb - ra + CHUNK - 1) / CHUNK + 2;
         const uint32_t st = pcount % STAGES;
         const int y = ra - CHUNK + CHUNK * pi;
-        if constexpr (SHARD) {
-            // a chunk that touches the halo rows needs the prologue copies of ALL CTAs (normally long finished by now)
-            if ((y < 0 && sp->up_rows) || (y + CHUNK > p.rows && sp->down_rows)) {
-                shard_wait_ge(&sp->link.self->halo_landed, sp->link.epoch, sp->link.self);
-                asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above orders the async-proxy read below
-            }
-        }
         fence_proxy_async();
         mbar_arrive_expect_tx(bar0 + 8 * st, STAGE_BYTES);
         tma_load_3d(smem0 + st * STAGE_BYTES, &tmap, 0, strip * (TW / 8) - 1, y + p.tma_row_off, bar0 + 8 * st);
         ++pcount;
         if (++pi == n_in) { pi = 0; pu += gridDim.x; }
     };
-
-    if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-        for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
-        fence_barrier_init();
-        if constexpr (SHARD) {
-            // this kernel is stream-ordered after whatever produced my source block: tell the neighbours it is complete,
-            // then wait until theirs are
-            if (blockIdx.x == 0) {
-                if (sp->link.up) st_release_sys(&sp->link.up->ready_from[1], sp->link.epoch);
-                if (sp->link.down) st_release_sys(&sp->link.down->ready_from[0], sp->link.epoch);
-            }
-            if (sp->up_rows) shard_wait_ge(&sp->link.self->ready_from[0], sp->link.epoch, sp->link.self);
-            if (sp->down_rows) shard_wait_ge(&sp->link.self->ready_from[1], sp->link.epoch, sp->link.self);
-        }
-    }
-    __syncthreads();
-    // Normally the first chunks of a CTA touch no halo row (the halo bands come last), so the pipeline fills while the copy below
-    // runs.  On a small block a CTA's first unit can be a halo band: waiting for `halo_landed` before this CTA has contributed its
-    // own slice would deadlock, so such a CTA fills its pipeline after the prologue instead.
-    bool fill_first = true;
-    if constexpr (SHARD) {
-        int b0 = blockIdx.x / p.n_strips;   // the band of this CTA's first unit (a unit has >= 10 chunks: only it matters here)
-        b0 = b0 + 1 == p.n_bands ? 0 : b0 + 1;
-        fill_first = blockIdx.x < n_units && !((b0 == 0 && sp->up_rows) || (b0 == p.n_bands - 1 && sp->down_rows));
-    }
-    if (tid == 0 && fill_first)
+    if (tid == 0)
         for (int i = 0; i < STAGES; ++i) produce();
-    if constexpr (SHARD) {
-        // ---- prologue: this CTA's slice of the neighbours' edge rows -> my halo rows (plain loads over NVLink, all issued before
-        // the first use so the round trips overlap) ----
-        const int per_side = sp->half * p.cols;                      // pixels
-        const int total = (sp->up_rows ? per_side : 0) + (sp->down_rows ? per_side : 0);
-        constexpr int BATCH = 4;
-        for (int base = blockIdx.x * NTHREADS * BATCH; base < total; base += gridDim.x * NTHREADS * BATCH) {
-            float4 v[BATCH];
-            float4* dstp[BATCH];
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k) {
-                int e = base + k * NTHREADS + tid;
-                dstp[k] = nullptr;
-                if (e < total) {
-                    const bool upper = sp->up_rows && e < per_side;
-                    if (!upper && sp->up_rows) e -= per_side;
-                    const int r = e / p.cols, x = e - r * p.cols;
-                    if (upper) {
-                        v[k] = *(sp->up_rows + (size_t)r * sp->up_pitch_px + x);
-                        dstp[k] = const_cast<float4*>(p.src) + (long long)(r - sp->half) * (long long)p.src_pitch_px + x;
-                    } else {
-                        v[k] = *(sp->down_rows + (size_t)r * sp->down_pitch_px + x);
-                        dstp[k] = const_cast<float4*>(p.src) + (long long)(p.rows + r) * (long long)p.src_pitch_px + x;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < BATCH; ++k)
-                if (dstp[k]) *dstp[k] = v[k];
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");   // these generic-proxy stores are read by TMA (async proxy) later on
-        __syncthreads();
-        if (tid == 0) {
-            ShardCtrl* me = sp->link.self;
-            __threadfence();
-            if (atomicAdd(&me->halo_reads[0], 1u) == gridDim.x - 1u) {   // every CTA's slice has landed
-                me->halo_reads[0] = 0;
-                __threadfence();
-                st_release_sys(&me->halo_landed, sp->link.epoch);
-                // the neighbours' rows have been read: they may overwrite their source again
-                if (sp->up_rows) st_release_sys(&sp->link.up->done_from[1], sp->link.epoch);
-                if (sp->down_rows) st_release_sys(&sp->link.down->done_from[0], sp->link.epoch);
-            }
-            if (!fill_first)
-                for (int i = 0; i < STAGES; ++i) produce();
-        }
-    }
 
     // H-pass role: lane -> pixel group (8 consecutive pixels), warp -> row of the chunk
     const int ht = tid & 31, hr = tid >> 5;
@@ -324,9 +253,9 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
     const uint32_t h_ring_col = ring + (uint32_t)ht * 128u;
     const uint32_t h_key = (uint32_t)ht & 7u;
 
-    uint32_t ccount = 0;  // chunks consumed by this CTA
+    uint32_t ccount = count0;  // chunks consumed by this CTA
 
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    for (int unit = (int)u_first; unit < n_units; unit += gridDim.x) {
         int band = unit / p.n_strips;
         const int strip = unit - band * p.n_strips;
         if constexpr (SHARD) band = band + 1 == p.n_bands ? 0 : band + 1;
@@ -344,11 +273,11 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             const int y0 = ra - CHUNK + CHUNK * i;
             bool fix_r = p.fix_rows && (y0 < 0 || y0 + CHUNK > p.rows);
             if constexpr (SHARD) {   // rows beyond the block on a neighbour side are real rows (already in the halo), not border pixels
-                if ((y0 < 0 && sp->up_rows) || (y0 + CHUNK > p.rows && sp->down_rows)) fix_r = false;
+                if (touches_neighbour(y0)) fix_r = false;
             }
             const bool fix_x = (p.fix_left && g0 < 0) || (p.fix_right && (g0 + G) * 8 > p.ngroups * 8);
             if (fix_r || fix_x) {
-                fixup_stage<NTHREADS, SHARD>(stage, y0, g0 * 8, fix_x, fix_r, p, sp);
+                fixup_stage<NTHREADS, SHARD>(stage, y0, g0 * 8, fix_x, fix_r, p, (nbr & 1u) ? INT_MIN : 0, (nbr & 2u) ? INT_MAX : p.rows);
                 __syncthreads();
             }
 
@@ -414,7 +343,116 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             __syncthreads();  // V(i-2) done reading the slot H(i+1) will overwrite
         }
     }
-    if constexpr (SHARD) {
+    return ccount;
+}
+
+// The shard kernel runs the unit loop twice -- two inlined copies -- with the wait for the halo rows in between.  With a spin loop
+// anywhere INSIDE the loop ptxas stops keeping the 30 taps in uniform registers and reloads them from the constant bank in every H
+// and V pass (0.50 ms against 0.44 ms for the same rows); behind a real call the taps arrive through a generic pointer and every
+// FFMA takes three vector registers.
+template <int HALF, bool EXACT, int STAGES>
+__device__ __forceinline__ uint32_t fused_units_call(const CUtensorMap& tmap, const FusedParams& p, unsigned nbr, int k_begin, int k_end, uint32_t count0) {
+    return fused_units<HALF, EXACT, STAGES, false, true>(tmap, p, nbr, k_begin, k_end, count0);
+}
+
+template <int HALF, bool EXACT, int STAGES, bool F2, bool SHARD>
+__device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, const FusedParams& p, const ShardParams* sp) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem0 + STAGES * STAGE_BYTES + RING_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int i = 0; i < STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
+        fence_barrier_init();
+    }
+    if constexpr (!SHARD) {
+        __syncthreads();
+        fused_units<HALF, EXACT, STAGES, F2, false>(tmap, p, 0u, 0, INT_MAX / 2048, 0u);
+    } else {
+        ShardCtrl* me = sp->link.self;
+        const unsigned long long epoch = sp->link.epoch;
+        const unsigned nbr = (sp->up_rows ? 1u : 0u) | (sp->down_rows ? 2u : 0u);
+        // ---- prologue: the CTAs with a slice of the neighbours' edge rows copy it into my halo rows (plain loads over NVLink, all
+        // issued before the first use so the round trips overlap); the others go straight to their rows ----
+        const int per_side = sp->half * p.cols;                      // pixels
+        const int total = (sp->up_rows ? per_side : 0) + (sp->down_rows ? per_side : 0);
+        constexpr int BATCH = 12;   // loads in flight per thread: the copy is a handful of NVLink round trips, not a bandwidth problem
+        // The copy is done by the CTAs with the lightest load: units are dealt round robin, so CTAs [rem, grid) have one unit less
+        // than the others (the host launches a full grid even when there are fewer units than SMs: those CTAs have none), which is
+        // far more slack than the copy needs.  rem == 0: everyone carries the same load and shares the copy.
+        const int rem = (p.n_strips * p.n_bands) % (int)gridDim.x;
+        const int n_copiers = (int)gridDim.x - rem;
+        const int ci = (int)blockIdx.x - rem;
+        const bool copier = ci >= 0 && (long long)ci * NTHREADS * BATCH < total;
+        if (tid == 0) {
+            // this kernel is stream-ordered after whatever produced my source block: tell the neighbours it is complete; a CTA that
+            // reads their rows waits until theirs are
+            if (blockIdx.x == 0) {
+                me->dbg[0] = global_timer_ns();
+                if (sp->link.up) st_release_sys(&sp->link.up->ready_from[1], epoch);
+                if (sp->link.down) st_release_sys(&sp->link.down->ready_from[0], epoch);
+            }
+            if (copier) {
+                if (sp->up_rows) shard_wait_ge(&me->ready_from[0], epoch, me);
+                if (sp->down_rows) shard_wait_ge(&me->ready_from[1], epoch, me);
+                if (ci == 0) me->dbg[1] = global_timer_ns();
+            }
+        }
+        __syncthreads();
+        if (copier) {
+            for (int base = ci * NTHREADS * BATCH; base < total; base += n_copiers * NTHREADS * BATCH) {
+                float4 v[BATCH];
+                float4* dstp[BATCH];
+    #pragma unroll
+                for (int k = 0; k < BATCH; ++k) {
+                    int e = base + k * NTHREADS + tid;
+                    dstp[k] = nullptr;
+                    if (e < total) {
+                        const bool upper = sp->up_rows && e < per_side;
+                        if (!upper && sp->up_rows) e -= per_side;
+                        const int r = e / p.cols, x = e - r * p.cols;
+                        if (upper) {
+                            v[k] = *(sp->up_rows + (size_t)r * sp->up_pitch_px + x);
+                            dstp[k] = const_cast<float4*>(p.src) + (long long)(r - sp->half) * (long long)p.src_pitch_px + x;
+                        } else {
+                            v[k] = *(sp->down_rows + (size_t)r * sp->down_pitch_px + x);
+                            dstp[k] = const_cast<float4*>(p.src) + (long long)(p.rows + r) * (long long)p.src_pitch_px + x;
+                        }
+                    }
+                }
+    #pragma unroll
+                for (int k = 0; k < BATCH; ++k)
+                    if (dstp[k]) *dstp[k] = v[k];
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // these generic-proxy stores are read by TMA (async proxy) later on
+            __syncthreads();
+        }
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(&me->halo_reads[0], 1u) == gridDim.x - 1u) {   // every CTA's slice has landed
+                me->halo_reads[0] = 0;
+                me->dbg[2] = global_timer_ns();
+                __threadfence();
+                st_release_sys(&me->halo_landed, epoch);
+                // the neighbours' rows have been read: they may overwrite their source again
+                if (sp->up_rows) st_release_sys(&sp->link.up->done_from[1], epoch);
+                if (sp->down_rows) st_release_sys(&sp->link.down->done_from[0], epoch);
+            }
+        }
+        // ---- the rows: first the units that read no halo row, then -- once every CTA's copy has landed (normally long ago) -- the
+        // two bands next to the neighbours, which the unit order puts last ----
+        const long long first_halo_unit = (long long)max(0, p.n_bands - 2) * p.n_strips;
+        const int k_split = first_halo_unit <= (long long)blockIdx.x ? 0 : (int)((first_halo_unit - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const uint32_t count = fused_units_call<HALF, EXACT, STAGES>(tmap, p, nbr, 0, k_split, 0u);
+        if ((long long)blockIdx.x + (long long)k_split * gridDim.x < (long long)p.n_strips * p.n_bands) {   // this CTA has halo units
+            if (tid == 0) {
+                shard_wait_ge(&me->halo_landed, epoch, me);
+                asm volatile("fence.proxy.async;" ::: "memory");   // the acquire above orders TMA's (async proxy) reads of the halo rows
+            }
+            __syncthreads();
+            fused_units_call<HALF, EXACT, STAGES>(tmap, p, nbr, k_split, INT_MAX / 2048, count);
+        }
         // The kernel may not complete before both neighbours have finished reading this block's edge rows: whatever runs
         // next on this stream is then free to overwrite the source.  The last CTA to leave does the waiting.
         if (tid == 0) {
@@ -422,12 +460,15 @@ __device__ __forceinline__ void fused_sep_rgbaf32_body(const CUtensorMap& tmap, 
             __threadfence();
             if (atomicAdd(&me->exit_ticket, 1u) == gridDim.x - 1u) {
                 me->exit_ticket = 0;
+                me->dbg[3] = global_timer_ns();
                 if (sp->link.up) shard_wait_ge(&me->done_from[0], sp->link.epoch, me);
                 if (sp->link.down) shard_wait_ge(&me->done_from[1], sp->link.epoch, me);
+                me->dbg[4] = global_timer_ns();
             }
         }
     }
 }
+
 
 template <int HALF, bool EXACT, int STAGES, bool F2>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -795,6 +836,11 @@ int conv_separable_fused_rgbaf32_shard(const zb_image* src, zb_image* dst, const
     sp.link = link;
     if (!sp.up_rows) sp.link.up = nullptr;
     if (!sp.down_rows) sp.link.down = nullptr;
+    {   // always a full grid: CTAs beyond the unit count only copy halo rows (all CTAs are co-resident: one per SM)
+        DeviceInfo di;
+        if ((rc = device_info(&di))) return rc;
+        grid = di.sm_count;
+    }
     t_last_kernel = exact ? "fused_sep_rgbaf32_shard_exact" : "fused_sep_rgbaf32_shard";
     switch (half) {
         case 1: return launch_shard<1>(tmap, p, sp, grid, exact, s);

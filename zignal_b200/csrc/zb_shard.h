@@ -25,6 +25,7 @@ struct ShardCtrl {
     unsigned int error;           // local: set when a wait timed out (a peer never arrived)
     unsigned int gather_ticket;   // local: blocks of the running statistics kernel that have added their partial sums
     unsigned int pad[3];
+    unsigned long long dbg[8];    // local: %globaltimer stamps of the last sharded convolution kernel (zb_shard_debug_times)
 };
 
 // What a kernel needs to talk to its row neighbours.  All pointers are in THIS process's address space (peer pointers are
@@ -59,7 +60,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 // Spin until *flag >= epoch.  A peer that never arrives (crashed rank, mismatched call order) must not hang the GPU:
 // after ~20 s the wait gives up and records the failure in the control block (zb_shard_status reports it).
-static __device__ __noinline__ bool shard_wait_ge(const unsigned long long* flag, unsigned long long epoch, ShardCtrl* self) {
+static __device__ __forceinline__ bool shard_wait_ge(const unsigned long long* flag, unsigned long long epoch, ShardCtrl* self) {
     if (ld_acquire_sys(flag) >= epoch) return true;
     const unsigned long long t0 = global_timer_ns();
     unsigned spins = 0;

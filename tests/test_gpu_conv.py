@@ -149,7 +149,7 @@ def test_fused_rgba8_views_fallbacks_and_gaussian(zb):
     # a view that breaks TMA alignment (offset 3 px) takes the shared-memory tile kernel; taps that need i64 accumulators the two-pass path
     v2 = big.view(zb.Rectangle(3, 0, 299, 100))
     got = v2.convolve_separable(kx, ky, zb.BorderMode.WRAP).to_numpy()
-    assert L.zb_last_kernel().decode() == "sep_tile_u8"
+    assert L.zb_last_kernel().decode() in ("sep_tile_u8", "sep_tile_u8_dp")
     assert np.array_equal(got, zo.conv_separable(np.ascontiguousarray(img[0:100, 3:299]), kx, ky, "wrap"))
     huge = (rng.standard_normal(5) * 3000).astype(np.float32)
     got = big.convolve_separable(huge, huge, zb.BorderMode.MIRROR).to_numpy()
@@ -331,6 +331,30 @@ def test_row_block_conv_single_rank(zb):
             assert np.array_equal(ob.interior_tensor().cpu().numpy(), want), (halo, border)
 
 
+@pytest.mark.parametrize("shape", [(400, 1500), (330, 800, 3), (300, 1501), (260, 699, 3), (280, 516, 4)])
+def test_tile_u8_kernel_interior_tiles(zb, shape):
+    """Images large enough to have interior tiles (which the tile kernels copy as 32-bit words when base, pitch and row length are
+    4-byte aligned; the odd widths keep the per-byte loader): Gaussian taps (dot-product variant) and signed taps (IMAD variant),
+    a view whose rows start at an odd byte, bit-exact against the oracle."""
+    L = zb.lib()
+    rng = np.random.default_rng(shape[1])
+    img = rand_image(rng, shape, np.uint8)
+    dev = zb.Image.from_numpy(img)
+    for k in (zb.gaussian_taps(2.25), zb.gaussian_taps(1.0), (rng.standard_normal(9) * 0.4).astype(np.float32)):
+        for border in ("mirror", "zero"):
+            if len(shape) == 3 and shape[2] == 4:
+                L.zb_set_force_generic(0)
+            got = dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy()
+            name = L.zb_last_kernel().decode()
+            assert name.startswith("sep_tile_u8") or name.startswith("fused_sep_rgba8"), name
+            assert np.array_equal(got, zo.conv_separable(img, k, k, border)), (name, border)
+    v = dev.view(zb.Rectangle(3, 2, shape[1] - 5, shape[0] - 1))
+    crop = np.ascontiguousarray(img[2:shape[0] - 1, 3:shape[1] - 5])
+    got = v.convolve_separable(zb.gaussian_taps(2.25), zb.gaussian_taps(2.25), zb.BorderMode.REPLICATE).to_numpy()
+    assert L.zb_last_kernel().decode().startswith("sep_tile_u8")
+    assert np.array_equal(got, zo.conv_separable(crop, zb.gaussian_taps(2.25), zb.gaussian_taps(2.25), "replicate"))
+
+
 @pytest.mark.parametrize("shape", [(70, 131), (129, 257, 3), (200, 90, 3), (65, 300, 4), (33, 1000)])
 @pytest.mark.parametrize("border", BORDERS)
 def test_tile_u8_kernel_against_oracle_and_two_pass(zb, shape, border):
@@ -343,10 +367,16 @@ def test_tile_u8_kernel_against_oracle_and_two_pass(zb, shape, border):
     bm = border_enum(zb, border)
     for nx, ny in [(3, 3), (15, 15), (4, 9), (1, 7), (31, 2), (5, 29)]:
         kx, ky = _taps(rng, nx), _taps(rng, ny)
-        got = dev.convolve_separable(kx, ky, bm).to_numpy()
-        name = L.zb_last_kernel().decode()
-        assert name == "sep_tile_u8" or (name.startswith("fused_sep_rgba8") and len(shape) == 3 and shape[2] == 4), (nx, ny, name)
-        assert np.array_equal(got, zo.conv_separable(img, kx, ky, border)), (nx, ny)
+        want = zo.conv_separable(img, kx, ky, border)
+        for dp in (1, 0):   # dot-product variant (byte taps, half <= 8) and the IMAD variant: one result
+            L.zb_tune(b"conv.u8_dp", dp)
+            got = dev.convolve_separable(kx, ky, bm).to_numpy()
+            name = L.zb_last_kernel().decode()
+            L.zb_tune(b"conv.u8_dp", 1)
+            assert name in ("sep_tile_u8", "sep_tile_u8_dp") or (name.startswith("fused_sep_rgba8") and len(shape) == 3 and shape[2] == 4), (nx, ny, name)
+            if name.startswith("sep_tile"):
+                assert (name == "sep_tile_u8_dp") == bool(dp and max(nx, ny) // 2 <= 8 and max(nx, ny) // 2 >= 1 and _dp_eligible(kx, ky)), (nx, ny, name, dp)
+            assert np.array_equal(got, want), (nx, ny, dp, name)
     L.zb_set_force_generic(1)
     try:
         kx, ky = _taps(rng, 11), _taps(rng, 7)

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int TWB = 256;          // output bytes per tile row = threads per CTA
 constexpr int TU_MAX_HALF = 15;
+constexpr int TU_DP_MAX_HALF = 8;        // the dot-product variant: registers of the vertical window, 16 tap words per output byte
 
 struct TileParams {
     int kx[2 * TU_MAX_HALF + 1];   // taps aligned to the common half-width (zero padded)
@@ -34,22 +35,57 @@ struct TileParams {
     uint8_t* dst;
     size_t src_pitch, dst_pitch;   // bytes
     int rows, cols, row_bytes, border;
+    // DP variant: horizontal tap words tw[m][j] = the four Q8 taps (bytes) that output byte m of an 8-byte run applies to bytes
+    // 4j .. 4j + 3 of the run's span; vertical tap pairs for even (kye) and odd (kyo) output rows
+    uint32_t tw[8][20];
+    uint32_t kye[TU_DP_MAX_HALF + 1], kyo[TU_DP_MAX_HALF + 1];
+    int dst_word_ok;               // dst base and pitch are multiples of 4: the vertical pass stores whole words
+    int src_word_ok;               // src base, pitch and row length are multiples of 4: interior tiles load whole words
 };
 
-template <int CH, int HALF>
-__global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant__ TileParams p) {
-    constexpr int K = 2 * HALF + 1;
-    constexpr int TH = HALF <= 7 ? 64 : 32;                 // output rows per tile
-    constexpr int IR = TH + 2 * HALF;                       // tile rows held in shared memory
-    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;      // input bytes per tile row (8-byte granular: 64-bit loads in the H pass)
-    extern __shared__ __align__(16) unsigned char smem[];
-    int* tmp = reinterpret_cast<int*>(smem);                // [IR][TWB] horizontal sums
-    uint8_t* in = smem + (size_t)IR * TWB * sizeof(int);    // [IR][IW]  border-resolved source bytes
-    const int t = threadIdx.x;
-    const int b0 = blockIdx.x * TWB;                        // first output byte of the tile within a row
-    const int y0 = blockIdx.y * TH;                         // first output row
-
-    // ---- load: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position (b0 + tb - HALF*CH), border-resolved.
+// Load stage shared by both tile kernels: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position
+// (b0 + tb - HALF*CH), border-resolved per pixel.
+template <int CH, int HALF, int IR, int IW>
+__device__ __forceinline__ void tile_load(const TileParams& p, uint8_t* in, int t, int b0, int y0) {
+    // Interior tiles of a 4-byte aligned image (base, pitch and row length): no pixel needs the border rule, so the tile is copied
+    // as 32-bit words -- two aligned loads (the second one a neighbour's first: an L1 hit) and a funnel shift per word, since a
+    // tile row starts HALF * CH bytes before a 256-byte boundary.
+    {
+        const int g0 = b0 - HALF * CH;                 // first byte of the tile row within the source row
+        if (p.src_word_ok && g0 >= 0 && g0 + IW <= p.row_bytes && y0 - HALF >= 0 && y0 - HALF + IR <= p.rows) {
+            constexpr int WPR = IW / 4;                // words per tile row
+            constexpr int NWORD = IR * WPR;
+            constexpr int UB = 4;
+            const uint8_t* base = p.src + (size_t)(y0 - HALF) * p.src_pitch + g0;
+            for (int i0 = t; i0 < NWORD; i0 += UB * TWB) {
+                uint32_t lo[UB], hi[UB];
+                unsigned sh[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int idx = i0 + u * TWB;
+                    lo[u] = hi[u] = 0u;
+                    sh[u] = 0u;
+                    if (idx < NWORD) {
+                        const int tr = idx / WPR, wq = idx - tr * WPR;
+                        const uintptr_t a = (uintptr_t)(base + (size_t)tr * p.src_pitch + 4 * wq);
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                        sh[u] = (unsigned)(a & 3u) * 8u;
+                        lo[u] = __ldg(q);
+                        if (sh[u]) hi[u] = __ldg(q + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int idx = i0 + u * TWB;
+                    if (idx < NWORD) {
+                        const int tr = idx / WPR, wq = idx - tr * WPR;
+                        *reinterpret_cast<uint32_t*>(in + tr * IW + 4 * wq) = __funnelshift_r(lo[u], hi[u], sh[u]);
+                    }
+                }
+            }
+            return;
+        }
+    }
     // LB rows are fetched per batch so that 2*LB independent global loads are in flight before the first shared-memory store
     // (one load per iteration would expose the full memory latency IR times per tile).
     {
@@ -95,6 +131,22 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant_
             }
         }
     }
+}
+
+template <int CH, int HALF>
+__global__ void __launch_bounds__(TWB) sep_tile_u8_kernel(const __grid_constant__ TileParams p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int TH = HALF <= 7 ? 64 : 32;                 // output rows per tile
+    constexpr int IR = TH + 2 * HALF;                       // tile rows held in shared memory
+    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;      // input bytes per tile row (8-byte granular: 64-bit loads in the H pass)
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* tmp = reinterpret_cast<int*>(smem);                // [IR][TWB] horizontal sums
+    uint8_t* in = smem + (size_t)IR * TWB * sizeof(int);    // [IR][IW]  border-resolved source bytes
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.x * TWB;                        // first output byte of the tile within a row
+    const int y0 = blockIdx.y * TH;                         // first output row
+
+    tile_load<CH, HALF, IR, IW>(p, in, t, b0, y0);
     __syncthreads();
 
     // ---- horizontal pass: tmp[tr][b] = sum_i in[tr][b + i*CH] * kx[i].  A thread produces a run of 8 consecutive bytes of one tile
@@ -177,6 +229,143 @@ int launch_tile(const TileParams& p, cudaStream_t s) {
     return ZB_OK;
 }
 
+// ================================================================================================
+// DP variant (every Q8 tap a byte 0 .. 255 and 255 * sum(kx) <= 65535: Gaussian, box, motion blur): the same tile on the
+// integer dot-product instructions.
+//   H : a thread produces 8 consecutive bytes of TWO tile rows.  Output byte m is sum_j dp4a(W_j, tw[m][j]) over the aligned
+//       32-bit words W_j of the run's span: instead of shifting the pixels into place for every output, the host shifts the TAPS
+//       (tw[m][j] holds the taps that fall on bytes 4j .. 4j + 3 for output m; words without a tap are skipped at compile time).
+//       Gray: 4-5 dp4a per output byte instead of 15 extract + multiply-add triples; Rgb: 11-12.  The sums (<= 65535) of the two
+//       rows share a word: tmp[pair][byte] = row 2 pair | row 2 pair + 1 << 16.
+//   V : a thread owns 4 byte columns x TH/4 rows with the pairs it needs in registers; an even output row is HALF + 1 dp2a over
+//       the pairs with taps (ky0, ky1), (ky2, ky3), ..., an odd one the same pairs with taps (0, ky0), (ky1, ky2), ... -- again the
+//       taps move, not the data.  divClampU8(65536) of a non-negative sum = min((acc + 32768) >> 16, 255); word stores.
+// Integer sums are order-independent: same bits as the reference (and as the IMAD variant above, which stays for other kernels).
+// ================================================================================================
+template <int CH, int HALF>
+__global__ void __launch_bounds__(TWB) sep_tile_u8_dp_kernel(const __grid_constant__ TileParams p) {
+    constexpr int K = 2 * HALF + 1;
+    constexpr int TH = 64;
+    constexpr int IR = TH + 2 * HALF;                       // even
+    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;
+    constexpr int NPAIR = IR / 2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(smem);                  // [NPAIR][TWB] horizontal sums of rows (2 pr, 2 pr + 1)
+    uint8_t* in = smem + (size_t)NPAIR * TWB * sizeof(uint32_t);        // [IR][IW]
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.x * TWB;
+    const int y0 = blockIdx.y * TH;
+    tile_load<CH, HALF, IR, IW>(p, in, t, b0, y0);
+    __syncthreads();
+
+    {
+        constexpr int SPAN = 8 + 2 * HALF * CH;          // bytes a run reads
+        constexpr int NQ = (SPAN + 7) / 8;               // 64-bit words
+        constexpr int NW = (SPAN + 3) / 4;               // 32-bit words
+        static_assert(NW <= 20, "tap word table");
+        for (int idx = t; idx < NPAIR * (TWB / 8); idx += TWB) {
+            const int pr = idx / (TWB / 8), run = idx % (TWB / 8);
+            uint32_t acc[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned long long* q = reinterpret_cast<const unsigned long long*>(in + (2 * pr + h) * IW + 8 * run);
+                unsigned long long w[NQ];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) w[i] = (8 * run + 8 * i < IW) ? q[i] : 0ull;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    uint32_t a = 0;
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) {
+                        // does a tap of output m fall on bytes 4j .. 4j + 3 of the span?  (compile time after unrolling)
+                        bool has = false;
+#pragma unroll
+                        for (int b = 4 * j; b < 4 * j + 4; ++b) has = has || (b >= m && (b - m) % CH == 0 && (b - m) / CH < K);
+                        if (has) a = __dp4a((uint32_t)(w[j >> 1] >> (32 * (j & 1))), p.tw[m][j], a);
+                    }
+                    acc[h][m] = a;
+                }
+            }
+            uint4* dsts = reinterpret_cast<uint4*>(tmp + pr * TWB + 8 * run);
+            dsts[0] = make_uint4(acc[0][0] | (acc[1][0] << 16), acc[0][1] | (acc[1][1] << 16), acc[0][2] | (acc[1][2] << 16), acc[0][3] | (acc[1][3] << 16));
+            dsts[1] = make_uint4(acc[0][4] | (acc[1][4] << 16), acc[0][5] | (acc[1][5] << 16), acc[0][6] | (acc[1][6] << 16), acc[0][7] | (acc[1][7] << 16));
+        }
+    }
+    __syncthreads();
+
+    {
+        constexpr int RPG = TH / 4;                       // rows per thread (16)
+        constexpr int NE = RPG / 2 + HALF;                // pairs the rows of a thread read
+        const int cg = t & 63, rg = t >> 6;
+        const int r0 = rg * RPG;
+        const int bcol = b0 + 4 * cg;
+        if (bcol < p.row_bytes && y0 + r0 < p.rows) {
+            uint4 E[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) E[e] = *reinterpret_cast<const uint4*>(tmp + (r0 / 2 + e) * TWB + 4 * cg);
+            const int nrows = min(RPG, p.rows - y0 - r0);
+            uint8_t* out = p.dst + (size_t)(y0 + r0) * p.dst_pitch + (size_t)bcol;
+            const int nb = min(4, p.row_bytes - bcol);
+#pragma unroll
+            for (int rr = 0; rr < RPG; ++rr) {
+                if (rr < nrows) {
+                    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                    for (int q = 0; q <= HALF; ++q) {
+                        const uint4 e = E[rr / 2 + q];
+                        const uint32_t kt = (rr & 1) ? p.kyo[q] : p.kye[q];
+                        a0 = __dp2a_lo(e.x, kt, a0);
+                        a1 = __dp2a_lo(e.y, kt, a1);
+                        a2 = __dp2a_lo(e.z, kt, a2);
+                        a3 = __dp2a_lo(e.w, kt, a3);
+                    }
+                    const uint32_t q0 = min((a0 + 32768u) >> 16, 255u), q1 = min((a1 + 32768u) >> 16, 255u), q2 = min((a2 + 32768u) >> 16, 255u),
+                                   q3 = min((a3 + 32768u) >> 16, 255u);
+                    uint8_t* o = out + (size_t)rr * p.dst_pitch;
+                    if (p.dst_word_ok && nb == 4) {
+                        *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                    } else {
+                        o[0] = (uint8_t)q0;
+                        if (nb > 1) o[1] = (uint8_t)q1;
+                        if (nb > 2) o[2] = (uint8_t)q2;
+                        if (nb > 3) o[3] = (uint8_t)q3;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int CH, int HALF>
+int launch_tile_dp(const TileParams& p, cudaStream_t s) {
+    constexpr int TH = 64;
+    constexpr int IR = TH + 2 * HALF;
+    constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;
+    constexpr int smem = (IR / 2) * TWB * (int)sizeof(uint32_t) + IR * IW;
+    auto k = sep_tile_u8_dp_kernel<CH, HALF>;
+    if (smem > 48 * 1024) ZB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(div_up((size_t)p.row_bytes, TWB), div_up((size_t)p.rows, TH));
+    if (grid.y > 65535u) return ZB_ERR_UNSUPPORTED;
+    k<<<grid, TWB, smem, s>>>(p);
+    ZB_LAUNCHED();
+    return ZB_OK;
+}
+
+template <int CH>
+int launch_half_dp(int half, const TileParams& p, cudaStream_t s) {
+    switch (half) {
+        case 1: return launch_tile_dp<CH, 1>(p, s);
+        case 2: return launch_tile_dp<CH, 2>(p, s);
+        case 3: return launch_tile_dp<CH, 3>(p, s);
+        case 4: return launch_tile_dp<CH, 4>(p, s);
+        case 5: return launch_tile_dp<CH, 5>(p, s);
+        case 6: return launch_tile_dp<CH, 6>(p, s);
+        case 7: return launch_tile_dp<CH, 7>(p, s);
+        case 8: return launch_tile_dp<CH, 8>(p, s);
+    }
+    return ZB_ERR_UNSUPPORTED;
+}
+
 template <int CH>
 int launch_half(int half, const TileParams& p, cudaStream_t s) {
     switch (half) {
@@ -232,6 +421,31 @@ int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, con
     p.cols = (int)src->cols;
     p.row_bytes = p.cols * channels;
     p.border = border;
+    p.src_word_ok = (((uintptr_t)p.src | p.src_pitch | (size_t)p.row_bytes) & 3u) == 0;
+    // DP variant: every tap a byte, horizontal sums within 16 bits (the vertical sums then fit 32 bits: 65535 * 255 * 17)
+    bool dp = g_tune_u8_dp.load() != 0 && half <= TU_DP_MAX_HALF && sax * 255 <= 65535;
+    for (int i = 0; i < 2 * half + 1 && dp; ++i) dp = p.kx[i] >= 0 && p.kx[i] <= 255 && p.ky[i] >= 0 && p.ky[i] <= 255;
+    if (dp) {
+        const int K = 2 * half + 1;
+        for (int m = 0; m < 8; ++m)
+            for (int i = 0; i < K; ++i) {
+                const int b = m + i * channels;          // byte of the span tap i of output m falls on
+                if (b / 4 >= 20) return ZB_ERR_UNSUPPORTED;
+                p.tw[m][b / 4] |= (uint32_t)p.kx[i] << (8 * (b % 4));
+            }
+        for (int q = 0; q <= half; ++q) {
+            const int e0 = 2 * q, e1 = 2 * q + 1, o0 = 2 * q - 1, o1 = 2 * q;
+            p.kye[q] = (uint32_t)(e0 < K ? p.ky[e0] : 0) | ((uint32_t)(e1 < K ? p.ky[e1] : 0) << 8);
+            p.kyo[q] = (uint32_t)(o0 >= 0 ? p.ky[o0] : 0) | ((uint32_t)(o1 < K ? p.ky[o1] : 0) << 8);
+        }
+        p.dst_word_ok = (((uintptr_t)p.dst | p.dst_pitch) & 3u) == 0;
+        t_last_kernel = "sep_tile_u8_dp";
+        switch (channels) {
+            case 1: return launch_half_dp<1>(half, p, s);
+            case 3: return launch_half_dp<3>(half, p, s);
+            default: return launch_half_dp<4>(half, p, s);
+        }
+    }
     t_last_kernel = "sep_tile_u8";
     switch (channels) {
         case 1: return launch_half<1>(half, p, s);

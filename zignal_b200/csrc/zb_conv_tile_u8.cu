@@ -41,6 +41,7 @@ struct TileParams {
     uint32_t kye[TU_DP_MAX_HALF + 1], kyo[TU_DP_MAX_HALF + 1];
     int dst_word_ok;               // dst base and pitch are multiples of 4: the vertical pass stores whole words
     int src_word_ok;               // src base, pitch and row length are multiples of 4: interior tiles load whole words
+    int no_clamp;                  // 255 * sum(kx) * sum(ky) + 32768 < 2^24: divClampU8 never clamps
 };
 
 // Load stage shared by both tile kernels: in[tr][tb] = source byte at row resolve(y0 + tr - HALF), byte position
@@ -54,32 +55,35 @@ __device__ __forceinline__ void tile_load(const TileParams& p, uint8_t* in, int 
         const int g0 = b0 - HALF * CH;                 // first byte of the tile row within the source row
         if (p.src_word_ok && g0 >= 0 && g0 + IW <= p.row_bytes && y0 - HALF >= 0 && y0 - HALF + IR <= p.rows) {
             constexpr int WPR = IW / 4;                // words per tile row
-            constexpr int NWORD = IR * WPR;
-            constexpr int UB = 4;
+            constexpr int UB = 4;                      // rows in flight per thread
+            // thread -> (word column tx [+ 64], rows ty, ty + 4, ...): no division, one pointer step per row
+            const int tx = t & 63, ty = t >> 6;
             const uint8_t* base = p.src + (size_t)(y0 - HALF) * p.src_pitch + g0;
-            for (int i0 = t; i0 < NWORD; i0 += UB * TWB) {
-                uint32_t lo[UB], hi[UB];
-                unsigned sh[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int idx = i0 + u * TWB;
-                    lo[u] = hi[u] = 0u;
-                    sh[u] = 0u;
-                    if (idx < NWORD) {
-                        const int tr = idx / WPR, wq = idx - tr * WPR;
-                        const uintptr_t a = (uintptr_t)(base + (size_t)tr * p.src_pitch + 4 * wq);
-                        const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-                        sh[u] = (unsigned)(a & 3u) * 8u;
-                        lo[u] = __ldg(q);
-                        if (sh[u]) hi[u] = __ldg(q + 1);
-                    }
-                }
+            for (int cq = 0; cq < (WPR + 63) / 64; ++cq) {
+                const int wq = tx + 64 * cq;
+                if (wq < WPR) {
+                    const uintptr_t a0 = (uintptr_t)(base + 4 * wq) + (size_t)ty * p.src_pitch;
+                    const unsigned sh = (unsigned)(a0 & 3u) * 8u;      // pitch is a multiple of 4: the same shift for every row
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+                    const size_t step = p.src_pitch;                    // bytes per row; 4 rows per iteration of this thread
+                    uint32_t* d = reinterpret_cast<uint32_t*>(in + ty * IW + 4 * wq);
+                    for (int tr0 = ty; tr0 < IR; tr0 += 4 * UB) {
+                        uint32_t lo[UB], hi[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int idx = i0 + u * TWB;
-                    if (idx < NWORD) {
-                        const int tr = idx / WPR, wq = idx - tr * WPR;
-                        *reinterpret_cast<uint32_t*>(in + tr * IW + 4 * wq) = __funnelshift_r(lo[u], hi[u], sh[u]);
+                        for (int u = 0; u < UB; ++u) {
+                            lo[u] = hi[u] = 0u;
+                            if (tr0 + 4 * u < IR) {
+                                const uint32_t* qq = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(q) + (size_t)(4 * u) * step);
+                                lo[u] = __ldg(qq);
+                                if (sh) hi[u] = __ldg(qq + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u)
+                            if (tr0 + 4 * u < IR) d[(4 * u) * (IW / 4)] = __funnelshift_r(lo[u], hi[u], sh);
+                        q = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(q) + (size_t)(4 * UB) * step);
+                        d += (4 * UB) * (IW / 4);
                     }
                 }
             }
@@ -306,29 +310,44 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_dp_kernel(const __grid_consta
             const int nrows = min(RPG, p.rows - y0 - r0);
             uint8_t* out = p.dst + (size_t)(y0 + r0) * p.dst_pitch + (size_t)bcol;
             const int nb = min(4, p.row_bytes - bcol);
+            // one output word: 4 byte columns of row rr; the sums start at 32768 (the rounding of divClampU8)
+            auto row_sums = [&](int rr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
+                a0 = a1 = a2 = a3 = 32768u;
 #pragma unroll
-            for (int rr = 0; rr < RPG; ++rr) {
-                if (rr < nrows) {
-                    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int q = 0; q <= HALF; ++q) {
+                    const uint4 e = E[rr / 2 + q];
+                    const uint32_t kt = (rr & 1) ? p.kyo[q] : p.kye[q];
+                    a0 = __dp2a_lo(e.x, kt, a0);
+                    a1 = __dp2a_lo(e.y, kt, a1);
+                    a2 = __dp2a_lo(e.z, kt, a2);
+                    a3 = __dp2a_lo(e.w, kt, a3);
+                }
+            };
+            if (nrows == RPG && nb == 4 && p.dst_word_ok && p.no_clamp) {
+                // whole strip, word stores, and 255 * sum(kx) * sum(ky) + 32768 < 2^24: the quotient is byte 2 of the sum as it stands
 #pragma unroll
-                    for (int q = 0; q <= HALF; ++q) {
-                        const uint4 e = E[rr / 2 + q];
-                        const uint32_t kt = (rr & 1) ? p.kyo[q] : p.kye[q];
-                        a0 = __dp2a_lo(e.x, kt, a0);
-                        a1 = __dp2a_lo(e.y, kt, a1);
-                        a2 = __dp2a_lo(e.z, kt, a2);
-                        a3 = __dp2a_lo(e.w, kt, a3);
-                    }
-                    const uint32_t q0 = min((a0 + 32768u) >> 16, 255u), q1 = min((a1 + 32768u) >> 16, 255u), q2 = min((a2 + 32768u) >> 16, 255u),
-                                   q3 = min((a3 + 32768u) >> 16, 255u);
-                    uint8_t* o = out + (size_t)rr * p.dst_pitch;
-                    if (p.dst_word_ok && nb == 4) {
-                        *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-                    } else {
-                        o[0] = (uint8_t)q0;
-                        if (nb > 1) o[1] = (uint8_t)q1;
-                        if (nb > 2) o[2] = (uint8_t)q2;
-                        if (nb > 3) o[3] = (uint8_t)q3;
+                for (int rr = 0; rr < RPG; ++rr) {
+                    uint32_t a0, a1, a2, a3;
+                    row_sums(rr, a0, a1, a2, a3);
+                    *reinterpret_cast<uint32_t*>(out + (size_t)rr * p.dst_pitch) =
+                        __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+                }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < RPG; ++rr) {
+                    if (rr < nrows) {
+                        uint32_t a0, a1, a2, a3;
+                        row_sums(rr, a0, a1, a2, a3);
+                        const uint32_t q0 = min(a0 >> 16, 255u), q1 = min(a1 >> 16, 255u), q2 = min(a2 >> 16, 255u), q3 = min(a3 >> 16, 255u);
+                        uint8_t* o = out + (size_t)rr * p.dst_pitch;
+                        if (p.dst_word_ok && nb == 4) {
+                            *reinterpret_cast<uint32_t*>(o) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                        } else {
+                            o[0] = (uint8_t)q0;
+                            if (nb > 1) o[1] = (uint8_t)q1;
+                            if (nb > 2) o[2] = (uint8_t)q2;
+                            if (nb > 3) o[3] = (uint8_t)q3;
+                        }
                     }
                 }
             }
@@ -439,6 +458,7 @@ int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, con
             p.kyo[q] = (uint32_t)(o0 >= 0 ? p.ky[o0] : 0) | ((uint32_t)(o1 < K ? p.ky[o1] : 0) << 8);
         }
         p.dst_word_ok = (((uintptr_t)p.dst | p.dst_pitch) & 3u) == 0;
+        p.no_clamp = 255 * sax * say + 32768 < (1LL << 24);
         t_last_kernel = "sep_tile_u8_dp";
         switch (channels) {
             case 1: return launch_half_dp<1>(half, p, s);

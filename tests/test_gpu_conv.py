@@ -107,6 +107,34 @@ def test_fused_rgbaf32_exact_and_fma(zb, rows, cols, border):
     L.zb_tune(b"conv.variant", -1)
 
 
+@pytest.mark.parametrize("rows,cols", [(64, 256), (96, 520), (300, 776), (40, 16), (72, 264), (513, 1032)])
+def test_fused_rgbaf32_x_border_copies(zb, rows, cols):
+    """.replicate / .mirror with cols % 8 == 0: the 8 columns either side of the image are produced by 16-byte copies inside the
+    TMA stage (host-resolved source columns) instead of the generic patch pass.  Both ways must give the same bits (15, 17 and 7
+    taps: phase-synchronous and warp-specialised kernels; fma and exact arithmetic) and match the oracle."""
+    L = zb.lib()
+    rng = np.random.default_rng(rows + cols)
+    img = rand_image(rng, (rows, cols, 4), np.float32)
+    dev = zb.Image.from_numpy(img)
+    try:
+        for border in ("mirror", "replicate"):
+            for half in (7, 8, 3):
+                k = _taps(rng, 2 * half + 1)
+                for exact in (0, 1):
+                    L.zb_set_exact_f32(exact)
+                    res = []
+                    for knob in (1, 0):
+                        L.zb_tune(b"conv.edge_fast", knob)
+                        res.append(dev.convolve_separable(k, k, border_enum(zb, border)).to_numpy())
+                        assert L.zb_last_kernel().decode().startswith("fused_sep_rgbaf32")
+                    assert np.array_equal(res[0], res[1]), (border, half, exact)
+                    want = zo.conv_separable(img, k, k, border)
+                    assert (np.array_equal(res[0], want) if exact else rel_err(res[0], want) <= TOL_F32), (border, half, exact)
+    finally:
+        L.zb_set_exact_f32(0)
+        L.zb_tune(b"conv.edge_fast", 1)
+
+
 @pytest.mark.parametrize("rows,cols", [(64, 64), (96, 520), (300, 776), (513, 1032), (40, 16), (257, 260)])
 @pytest.mark.parametrize("border", BORDERS)
 def test_fused_rgba8_bit_exact(zb, rows, cols, border):

@@ -63,6 +63,10 @@ struct FusedParams {
     int fix_left;    // 1 if x < 0 needs patching
     int fix_right;   // 1 if x >= 8*ngroups needs patching (border != zero or ragged edge)
     int tma_row_off; // row of the tensor map that holds image row 0 (sharded blocks: the map starts at the first halo row)
+    int edge_fast;   // .replicate / .mirror with cols % 8 == 0: the 8 columns left of x = 0 and right of x = cols - 1 are copies of
+                     // columns TMA delivered into the same stage; lsrc / rsrc (host-resolved) say which
+    int lsrc[8];     // stage pixel index the halo pixel x = e - 8 of the FIRST strip is copied from
+    int rsrc[8];     // image column the halo pixel x = cols + e of the last strip is copied from
 };
 
 // Sharded launch (zb_shard_conv_separable): this rank holds one row block of a taller image, stored with `halo_cap` (>= CHUNK)
@@ -108,6 +112,29 @@ __device__ __noinline__ void fixup_stage(uint32_t stage, int y0, int xs0, bool f
         const uint32_t line = (uint32_t)(rr * G + (xx >> 3));
         return stage + line * 128 + ((((uint32_t)xx & 7u) ^ (line & 7u)) << 4);
     };
+    if (fix_x && p.edge_fast) {
+        // .replicate / .mirror with cols % 8 == 0 (the usual case): the 8 columns either side of the image are 16-byte copies inside
+        // the stage from the columns the host resolved (FusedParams::lsrc / rsrc) -- 8 rows x 8 columns per side, no index
+        // arithmetic, no divisions.  It lives in this out-of-line function on purpose.  Of the 33 us the border costs per launch at
+        // 8192 x 8192 (.mirror 0.436 ms, .zero 0.403) the patch LOOP is the small part (this version: -3 us); the rest is the call and
+        // the extra barrier per chunk of an edge strip.  Both attempts to avoid them -- the same copies inlined into the chunk loop,
+        // and the owner thread of each row copying its halo pixels right before reading them (no barrier at all) -- removed 20 us of
+        // border cost and added 19-27 us to EVERY border mode: the loop's code grew by 50-100 instructions and 10-14 registers and
+        // the kernel, FP32-issue bound with 1920 FFMAs per chunk, lost more in the steady state than it won at the edges.
+        fix_x = false;
+        if (threadIdx.x < 128) {
+            const int side = threadIdx.x >> 6, rr = (threadIdx.x >> 3) & 7, e = threadIdx.x & 7;
+            const int y = y0 + rr;
+            bool row_ok = y >= 0 && y < p.rows;                  // rows beyond the image are rebuilt whole by the row pass
+            if constexpr (SHARD) row_ok = row_ok || (y < 0 && y >= nb_lo) || (y >= p.rows && y < nb_hi);   // neighbour rows are real rows
+            const bool edge = side == 0 ? xs0 < 0 : xs0 + G * 8 > p.cols;
+            if (row_ok && edge) {
+                const int s_dst = side == 0 ? e : p.cols - xs0 + e;
+                const int s_src = side == 0 ? p.lsrc[e] : p.rsrc[e] - xs0;
+                if (s_dst < G * 8) sts128(stage_addr(rr, s_dst), lds128(stage_addr(rr, s_src)));
+            }
+        }
+    }
     if (fix_x) {
         const int nleft = xs0 < 0 ? min(-xs0, G * 8) : 0;                      // entries [0, nleft) have x < 0
         const int r0 = max(0, xlimit - xs0);                                    // first entry with x >= xlimit
@@ -749,6 +776,12 @@ static int fused_prepare(const zb_image* src, zb_image* dst, const float* kx, in
     p.fix_rows = border != ZB_BORDER_ZERO;
     p.fix_left = border != ZB_BORDER_ZERO;
     p.fix_right = (border != ZB_BORDER_ZERO) || (p.cols % 8 != 0);
+    p.edge_fast = g_tune_edge_fast.load() && (border == ZB_BORDER_REPLICATE || border == ZB_BORDER_MIRROR) && p.cols % 8 == 0 && p.cols >= 16;
+    for (int e = 0; e < 8; ++e) {   // border.zig:46-63 resolveIndex for the 8 columns either side (replicate; mirror = reflect-101)
+        const int xl = e - 8, xr = p.cols + e;
+        p.lsrc[e] = 8 + (border == ZB_BORDER_REPLICATE ? 0 : -xl);
+        p.rsrc[e] = border == ZB_BORDER_REPLICATE ? p.cols - 1 : 2 * (p.cols - 1) - xr;
+    }
 
     if ((rc = encode_block_map(encode, tmap, src->data, p.ngroups, p.rows, src->stride))) return rc;
     const int n_units = p.n_strips * p.n_bands;

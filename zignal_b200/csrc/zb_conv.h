@@ -26,5 +26,7 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
 // zb_conv_tile_u8.cu: single-pass (shared-memory tile) separable convolution of any 8-bit format / alignment / border mode.
 int conv_separable_tile_u8(const zb_image* src, zb_image* dst, int channels, const float* kx, int nx, const float* ky, int ny, int border,
                            cudaStream_t s);
+// Dense kernels up to 7 x 7 on 8-bit images from shared-memory tiles (zb_conv_tile_u8.cu); ZB_ERR_UNSUPPORTED outside its envelope.
+int convolve_tile_u8(const zb_image* src, zb_image* dst, int channels, const int32_t* ki, int kh, int kw, int border, cudaStream_t s);
 
 }  // namespace zb

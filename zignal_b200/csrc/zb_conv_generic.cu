@@ -289,6 +289,10 @@ int convolve_generic(const zb_image* src_in, zb_image* dst, int pixfmt, const fl
     int64_t sa = 0;
     for (size_t i = 0; i < size; ++i) { ki[i] = (int32_t)roundf(kernel[i] * 256.0f); sa += llabs((long long)ki[i]); }  // :94-111
     const bool a32 = sa * 255 < 2147483647LL - 128;
+    if (a32 && !g_force_generic.load()) {   // kernels up to 7 x 7: shared-memory tiles, every source byte extracted once
+        rc = convolve_tile_u8(&src, dst, ch, ki, kh, kw, border, s);
+        if (rc != ZB_ERR_UNSUPPORTED) return rc;
+    }
     ZB_CUDA(cudaMemcpyAsync(taps.p, ki, size * 4, cudaMemcpyHostToDevice, s));
     const int32_t* dk = (const int32_t*)taps.p;
     t_last_kernel = "conv2d_generic_u8";

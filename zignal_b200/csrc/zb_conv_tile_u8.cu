@@ -497,6 +497,57 @@ int launch_dense_half(int half, const TileParams& p, cudaStream_t s) {
     return ZB_ERR_UNSUPPORTED;
 }
 
+// ================================================================================================
+// Image.sobel on a gray Image(u8) (edges.zig:33-73): two 3 x 3 convolutions with .replicate, magnitude sqrt(gx^2 + gy^2) / 4,
+// trunc(clamp(0, 255)).  The reference convolves in f32, but every product and partial sum is a small integer (|g| <= 1020), so
+// integer arithmetic gives the same numbers; gx^2 + gy^2 < 2^24 converts to f32 exactly and the square root, the division by 4
+// and the truncation are the reference's own f32 operations.  Byte tile as above, a thread per 8 consecutive bytes, every source
+// byte extracted once.
+// ================================================================================================
+__global__ void __launch_bounds__(TWB) sobel_tile_u8_kernel(const __grid_constant__ TileParams p) {
+    constexpr int TH = 32;
+    constexpr int IR = TH + 2;
+    constexpr int IW = (TWB + 2 + 7) & ~7;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint8_t* in = smem;
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.x * TWB;
+    const int y0 = blockIdx.y * TH;
+    tile_load<1, 1, IR, IW>(p, in, t, b0, y0);
+    __syncthreads();
+    for (int idx = t; idx < TH * (TWB / 8); idx += TWB) {
+        const int r = idx / (TWB / 8), run = idx % (TWB / 8);
+        const int bcol = b0 + 8 * run;
+        if (y0 + r >= p.rows || bcol >= p.row_bytes) continue;
+        int px[3][10];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const uint2* q = reinterpret_cast<const uint2*>(in + (r + dy) * IW + 8 * run);
+            const uint2 a = q[0], b = q[1];
+            const uint32_t w[3] = {a.x, a.y, b.x};
+#pragma unroll
+            for (int sb = 0; sb < 10; ++sb) px[dy][sb] = (int)__byte_perm(w[sb >> 2], 0u, 0x4440u | (uint32_t)(sb & 3));
+        }
+        uint32_t qv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int gx = (px[0][m + 2] - px[0][m]) + 2 * (px[1][m + 2] - px[1][m]) + (px[2][m + 2] - px[2][m]);            // edges.zig:14-18
+            const int gy = (px[2][m] + 2 * px[2][m + 1] + px[2][m + 2]) - (px[0][m] + 2 * px[0][m + 1] + px[0][m + 2]);      // :21-25
+            const float mag = __fsqrt_rn((float)(gx * gx + gy * gy));
+            qv[m] = (uint32_t)(int)fminf(__fmul_rn(mag, 0.25f), 255.0f);   // >= 0 by construction; x / 4 == x * 0.25 exactly
+        }
+        uint8_t* o = p.dst + (size_t)(y0 + r) * p.dst_pitch + (size_t)bcol;
+        const int nb = min(8, p.row_bytes - bcol);
+        if (p.dst_dword_ok && nb == 8) {
+            *reinterpret_cast<uint2*>(o) = make_uint2(qv[0] | (qv[1] << 8) | (qv[2] << 16) | (qv[3] << 24), qv[4] | (qv[5] << 8) | (qv[6] << 16) | (qv[7] << 24));
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (m < nb) o[m] = (uint8_t)qv[m];
+        }
+    }
+}
+
 }  // namespace
 
 // Returns ZB_ERR_UNSUPPORTED outside its envelope (the caller then runs the two-pass path).
@@ -599,6 +650,29 @@ int convolve_tile_u8(const zb_image* src, zb_image* dst, int channels, const int
         case 3: return launch_dense_half<3>(half, p, s);
         default: return launch_dense_half<4>(half, p, s);
     }
+}
+
+// Image.sobel of a gray Image(u8) from byte tiles; ZB_ERR_UNSUPPORTED outside its envelope (the caller keeps its per-pixel kernel).
+int sobel_tile_u8_gray(const zb_image* src, zb_image* dst, cudaStream_t s) {
+    if (images_overlap(src, dst, 1)) return ZB_ERR_UNSUPPORTED;
+    if ((uint64_t)src->cols >= (1u << 30) || src->rows >= (1u << 30)) return ZB_ERR_UNSUPPORTED;
+    TileParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const uint8_t*)src->data;
+    p.dst = (uint8_t*)dst->data;
+    p.src_pitch = (size_t)src->stride;
+    p.dst_pitch = (size_t)dst->stride;
+    p.rows = (int)src->rows;
+    p.cols = (int)src->cols;
+    p.row_bytes = p.cols;
+    p.border = ZB_BORDER_REPLICATE;
+    p.src_word_ok = (((uintptr_t)p.src | p.src_pitch | (size_t)p.row_bytes) & 3u) == 0;
+    p.dst_dword_ok = (((uintptr_t)p.dst | p.dst_pitch) & 7u) == 0;
+    dim3 grid(div_up((size_t)p.row_bytes, TWB), div_up((size_t)p.rows, 32));
+    if (grid.y > 65535u) return ZB_ERR_UNSUPPORTED;
+    sobel_tile_u8_kernel<<<grid, TWB, 34 * ((TWB + 2 + 7) & ~7), s>>>(p);
+    ZB_LAUNCHED();
+    return ZB_OK;
 }
 
 }  // namespace zb

@@ -288,9 +288,9 @@ __device__ __forceinline__ uint32_t map_colour(float rf, float gf, float bf, con
         const float n = __fsub_rn(t, 12582912.0f);
         const float d = __fsub_rn(x, n);
         bad |= !(fabsf(d) < m.safe[j]);
-        const float c = fminf(fmaxf(n, 0.0f), 255.0f);
-        const uint32_t bits = __float_as_uint(__fadd_rn(c, 8388608.0f));   // integer c in the low mantissa byte
-        out |= (bits & 0xFFu) << (8 * j);
+        // t = 1.5 * 2^23 + round(x): the integer sits in the mantissa, so clamp(round(x), 0, 255) is one subtraction and one
+        // min-with-relu (an |x| beyond 2^22 breaks this reading of t, but then d is huge and the pixel is recomputed exactly)
+        out |= (uint32_t)__vimin_s32_relu(__float_as_int(t) - 0x4B400000, 255) << (8 * j);
     }
     return out;
 }
@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img,
             }
         }
     };
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (((uintptr_t)img & 15u) == 0) {
-        const size_t n16 = n_px / 16;
+        // grid-stride: a few resident CTAs per SM walk the image (one CTA per 4096 pixels spent a third of its life being launched)
+        const size_t n16 = n_px / 16, n_threads = (size_t)gridDim.x * blockDim.x;
+        for (size_t tid = tid0; tid <= n16; tid += n_threads)
         if (tid < n16) {
             uint4* q4 = reinterpret_cast<uint4*>(img) + tid * CH;
             uint32_t w[4 * CH];
@@ -404,11 +406,12 @@ __global__ void __launch_bounds__(256) fdm_map_kernel(uint8_t* __restrict__ img,
             }
 #pragma unroll
             for (int i = 0; i < CH; ++i) q4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-        } else if (tid == n16) {   // the tail (< 16 pixels), byte by byte
+        } else {   // tid == n16: the tail (< 16 pixels), byte by byte
             for (size_t px = n16 * 16; px < n_px; ++px) map_px(img + px * CH);
         }
         return;
     }
+    const size_t tid = tid0;
     const size_t n_groups = n_px / 4;
     if (tid < n_groups) {
         uint8_t b[4 * CH];
@@ -668,7 +671,11 @@ int map_enqueue(zb_fdm* f, cudaStream_t s) {
     MapParams* dp = (MapParams*)f->d_params;
     uint8_t* img = (uint8_t*)f->source.data;
     // one thread per 16-pixel run (16-byte aligned images) or 4-pixel group, one more for the tail
-    const unsigned blocks = (((uintptr_t)img) & 15u) == 0 ? div_up(n_px / 16 + 1, 256) : div_up(n_px / 4 + 1, 256);
+    unsigned blocks = (((uintptr_t)img) & 15u) == 0 ? div_up(n_px / 16 + 1, 256) : div_up(n_px / 4 + 1, 256);
+    if ((((uintptr_t)img) & 15u) == 0) {   // the aligned path strides over the image: 8 CTAs per SM are plenty
+        DeviceInfo di;
+        if (device_info(&di) == ZB_OK && blocks > 8u * (unsigned)di.sm_count) blocks = 8u * (unsigned)di.sm_count;
+    }
     switch (channels_of(f->pixfmt)) {
         case 1: fdm_map_kernel<1><<<blocks, 256, 0, s>>>(img, n_px, dp); break;
         case 3: fdm_map_kernel<3><<<blocks, 256, 0, s>>>(img, n_px, dp); break;

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int TWB = 256;          // output bytes per tile row = threads per CTA
 constexpr int TU_MAX_HALF = 15;
+constexpr int DP_TH = 48;               // rows per tile of the dot-product variant: 48 KB of shared memory -> four CTAs per SM
 constexpr int TU_DP_MAX_HALF = 8;        // the dot-product variant: registers of the vertical window, 16 tap words per output byte
 
 struct TileParams {
@@ -249,9 +250,9 @@ int launch_tile(const TileParams& p, cudaStream_t s) {
 // Integer sums are order-independent: same bits as the reference (and as the IMAD variant above, which stays for other kernels).
 // ================================================================================================
 template <int CH, int HALF>
-__global__ void __launch_bounds__(TWB) sep_tile_u8_dp_kernel(const __grid_constant__ TileParams p) {
+__global__ void __launch_bounds__(TWB, 4) sep_tile_u8_dp_kernel(const __grid_constant__ TileParams p) {
     constexpr int K = 2 * HALF + 1;
-    constexpr int TH = 64;
+    constexpr int TH = DP_TH;
     constexpr int IR = TH + 2 * HALF;                       // even
     constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;
     constexpr int NPAIR = IR / 2;
@@ -300,11 +301,15 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_dp_kernel(const __grid_consta
     __syncthreads();
 
     {
-        constexpr int RPG = TH / 4;                       // rows per thread (16)
-        constexpr int NE = RPG / 2 + HALF;                // pairs the rows of a thread read
+        constexpr int RPT = TH / 4;                       // rows per thread (12), produced in strips of RPG rows: a strip's window of
+        constexpr int RPG = RPT / 2;                      // row pairs stays in registers (6 rows: 10 pair words x 4 columns)
+        constexpr int NE = RPG / 2 + HALF;                // pairs the rows of a strip read
+        static_assert(RPG % 2 == 0, "strips start on an even row");
         const int cg = t & 63, rg = t >> 6;
-        const int r0 = rg * RPG;
         const int bcol = b0 + 4 * cg;
+#pragma unroll 1
+        for (int strip = 0; strip < 2; ++strip) {
+        const int r0 = rg * RPT + strip * RPG;
         if (bcol < p.row_bytes && y0 + r0 < p.rows) {
             uint4 E[NE];
 #pragma unroll
@@ -354,12 +359,13 @@ __global__ void __launch_bounds__(TWB) sep_tile_u8_dp_kernel(const __grid_consta
                 }
             }
         }
+        }
     }
 }
 
 template <int CH, int HALF>
 int launch_tile_dp(const TileParams& p, cudaStream_t s) {
-    constexpr int TH = 64;
+    constexpr int TH = DP_TH;
     constexpr int IR = TH + 2 * HALF;
     constexpr int IW = (TWB + 2 * HALF * CH + 7) & ~7;
     constexpr int smem = (IR / 2) * TWB * (int)sizeof(uint32_t) + IR * IW;

@@ -53,6 +53,8 @@ struct U8Params {
     float kxf[MAXK];  // the same Q8 taps as floats (FMATH variant)
     float kyf[MAXK];  // ky_q8 / 65536: the vertical sums come out as acc / 65536 (exact), ready for round_clamp_byte
     unsigned kx4[5];  // DP variant: horizontal taps packed four bytes per word (tap 4q + b in byte b), zero beyond the kernel
+    unsigned kxs[4][5];  // the same taps delayed by sh = 0..3 bytes (tap 4q + b - sh in byte b): a window that starts sh bytes into a
+                         // word meets ALIGNED words with shifted taps instead of being funnel-shifted into place
     unsigned ky4[5];  // DP variant: vertical taps likewise; dp2a.lo reads bytes 0,1 (taps 4q, 4q+1), dp2a.hi bytes 2,3
     const uint32_t* src;
     uint32_t* dst;
@@ -324,8 +326,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_sep_rgba8_kernel(const __gr
 // DP variant: the same single-pass structure on the integer dot-product instructions.
 // When every Q8 tap is a byte (0 .. 255: every kernel with non-negative taps -- Gaussian, box, motion blur) and the horizontal
 // sums fit 16 bits (255 * sum(kx) <= 65535), the reference's integer arithmetic maps onto
-//   horizontal  dp4a: the 4 pixels of a group are byte-transposed into one word per channel, a window of 4 consecutive
-//               bytes at any offset is one funnel shift, and 4 taps are ONE instruction (15 taps: 4 dp4a instead of 15 FMAs);
+//   horizontal  dp4a: the 4 pixels of a group are byte-transposed into one word per channel and 4 taps are ONE instruction; a window
+//               that starts sh bytes into a word is not shifted into place -- it meets the aligned words with taps delayed by
+//               sh bytes (15 taps: 4 or 5 dp4a instead of 15 FMAs);
 //   vertical    dp2a: the horizontal sums of two consecutive rows share a register (lo / hi 16 bits) and 2 taps are one
 //               instruction (15 taps: 8 dp2a); the pair registers for odd rows are one PRMT from the even ones.
 // The ring holds u16 sums (8 B per pixel instead of 16), so two CTAs fit an SM.  Integer sums are order-independent: the results
@@ -437,10 +440,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fused_sep_rgba8_dp_kernel(const _
                         const int sh = start & 3, j0 = start >> 2;
                         uint32_t acc = 0;
 #pragma unroll
-                        for (int q = 0; q < NW; ++q) {
-                            const uint32_t win = sh == 0 ? P[c][j0 + q] : __funnelshift_r(P[c][j0 + q], P[c][j0 + q + 1], 8 * sh);
-                            acc = __dp4a(win, p.kx4[q], acc);
-                        }
+                        for (int q = 0; q < (K + sh + 3) / 4; ++q) acc = __dp4a(P[c][j0 + q], p.kxs[sh][q], acc);   // the taps move, not the pixels
                         hsum[c][o] = acc;   // <= 255 * sum(kx) <= 65535
                     }
                 }
@@ -604,6 +604,14 @@ int conv_separable_fused_rgba8(const zb_image* src, zb_image* dst, const float* 
                 if (t < MAXK) { p.kx4[q] |= (unsigned)p.kx[t] << (8 * b); p.ky4[q] |= (unsigned)p.ky[t] << (8 * b); }
             }
         }
+        for (int sh = 0; sh < 4; ++sh)
+            for (int q = 0; q < 5; ++q) {
+                p.kxs[sh][q] = 0;
+                for (int b = 0; b < 4; ++b) {
+                    const int t = 4 * q + b - sh;
+                    if (t >= 0 && t < MAXK) p.kxs[sh][q] |= (unsigned)p.kx[t] << (8 * b);
+                }
+            }
         t_last_kernel = "fused_sep_rgba8_dp";
         switch (half) {
             case 1: return launch_u8_dp<1>(tmap, p, n_units, di.sm_count, s);

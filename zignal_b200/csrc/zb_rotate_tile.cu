@@ -195,11 +195,8 @@ int rotate_tile_rgba8(const zb_image* src, unsigned long long spitch, zb_image* 
     // (A persistent variant with two tile buffers and TMA prefetch of the next tile was measured slower: 1.11 ms against 0.94 ms
     // for 128 frames -- the per-tile bookkeeping of 512 threads costs more issue slots than the hidden load latency returns.)
     const uint32_t smem = p.tile_bytes + RT_SMEM_EXTRA;   // < 48 KB: no size attribute needed
-    static bool carveout_set = false;   // five 40 KB tiles per SM need the largest shared-memory carveout; the default heuristic stops at four
-    if (!carveout_set) {
-        cudaFuncSetAttribute(rotate_tile_rgba8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
+    // five 40 KB tiles per SM need the largest shared-memory carveout (a per-device hint; setting it is cheap)
+    cudaFuncSetAttribute(rotate_tile_rgba8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const dim3 grid(div_up(dst->cols, RT_T), div_up(dst->rows, RT_T), n);
     rotate_tile_rgba8_kernel<<<grid, RT_THREADS, smem, s>>>(tmap, p);
     t_last_kernel = "rotate_tile_rgba8";

@@ -396,7 +396,7 @@ int zb_set_force_generic(int on);
 /* Kernel tuning knobs for experiments ("conv.stages" 2|3, "conv.f32x2" 0|1, "conv.band_rows" >= 64,
  * "conv.variant" -1 auto | 0 phase-synchronous | 1 warp-specialised, "conv.u8_fmath" 0|1,
  * "host.band_rows": rows per PCIe band of the pipelined host-pointer path, 0 = stage the whole image,
- * "conv.u8_dp" 0|1, "conv.edge_fast" 0|1 (x borders of .replicate / .mirror as in-stage copies), "sobel.tile" 0|1, "rotate.tile" 0 gather kernel |
+ * "conv.u8_dp" 0|1, "conv.edge_fast" 0|1 (x borders of .replicate / .mirror as in-stage copies), "sobel.tile" 0|1, "jacobi.cluster" 0|1 (SVD inside one cluster's shared memory when it fits), "rotate.tile" 0 gather kernel |
  * 1 shared-memory tile kernel where it applies). */
 int zb_tune(const char* key, int value);
 /* Name of the kernel variant the last zb_conv_separable call selected on this thread. */

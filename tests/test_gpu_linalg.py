@@ -28,9 +28,21 @@ def test_svd_device_kernel_vs_oracle(zb, dtype, shape, mode):
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])
     a = (rng.standard_normal(shape) @ np.diag(np.logspace(0, -3, shape[1]))).astype(dtype)    # graded spectrum
     u, s, v, conv = _svd_prod(a, mode, True)
-    assert conv == 0 and zb.lib().zb_last_kernel().decode() == "jacobi_svd_onesided"
+    # from 32 columns on, a problem that fits one cluster's shared memory runs there (hardware cluster barrier per round)
+    assert conv == 0 and zb.lib().zb_last_kernel().decode() == ("jacobi_svd_cluster" if shape[1] >= 32 else "jacobi_svd_onesided")
     assert zb.lib().zb_last_sweeps() <= 20, zb.lib().zb_last_sweeps()          # quadratic convergence, not the sweep limit
     _check_svd_against_oracle(a, u, s, v, mode)
+    if shape[1] >= 32 and mode == "skinny_u":   # the cooperative kernel (global-memory barrier) runs the same arithmetic in the same order
+        zb.lib().zb_tune(b"jacobi.cluster", 0)
+        try:
+            u2, s2, v2, conv2 = _svd_prod(a, mode, True)
+            assert conv2 == 0 and zb.lib().zb_last_kernel().decode() == "jacobi_svd_onesided"
+        finally:
+            zb.lib().zb_tune(b"jacobi.cluster", 1)
+        if shape[0] <= 2048:     # both are warp-per-pair kernels: bit for bit
+            assert np.array_equal(s, s2) and np.array_equal(v, v2) and np.array_equal(u, u2)
+        else:                    # the cooperative path takes a CTA per pair there (another summation order)
+            assert np.allclose(s, s2, rtol=0, atol=64 * np.finfo(dtype).eps * s[0])
 
 
 def test_svd_rank_deficient_and_clustered(zb):

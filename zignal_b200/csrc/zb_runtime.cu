@@ -22,6 +22,7 @@ std::atomic<int> g_tune_u8_dp{1};
 std::atomic<int> g_tune_rotate_tile{1};
 std::atomic<int> g_tune_edge_fast{1};
 std::atomic<int> g_tune_sobel_tile{1};
+std::atomic<int> g_tune_jacobi_cluster{1};
 
 int set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
     snprintf(t_last_error, sizeof(t_last_error), "%s: %s (%s:%d)", cudaGetErrorName(e), what, file, line);
@@ -122,6 +123,7 @@ int zb_tune(const char* key, int value) {
     if (!strcmp(key, "conv.u8_dp")) { g_tune_u8_dp.store(value ? 1 : 0); return ZB_OK; }
     if (!strcmp(key, "conv.edge_fast")) { g_tune_edge_fast.store(value ? 1 : 0); return ZB_OK; }
     if (!strcmp(key, "sobel.tile")) { g_tune_sobel_tile.store(value ? 1 : 0); return ZB_OK; }
+    if (!strcmp(key, "jacobi.cluster")) { g_tune_jacobi_cluster.store(value ? 1 : 0); return ZB_OK; }
     if (!strcmp(key, "rotate.tile")) { g_tune_rotate_tile.store(value ? 1 : 0); return ZB_OK; }
     if (!strcmp(key, "host.band_rows")) { if (value < 0) return ZB_ERR_INVALID_ARGUMENT; g_tune_host_band_rows.store(value); return ZB_OK; }
     if (!strcmp(key, "conv.band_rows")) { if (value < 64) return ZB_ERR_INVALID_ARGUMENT; g_tune_band_rows.store(value); return ZB_OK; }

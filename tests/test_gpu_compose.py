@@ -147,15 +147,15 @@ def test_letterbox(zb, src_shape, dst_shape, method):
 
 
 @pytest.mark.parametrize("shape,dtype", [((37, 45), np.uint8), ((40, 33, 3), np.uint8), ((29, 31, 4), np.uint8), ((35, 36), np.float32), ((1, 7), np.uint8),
-                                         ((300, 1000), np.uint8), ((130, 777), np.uint8)])
+                                         ((300, 1000), np.uint8), ((130, 777), np.uint8), ((140, 530, 3), np.uint8), ((97, 600, 4), np.uint8)])
 def test_sobel(zb, shape, dtype):
     rng = np.random.default_rng(shape[0])
     img = rand_image(rng, shape, dtype)
     if dtype == np.float32:
         img = (img * 255.0).astype(np.float32)     # float scalars pass through un-normalised (edges.zig:38-48)
     got = zb.Image.from_numpy(img).sobel().to_numpy()
-    gray8 = dtype == np.uint8 and len(shape) == 2
-    assert zb.lib().zb_last_kernel().decode() == ("sobel_tile_u8" if gray8 else "sobel_fused")   # gray bytes: the byte-tile kernel
+    gray8 = dtype == np.uint8            # every 8-bit input (gray, Rgb, Rgba: luma inside the loader) takes the byte-tile kernel
+    assert zb.lib().zb_last_kernel().decode() == ("sobel_tile_u8" if gray8 else "sobel_fused")
     assert np.array_equal(got, zo.sobel(img))
     if gray8:
         zb.lib().zb_tune(b"sobel.tile", 0)

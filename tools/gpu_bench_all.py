@@ -64,9 +64,9 @@ for shp, name in (((8192, 8192, 3), "RGB u8"), ((8192, 8192), "gray u8")):
     x = torch.randint(0, 256, shp, device="cuda", dtype=torch.uint8, generator=g)
     s, d = Image.from_tensor(x), Image.from_tensor(torch.empty_like(x))
     rec(f"gaussian 15x15 8192^2 {name}", time_it(lambda: s.gaussian_blur(2.25, out=d), n=5, warm=1), 2 * x.numel(), 8192 * 8192)
-    if len(shp) == 2:
-        e = Image.from_tensor(torch.empty_like(x))
-        rec("sobel 8192^2 gray u8", time_it(lambda: s.sobel(out=e), n=5, warm=1), 2 * x.numel(), 8192 * 8192, "luma plane + two 3x3 f32 convolutions + magnitude")
+    e = Image.from_tensor(torch.empty((8192, 8192), device="cuda", dtype=torch.uint8))
+    rec(f"sobel 8192^2 {name}", time_it(lambda: s.sobel(out=e), n=5, warm=1), x.numel() + 8192 * 8192, 8192 * 8192, "byte tiles: luma on the way in, integer gradients, f32 magnitude")
+    del e
     del x, s, d
 # C3
 x = torch.randint(0, 256, (16384, 16384, 3), device="cuda", dtype=torch.uint8, generator=g)

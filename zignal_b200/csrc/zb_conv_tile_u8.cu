@@ -510,6 +510,9 @@ int launch_dense_half(int half, const TileParams& p, cudaStream_t s) {
 // and the truncation are the reference's own f32 operations.  Byte tile as above, a thread per 8 consecutive bytes, every source
 // byte extracted once.
 // ================================================================================================
+// CH = 3 / 4 (Rgb / Rgba input): the loader converts to luma on the way in -- convertColor(u8, px), color.zig:1031-1041:
+// (13933 r + 46871 g + 4732 b + 32768) >> 16 -- with the .replicate rule applied to the pixel; the gradient code is the gray one.
+template <int CH>
 __global__ void __launch_bounds__(TWB) sobel_tile_u8_kernel(const __grid_constant__ TileParams p) {
     constexpr int TH = 32;
     constexpr int IR = TH + 2;
@@ -517,9 +520,19 @@ __global__ void __launch_bounds__(TWB) sobel_tile_u8_kernel(const __grid_constan
     extern __shared__ __align__(16) unsigned char smem[];
     uint8_t* in = smem;
     const int t = threadIdx.x;
-    const int b0 = blockIdx.x * TWB;
+    const int b0 = blockIdx.x * TWB;                 // first output column of the tile (gray bytes == pixels)
     const int y0 = blockIdx.y * TH;
-    tile_load<1, 1, IR, IW>(p, in, t, b0, y0);
+    if constexpr (CH == 1) {
+        tile_load<1, 1, IR, IW>(p, in, t, b0, y0);
+    } else {
+        for (int idx = t; idx < IR * IW; idx += TWB) {
+            const int tr = idx / IW, tb = idx - tr * IW;
+            const int y = min(max(y0 + tr - 1, 0), p.rows - 1), x = min(max(b0 + tb - 1, 0), p.cols - 1);   // .replicate
+            const uint8_t* q = p.src + (size_t)y * p.src_pitch + (size_t)x * CH;
+            const int v = (13933 * (int)q[0] + 46871 * (int)q[1] + 4732 * (int)q[2] + 32768) >> 16;
+            in[idx] = (uint8_t)min(max(v, 0), 255);
+        }
+    }
     __syncthreads();
     for (int idx = t; idx < TH * (TWB / 8); idx += TWB) {
         const int r = idx / (TWB / 8), run = idx % (TWB / 8);
@@ -658,25 +671,36 @@ int convolve_tile_u8(const zb_image* src, zb_image* dst, int channels, const int
     }
 }
 
-// Image.sobel of a gray Image(u8) from byte tiles; ZB_ERR_UNSUPPORTED outside its envelope (the caller keeps its per-pixel kernel).
-int sobel_tile_u8_gray(const zb_image* src, zb_image* dst, cudaStream_t s) {
-    if (images_overlap(src, dst, 1)) return ZB_ERR_UNSUPPORTED;
+// Image.sobel of an 8-bit image (gray, Rgb, Rgba) into a gray Image(u8) from byte tiles; ZB_ERR_UNSUPPORTED outside its envelope (the
+// caller keeps its per-pixel kernel).
+int sobel_tile_u8(const zb_image* src, zb_image* dst, int channels, cudaStream_t s) {
+    if (channels != 1 && channels != 3 && channels != 4) return ZB_ERR_UNSUPPORTED;
+    {   // src and dst have different pixel sizes: compare the byte ranges by hand
+        const uintptr_t a0 = (uintptr_t)src->data, a1 = a0 + ((size_t)(src->rows - 1) * src->stride + src->cols) * channels;
+        const uintptr_t b0 = (uintptr_t)dst->data, b1 = b0 + ((size_t)(dst->rows - 1) * dst->stride + dst->cols);
+        if (a0 < b1 && b0 < a1) return ZB_ERR_UNSUPPORTED;
+    }
     if ((uint64_t)src->cols >= (1u << 30) || src->rows >= (1u << 30)) return ZB_ERR_UNSUPPORTED;
     TileParams p;
     memset(&p, 0, sizeof(p));
     p.src = (const uint8_t*)src->data;
     p.dst = (uint8_t*)dst->data;
-    p.src_pitch = (size_t)src->stride;
+    p.src_pitch = (size_t)src->stride * channels;
     p.dst_pitch = (size_t)dst->stride;
     p.rows = (int)src->rows;
     p.cols = (int)src->cols;
-    p.row_bytes = p.cols;
+    p.row_bytes = p.cols;                      // of the gray tile and of the destination
     p.border = ZB_BORDER_REPLICATE;
-    p.src_word_ok = (((uintptr_t)p.src | p.src_pitch | (size_t)p.row_bytes) & 3u) == 0;
+    p.src_word_ok = channels == 1 && (((uintptr_t)p.src | p.src_pitch | (size_t)p.row_bytes) & 3u) == 0;
     p.dst_dword_ok = (((uintptr_t)p.dst | p.dst_pitch) & 7u) == 0;
     dim3 grid(div_up((size_t)p.row_bytes, TWB), div_up((size_t)p.rows, 32));
     if (grid.y > 65535u) return ZB_ERR_UNSUPPORTED;
-    sobel_tile_u8_kernel<<<grid, TWB, 34 * ((TWB + 2 + 7) & ~7), s>>>(p);
+    const int smem = 34 * ((TWB + 2 + 7) & ~7);
+    switch (channels) {
+        case 1: sobel_tile_u8_kernel<1><<<grid, TWB, smem, s>>>(p); break;
+        case 3: sobel_tile_u8_kernel<3><<<grid, TWB, smem, s>>>(p); break;
+        default: sobel_tile_u8_kernel<4><<<grid, TWB, smem, s>>>(p); break;
+    }
     ZB_LAUNCHED();
     return ZB_OK;
 }

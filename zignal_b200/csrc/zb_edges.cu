@@ -269,8 +269,8 @@ extern "C" int zb_sobel(const zb_image* src, zb_image* dst, int pixfmt, zb_strea
     if (rc) return rc;
     const int rows = (int)src->rows, cols = (int)src->cols;
     if (!g_force_generic.load()) {   // one pass; the composition below stays as the cross-check (zb_set_force_generic)
-        if (pixfmt == ZB_PIX_U8 && g_tune_sobel_tile.load()) {   // gray bytes: shared-memory byte tiles, integer gradients (zb_conv_tile_u8.cu)
-            rc = sobel_tile_u8_gray(src, dst, s);
+        if (pixfmt != ZB_PIX_F32 && g_tune_sobel_tile.load()) {   // 8-bit input: shared-memory byte tiles (luma on the way in), integer gradients (zb_conv_tile_u8.cu)
+            rc = sobel_tile_u8(src, dst, channels_of(pixfmt), s);
             if (rc != ZB_ERR_UNSUPPORTED) {
                 if (rc == ZB_OK) t_last_kernel = "sobel_tile_u8";
                 return rc;

@@ -3,11 +3,12 @@
 // interpolation.zig:313-368 (bilinear: out-of-range neighbours are zero pixels under .zero, integer lerp with
 // fx = @round(frac * 256) and +32768 rounding).
 //
-// The gather kernel of zb_warp.cu spends ~100 instructions per interior pixel, most of them on 64-bit addressing, edge tests and
+// The gather kernel of zb_warp.cu spends ~130 instructions per interior pixel, most of them on 64-bit addressing, edge tests and
 // four scattered global loads.  Here a CTA owns a 64 x 64 destination tile:
 //   * the source coordinates are monotone in the column and in the row (every step of the formula is a monotone f32 operation), so
 //     the four corners of the tile bound the source footprint exactly; TMA loads that bounding box (<= 95 x 92 pixels for any
-//     angle) into shared memory as 16-row boxes of a {cols, rows, frames} tensor map.  TMA fills what lies outside the image with
+//     angle; the start column rounded down to a 16-byte boundary, which TMA insists on) into shared memory as 8-row boxes of a
+//     {cols, rows, frames} tensor map.  TMA fills what lies outside the image with
 //     zeros, which IS the `.zero` border: no edge test per sample, and a tile whose footprint misses the image is only zero stores;
 //   * floor(x) and @round(256 * frac(x)) come out of ONE magic-number add per axis: round-half-up(256 x) = floor(256 x + 1/2)
 //     = 256 * floor(x) + fx with fx = 256 carried into the integer part (left + 1 with weight 0 is the same sample as left with

@@ -32,6 +32,14 @@ elif cfg in ("boxblur", "sharpen", "gauss8", "conv3"):
     k3 = np.full((3, 3), 1 / 9, np.float32)
     fn = {"boxblur": lambda: s.box_blur(3, out=d), "sharpen": lambda: s.sharpen(3, out=d), "gauss8": lambda: s.gaussian_blur(2.25, out=d),
           "conv3": lambda: s.convolve(k3, BorderMode.MIRROR, out=d)}[cfg]
+elif cfg == "sobelgray":
+    x = torch.randint(0, 256, (8192, 8192), device="cuda", dtype=torch.uint8, generator=g)
+    s, d = Image.from_tensor(x), Image.from_tensor(torch.empty_like(x))
+    fn = lambda: s.sobel(out=d)
+elif cfg == "svd256":
+    xr = torch.randn(4096, 256, device="cuda", generator=g)
+    cov = (xr.T @ xr / 4095).contiguous()
+    fn = lambda: matrix.svd_device(cov.clone(), True, False)
 elif cfg in ("gaussgray", "gaussrgb"):
     shape = (8192, 8192) if cfg == "gaussgray" else (8192, 8192, 3)
     x = torch.randint(0, 256, shape, device="cuda", dtype=torch.uint8, generator=g)

@@ -59,10 +59,25 @@ template <typename T>
 ZJ_HD bool hestenes_rotation(double alpha, double beta, double gamma, double tol, double abs_floor, T& c, T& s) {
     // orthogonal to working precision, or both columns are rounding noise of a rank-deficient matrix (|gamma| at the level of
     // (eps |A|)^2: rotating noise against noise would never settle)
-    if (gamma == 0.0 || fabs(gamma) <= tol * sqrt(alpha * beta) || fabs(gamma) <= abs_floor) return false;
-    const double zeta = (beta - alpha) / (2.0 * gamma);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    if (gamma == 0.0 || fabs(gamma) <= abs_floor) return false;
+    // On the device a pair is one dependency chain and the f64 divisions and square roots are most of it (ncu: ~535 instructions per
+    // pair and round with the textbook form zeta = (beta - alpha) / 2 gamma, t = sgn / (|zeta| + sqrt(1 + zeta^2)), c = 1 / sqrt(1 + t^2)
+    // and a square root in the test: three of each).  The same rotation with one division and two square roots:
+    //   t = 2 gamma sgn(d) / (|d| + sqrt(d^2 + 4 gamma^2)),  d = beta - alpha   (a sum of positives: no cancellation)
+    //   c = rsqrt(1 + t^2)
+    // and, for f32 data (whose squared sums stay far inside the f64 range), the test on squares.
+    if (sizeof(T) == 4) {
+        if (gamma * gamma <= tol * tol * alpha * beta) return false;
+    } else if (fabs(gamma) <= tol * sqrt(alpha * beta)) {
+        return false;
+    }
+    const double d = beta - alpha;
+    const double t = (d >= 0.0 ? 2.0 : -2.0) * gamma / (fabs(d) + sqrt(d * d + 4.0 * gamma * gamma));
+#ifdef __CUDA_ARCH__
+    const double cc = rsqrt(1.0 + t * t);
+#else
     const double cc = 1.0 / sqrt(1.0 + t * t);
+#endif
     c = (T)cc;
     s = (T)(cc * t);
     return true;
